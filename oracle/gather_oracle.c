@@ -1,0 +1,234 @@
+/*
+ * gather_oracle.c -- CPU oracle, sample-gather half.  TEST INFRASTRUCTURE ONLY (see oracle.h).
+ *
+ * Restates the reference's gather (brdfdata.cpp:629-681 pixel<->face map, :945-960 radiance fetch,
+ * :799-943 per-sample cosines, :314-330 face normals, :130-147 ambient subtraction, :683-756 LED
+ * table).  The projection is the Tsai .cal camera (the literal GL path of the
+ * reference cannot land a single centroid inside the photographs).
+ *
+ * PARITY UNPINNED at this boundary: the reference C++ needs OpenCV/Eigen/libigl/GL and cannot be
+ * built here, and it ships no test for these functions, so this file DEFINES the arithmetic the
+ * CUDA gather must reproduce bit-for-bit:
+ *   - every operation is a single IEEE-754 double +,-,*,/ or sqrt, never fused (-ffp-contract=off);
+ *   - 3-term sums/dots associate left to right: (a0*b0 + a1*b1) + a2*b2;
+ *   - centroid = (((0 + v0) + v1) + v2) / 3.0  per component (brdfdata.cpp:653-660);
+ *   - normalisation divides each component by sqrt((x*x + y*y) + z*z) when that is > 0;
+ *   - double -> int conversion truncates (brdfdata.cpp:677).
+ */
+#include <math.h>
+#include <stddef.h>
+#include <stdlib.h>
+
+#include "oracle.h"
+
+enum { CAM_CX = 0, CAM_CY, CAM_F, CAM_SX, CAM_N = 4, CAM_O = 7, CAM_A = 10, CAM_P = 13 };
+
+static double dot3(const double *a, const double *b) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
+
+static void normalize3(double *v)
+{
+    const double z = (v[0] * v[0] + v[1] * v[1]) + v[2] * v[2];
+    if (z > 0.0) {
+        const double r = sqrt(z);
+        v[0] /= r; v[1] /= r; v[2] /= r;
+    }
+}
+
+static void centroid(const double *V, const int *F, int face, double *c)
+{
+    int j, k;
+    for (k = 0; k < 3; ++k) {
+        double s = 0.0;
+        for (j = 0; j < 3; ++j) s += V[(size_t)F[(size_t)face * 3 + j] * 3 + k];
+        c[k] = s / 3.0;
+    }
+}
+
+/* brdfdata.cpp:695-755: 4x4 serpentine grid, x fixed */
+void oracle_led_table(double *led)
+{
+    const double x = 303.5, min_y = -157.1, max_y = -2.3, min_z = 555.3, max_z = 645.8;
+    const double y_step = (max_y - min_y) / 3, z_step = (max_z - min_z) / 3;
+    const double ys[4] = {max_y, max_y - y_step, min_y + y_step, min_y};
+    const double zs[4] = {min_z, min_z + z_step, max_z - z_step, max_z};
+    int i;
+    for (i = 0; i < 16; ++i) {
+        const int row = i / 4, col = i % 4;
+        led[i * 3 + 0] = x;
+        led[i * 3 + 1] = (row % 2 == 0) ? ys[col] : ys[3 - col];
+        led[i * 3 + 2] = zs[row];
+    }
+}
+
+/* brdfdata.cpp:314-330 */
+void oracle_face_normals(const double *V, const int *F, int nF, double *FN)
+{
+    int i, k;
+    for (i = 0; i < nF; ++i) {
+        const double *v0 = V + (size_t)F[(size_t)i * 3 + 0] * 3;
+        const double *v1 = V + (size_t)F[(size_t)i * 3 + 1] * 3;
+        const double *v2 = V + (size_t)F[(size_t)i * 3 + 2] * 3;
+        double e1[3], e2[3], nrm[3];
+        for (k = 0; k < 3; ++k) { e1[k] = v1[k] - v0[k]; e2[k] = v2[k] - v0[k]; }
+        nrm[0] = e1[1] * e2[2] - e1[2] * e2[1];
+        nrm[1] = e1[2] * e2[0] - e1[0] * e2[2];
+        nrm[2] = e1[0] * e2[1] - e1[1] * e2[0];
+        normalize3(nrm);
+        for (k = 0; k < 3; ++k) FN[(size_t)i * 3 + k] = nrm[k];
+    }
+}
+
+/* brdfdata.cpp:140-146: img = sat_u8(sat_u8(img - dark) - dark), the dark frame goes twice */
+void oracle_subtract_ambient(unsigned char *img, const unsigned char *dark, long nbytes)
+{
+    long i;
+    for (i = 0; i < nbytes; ++i) {
+        int v = (int)img[i] - (int)dark[i];
+        if (v < 0) v = 0;
+        v -= (int)dark[i];
+        if (v < 0) v = 0;
+        img[i] = (unsigned char)v;
+    }
+}
+
+/* Tsai pin-hole projection of a world point (kappa1 ignored: the reference never parses it,
+ * brdfdata.cpp:195-247).  Returns 1 and the pixel when the point is in front of the camera and
+ * inside the W x H image; image rows run top-down. */
+static int project_tsai(const double *c, const double *cam, int W, int H, int *col, int *row)
+{
+    double d[3], xc, yc, zc, u, v;
+    d[0] = c[0] - cam[CAM_P + 0];
+    d[1] = c[1] - cam[CAM_P + 1];
+    d[2] = c[2] - cam[CAM_P + 2];
+    xc = dot3(d, cam + CAM_N);
+    yc = dot3(d, cam + CAM_O);
+    zc = dot3(d, cam + CAM_A);
+    if (!(zc > 0.0)) return 0;
+    u = cam[CAM_CX] + ((cam[CAM_SX] * cam[CAM_F]) * xc) / zc;
+    v = cam[CAM_CY] + (cam[CAM_F] * yc) / zc;
+    if (!(u >= 0.0 && v >= 0.0 && u < (double)W && v < (double)H)) return 0;
+    *col = (int)u;
+    *row = (int)v;
+    return 1;
+}
+
+/* brdfdata.cpp:629-681: faces in index order, last writer wins, map starts at -1.
+ * Returns the number of faces that landed inside the image. */
+int oracle_calc_pixel2surface(const double *V, const int *F, int nF, const double *cam,
+                              int W, int H, int *map)
+{
+    int i, hits = 0;
+    for (i = 0; i < W * H; ++i) map[i] = -1;
+    for (i = 0; i < nF; ++i) {
+        double c[3];
+        int col, row;
+        centroid(V, F, i, c);
+        if (project_tsai(c, cam, W, H, &col, &row)) {
+            map[row * W + col] = i;
+            ++hits;
+        }
+    }
+    return hits;
+}
+
+/* brdfdata.cpp:857-899: cos(phi) = N . normalize(L_k - C) */
+void oracle_cos_ln(const double *V, const int *F, const double *FN, const double *led, int nled,
+                   int face, double *phi)
+{
+    int k;
+    for (k = 0; k < nled; ++k) {
+        double c[3], l[3];
+        centroid(V, F, face, c);
+        l[0] = led[k * 3 + 0] - c[0];
+        l[1] = led[k * 3 + 1] - c[1];
+        l[2] = led[k * 3 + 2] - c[2];
+        normalize3(l);
+        phi[k] = dot3(l, FN + (size_t)face * 3);
+    }
+}
+
+/* brdfdata.cpp:902-943: cos(theta') = N . normalize(L_k - 2C + P_cam) */
+void oracle_cos_nh(const double *V, const int *F, const double *FN, const double *led, int nled,
+                   const double *cam, int face, double *thetaDash)
+{
+    int k;
+    for (k = 0; k < nled; ++k) {
+        double c[3], h[3];
+        centroid(V, F, face, c);
+        h[0] = led[k * 3 + 0] - 2 * c[0] + cam[CAM_P + 0];
+        h[1] = led[k * 3 + 1] - 2 * c[1] + cam[CAM_P + 1];
+        h[2] = led[k * 3 + 2] - 2 * c[2] + cam[CAM_P + 2];
+        normalize3(h);
+        thetaDash[k] = dot3(h, FN + (size_t)face * 3);
+    }
+}
+
+/* brdfdata.cpp:799-855, reproduced literally including its two slips: the light
+ * direction uses the centroid's x for all three components (:835) and the result is R.P, not R.V
+ * (:849).  Only the Phong model (modelInfo 0) consumes it. */
+void oracle_cos_rv(const double *V, const int *F, const double *FN, const double *led, int nled,
+                   const double *cam, int face, double *theta)
+{
+    int k, a;
+    (void)cam;
+    for (k = 0; k < nled; ++k) {
+        const double *N = FN + (size_t)face * 3;
+        double c[3], l[3], P[3], R[3], s;
+        centroid(V, F, face, c);
+        l[0] = c[0] - led[k * 3 + 0];
+        l[1] = c[0] - led[k * 3 + 1];
+        l[2] = c[0] - led[k * 3 + 2];
+        normalize3(l);
+        s = dot3(N, l);
+        for (a = 0; a < 3; ++a) P[a] = s * N[a];
+        for (a = 0; a < 3; ++a) R[a] = l[a] - 2 * P[a];
+        theta[k] = dot3(R, P);
+    }
+}
+
+/* brdfdata.cpp:945-960 with the image row given directly (top-down; the GL flip H-1-y of :955
+ * belongs to the literal GL projection, not to the Tsai one). BGR interleaved u8. */
+void oracle_intensities_from_pixel(const unsigned char *const *images, int nimg, int W, int H,
+                                   int x, int row, int channel, double *I)
+{
+    int k;
+    (void)H;
+    for (k = 0; k < nimg; ++k)
+        I[k] = images[k][((size_t)row * W + x) * 3 + channel] / 255.0;
+}
+
+/* One camera, whole gather: map, then for every face that still owns its pixel (ascending face id)
+ * the 3 x nimg cosines and the 3 x nimg intensities.  Sample s = fit*nimg + k.  `I` holds the three
+ * BGR channels back to back with a channel stride of nF*nimg doubles. */
+int oracle_gather(const double *V, const int *F, int nF, const double *cam, const double *led,
+                  const unsigned char *const *images, int nimg, int W, int H,
+                  int *map, int *fit_face, int *fit_pixel,
+                  double *phi, double *thetaDash, double *theta, double *I)
+{
+    double *FN;
+    int i, ch, nfit = 0;
+
+    FN = (double *)malloc((size_t)nF * 3 * sizeof(double));
+    if (!FN) return -1;
+    oracle_face_normals(V, F, nF, FN);
+    oracle_calc_pixel2surface(V, F, nF, cam, W, H, map);
+
+    for (i = 0; i < nF; ++i) {
+        double c[3];
+        int col, row;
+        centroid(V, F, i, c);
+        if (!project_tsai(c, cam, W, H, &col, &row)) continue;
+        if (map[row * W + col] != i) continue; /* a later face overwrote this pixel */
+        fit_face[nfit] = i;
+        fit_pixel[nfit] = row * W + col;
+        oracle_cos_ln(V, F, FN, led, nimg, i, phi + (size_t)nfit * nimg);
+        oracle_cos_nh(V, F, FN, led, nimg, cam, i, thetaDash + (size_t)nfit * nimg);
+        oracle_cos_rv(V, F, FN, led, nimg, cam, i, theta + (size_t)nfit * nimg);
+        for (ch = 0; ch < 3; ++ch)
+            oracle_intensities_from_pixel(images, nimg, W, H, col, row, ch,
+                                          I + (size_t)ch * nF * nimg + (size_t)nfit * nimg);
+        ++nfit;
+    }
+    free(FN);
+    return nfit;
+}
