@@ -1,0 +1,131 @@
+// common.cuh -- context, resident data handles and launch helpers shared by the .cu files.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <string>
+
+#include "../../include/brdfgpu.h"
+#include "lm_engine.cuh"
+
+namespace brdfgpu {
+
+constexpr int kMaxM = BRDFGPU_MAX_PARAMS;
+constexpr int kPassThreads = 256;     // threads per CTA of the streaming passes
+constexpr int kMaxPassBlocks = 2048;  // upper bound on CTAs of one pass (partials buffer)
+constexpr int kResultDoubles = 16;    // >= NACC
+
+struct NcclApi;  // comm.cu
+
+}  // namespace brdfgpu
+
+// Opaque handles of include/brdfgpu.h
+struct brdfgpu_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    unsigned long long launches = 0;
+
+    // reduction scratch of the streaming passes
+    double* d_partials = nullptr;  // kMaxPassBlocks x kResultDoubles
+    unsigned* d_sync = nullptr;    // [0] ticket, [1] flag, ...
+    double* d_result = nullptr;    // kResultDoubles (+ fit output block)
+    double* h_result = nullptr;    // pinned mirror
+    // persistent-fit in/out block
+    void* d_fitio = nullptr;
+    void* h_fitio = nullptr;  // pinned
+
+    // multi-GPU
+    void* nccl_comm = nullptr;
+    int rank = 0, nranks = 1;
+};
+
+struct brdfgpu_samples {
+    long n = 0;
+    int model = 1;
+    double* c = nullptr;     // cosphi
+    double* L = nullptr;     // log(t), NaN = take the pow() path
+    double* x = nullptr;     // measurements
+    double* traw = nullptr;  // raw model cosine (read only on the pow() path)
+    bool owns = true;
+};
+
+struct brdfgpu_batch {
+    long nfit = 0;
+    int nper = 0;
+    int model = 1;
+    double *c = nullptr, *L = nullptr, *x = nullptr, *traw = nullptr;  // nfit x nper each
+    double* p = nullptr;     // nfit x 3
+    double* info = nullptr;  // nfit x 10
+    int* ret = nullptr;      // nfit
+    bool owns = true;
+};
+
+namespace brdfgpu {
+
+brdfgpu_ctx* default_ctx();  // process-wide context for the levmar-signature entry points
+void set_error(brdfgpu_ctx* ctx, const std::string& msg);
+
+#define BG_CUDA_OK(ctx, call)                                                                    \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess) {                                                                 \
+            ::brdfgpu::set_error((ctx), std::string(#call) + ": " + cudaGetErrorString(e_));     \
+            return BRDFGPU_LM_ERROR;                                                             \
+        }                                                                                        \
+    } while (0)
+
+inline int pass_blocks(const brdfgpu_ctx* ctx, long n, int ctas_per_sm) {
+    // grid sized in multiples of the SM count (148 on B200); small problems get fewer CTAs so the
+    // final cross-CTA reduction stays short
+    long want = (n / 2 + kPassThreads - 1) / kPassThreads;
+    long cap = (long)ctx->sm_count * ctas_per_sm;
+    if (cap > kMaxPassBlocks) cap = kMaxPassBlocks;
+    if (want < 1) want = 1;
+    return (int)(want < cap ? want : cap);
+}
+
+// ---- implemented in global_fit.cu ----
+struct GlobalFitSpec {
+    int m, itmax, jac_mode, has_lb, has_ub, has_dscl, has_opts;
+    double delta;
+    double p[kMaxM], lb[kMaxM], ub[kMaxM], dscl[kMaxM], opts[5];
+};
+struct GlobalFitOut {
+    int ret;
+    double p[kMaxM];
+    double info[10];
+    double JtJ[kMaxM * kMaxM];
+};
+
+int samples_alloc(brdfgpu_ctx* ctx, long n, int model, brdfgpu_samples** out);
+int samples_prepare(brdfgpu_ctx* ctx, brdfgpu_samples* s);  // L from traw
+int global_normal_eq(brdfgpu_ctx* ctx, const brdfgpu_samples* s, const double* p, double delta,
+                     int jac_mode, double* out11, bool sync);
+int global_cost(brdfgpu_ctx* ctx, const brdfgpu_samples* s, const double* p, double* out2, bool sync);
+int global_residuals(brdfgpu_ctx* ctx, const brdfgpu_samples* s, const double* p, double* e_host);
+int global_fit_bc(brdfgpu_ctx* ctx, const brdfgpu_samples* s, double* p, int m, const double* lb,
+                  const double* ub, const double* dscl, int itmax, const double* opts, double* info,
+                  double* covar, int drive, int jac_mode);
+int global_fit_unc(brdfgpu_ctx* ctx, const brdfgpu_samples* s, double* p, int m, int itmax,
+                   const double* opts, double* info, double* covar, int jac_mode);
+int model_predict(brdfgpu_ctx* ctx, const double* p, const double* angles_host, int model, int n, double* hx_host);
+int model_jacobian(brdfgpu_ctx* ctx, const double* p, const double* angles_host, int model, int n, int m,
+                   double* jac_host);
+
+// ---- synth.cu ----
+int synth_samples(brdfgpu_ctx* ctx, brdfgpu_samples* s, unsigned long long seed, long start, const double* truth);
+int synth_batch(brdfgpu_ctx* ctx, brdfgpu_batch* b, unsigned long long seed, long first_fit);
+
+// ---- batched_fit.cu ----
+int batch_alloc(brdfgpu_ctx* ctx, long nfit, int nper, int model, brdfgpu_batch** out);
+int batch_prepare(brdfgpu_ctx* ctx, brdfgpu_batch* b);
+int batch_fit(brdfgpu_ctx* ctx, brdfgpu_batch* b, const double* p0, const double* lb, const double* ub,
+              int itmax, const double* opts, int jac_mode);
+
+// ---- comm.cu ----
+int comm_allreduce_device(brdfgpu_ctx* ctx, double* d_buf, int count);
+
+}  // namespace brdfgpu

@@ -1,0 +1,581 @@
+// lm_engine.cuh -- the Levenberg-Marquardt control loop on REDUCED quantities.
+//
+// levmar (reference: levmar/lmbc_core.c:369-1022, lm_core.c:64-432) keeps n-sized arrays e, hx and
+// an n x m Jacobian in host memory and walks them serially.  Here nothing n-sized exists: the
+// control code only ever consumes
+//     J^T J (m x m), J^T e (m)            from a Jacobian evaluation at p,
+//     ||x - f(p')||^2 (+ "some residual is non-finite")   from a trial evaluation,
+// which an Evaluator produces by streaming the samples on the GPU.  The same source is compiled
+// three times:
+//     host      -- HostEval launches one kernel per evaluation (global mode, NCCL all-reduce inside)
+//     device    -- GridEval inside one persistent cooperative kernel (global mode, single launch)
+//     device    -- GroupEval, one lane group per fit (batched mode)
+// so all modes make bit-identical decisions from identical sums.
+//
+// Evaluator concept:
+//     void   jac (const double* p, double* JtJ /*m*m row-major, full*/, double* Jte /*m*/);
+//     double cost(const double* p, bool& elems_nonfinite);
+#pragma once
+
+#include <cfloat>
+#include <cmath>
+
+#ifdef __CUDACC__
+#define BG_HD __host__ __device__
+#define BG_HDI __host__ __device__ __forceinline__
+#else
+#define BG_HD
+#define BG_HDI inline
+#endif
+
+namespace brdfgpu {
+
+// levmar/lmbc.c:35-38, lm.c:35-36, levmar.h:95-101
+constexpr double kEpsilon = 1E-12;
+constexpr double kOneThird = 0.3333333334;
+constexpr int kLsItMax = 150;
+constexpr double kPow = 2.1;
+constexpr double kInitMu = 1E-03;
+constexpr double kStopThresh = 1E-17;
+constexpr double kDiffDelta = 1E-06;
+constexpr int kLmError = -1;
+
+// misc.h:68 (not fabs: identical -0.0 / NaN behaviour)
+BG_HDI double lm_abs(double v) { return (v >= 0.0) ? v : -v; }
+BG_HDI bool lm_finite(double v) { return (v - v) == 0.0; }  // false for NaN and +-Inf
+
+struct LmOptions {
+    double tau, eps1, eps2, eps2_sq, eps3;
+    int itmax;
+};
+
+BG_HDI LmOptions lm_options(const double* opts, int itmax) {
+    LmOptions o;
+    if (opts) {  // lmbc_core.c:470-476
+        o.tau = opts[0]; o.eps1 = opts[1]; o.eps2 = opts[2]; o.eps2_sq = opts[2] * opts[2]; o.eps3 = opts[3];
+    } else {     // :477-483
+        o.tau = kInitMu; o.eps1 = kStopThresh; o.eps2 = kStopThresh;
+        o.eps2_sq = kStopThresh * kStopThresh; o.eps3 = kStopThresh;
+    }
+    o.itmax = itmax;
+    return o;
+}
+
+// ---------------------------------------------------------------------------------------------
+// m x m solve: Crout LU, implicit row scaling, partial pivoting (Axb_core.c:1196-1270).
+// Returns 0 when a row of A is all zero; a zero pivot is replaced by DBL_EPSILON.
+// ---------------------------------------------------------------------------------------------
+template <int MM>
+BG_HDI int lu_factor(double* a, int* perm, int m) {
+    double rowscale[MM];
+    int piv = -1;
+    for (int i = 0; i < m; ++i) {
+        double big = 0.0;
+        for (int j = 0; j < m; ++j) {
+            const double t = lm_abs(a[i * m + j]);
+            if (t > big) big = t;
+        }
+        if (big == 0.0) return 0;
+        rowscale[i] = 1.0 / big;
+    }
+    for (int j = 0; j < m; ++j) {
+        for (int i = 0; i < j; ++i) {
+            double s = a[i * m + j];
+            for (int k = 0; k < i; ++k) s -= a[i * m + k] * a[k * m + j];
+            a[i * m + j] = s;
+        }
+        double big = 0.0;
+        for (int i = j; i < m; ++i) {
+            double s = a[i * m + j];
+            for (int k = 0; k < j; ++k) s -= a[i * m + k] * a[k * m + j];
+            a[i * m + j] = s;
+            const double t = rowscale[i] * lm_abs(s);
+            if (t >= big) { big = t; piv = i; }
+        }
+        if (j != piv) {
+            for (int k = 0; k < m; ++k) {
+                const double t = a[piv * m + k];
+                a[piv * m + k] = a[j * m + k];
+                a[j * m + k] = t;
+            }
+            rowscale[piv] = rowscale[j];
+        }
+        perm[j] = piv;
+        if (a[j * m + j] == 0.0) a[j * m + j] = DBL_EPSILON;
+        if (j != m - 1) {
+            const double t = 1.0 / a[j * m + j];
+            for (int i = j + 1; i < m; ++i) a[i * m + j] *= t;
+        }
+    }
+    return 1;
+}
+
+template <int MM>
+BG_HDI void lu_substitute(const double* a, const int* perm, double* x, int m) {
+    int first = 0;
+    for (int i = 0; i < m; ++i) {
+        const int j = perm[i];
+        double s = x[j];
+        x[j] = x[i];
+        if (first != 0) {
+            for (int k = first - 1; k < i; ++k) s -= a[i * m + k] * x[k];
+        } else if (s != 0.0) {
+            first = i + 1;
+        }
+        x[i] = s;
+    }
+    for (int i = m - 1; i >= 0; --i) {
+        double s = x[i];
+        for (int j = i + 1; j < m; ++j) s -= a[i * m + j] * x[j];
+        x[i] = s / a[i * m + i];
+    }
+}
+
+template <int MM>
+BG_HDI int solve_lu(const double* A, const double* B, double* x, int m) {
+    double a[MM * MM];
+    int perm[MM];
+    for (int i = 0; i < m * m; ++i) a[i] = A[i];
+    for (int i = 0; i < m; ++i) x[i] = B[i];
+    if (!lu_factor<MM>(a, perm, m)) return 0;
+    lu_substitute<MM>(a, perm, x, m);
+    return 1;
+}
+
+// covariance C = sumsq/(n-m) * (JtJ)^-1 through the same LU (misc_core.c:426-591). 0 on failure.
+template <int MM>
+BG_HDI int lm_covar(const double* JtJ, double* C, double sumsq, int m, long n) {
+    double a[MM * MM], x[MM];
+    int perm[MM];
+    for (int i = 0; i < m * m; ++i) a[i] = JtJ[i];
+    if (!lu_factor<MM>(a, perm, m)) return 0;
+    for (int l = 0; l < m; ++l) {
+        for (int i = 0; i < m; ++i) x[i] = 0.0;
+        x[l] = 1.0;
+        lu_substitute<MM>(a, perm, x, m);
+        for (int i = 0; i < m; ++i) C[i * m + l] = x[i];
+    }
+    const double fact = sumsq / (double)(n - m);
+    for (int i = 0; i < m * m; ++i) C[i] *= fact;
+    return m;
+}
+
+// ---------------------------------------------------------------------------------------------
+// box helpers (lmbc_core.c:59-88, 94-142)
+// ---------------------------------------------------------------------------------------------
+BG_HDI double lm_median3(double lo, double v, double hi) {
+    if (lo >= v) {
+        if (hi >= lo) return lo;
+        return (hi <= v) ? v : hi;
+    }
+    if (hi >= v) return v;
+    return (hi <= lo) ? lo : hi;
+}
+
+struct Box {
+    const double* lb;  // may be nullptr
+    const double* ub;  // may be nullptr
+};
+
+BG_HDI void box_project(double* p, const Box& b, int m) {
+    if (!b.lb && !b.ub) return;
+    for (int i = m; i-- > 0;) {
+        if (b.lb && b.ub) p[i] = lm_median3(b.lb[i], p[i], b.ub[i]);
+        else if (b.ub) { if (p[i] > b.ub[i]) p[i] = b.ub[i]; }
+        else { if (p[i] < b.lb[i]) p[i] = b.lb[i]; }
+    }
+}
+
+struct LmCounters {
+    int nfev, njev, nlss;
+};
+
+// Calls the evaluator in the caller's (unscaled) coordinates; with diagonal scaling D the control
+// loop works on q = D^-1 p and J_q = J_p D (lmbc_core.c:360-366, 555-570), i.e.
+// JtJ_ij *= d_i d_j and Jte_i *= d_i -- the scaled sums are formed from the unscaled ones here
+// instead of scaling n rows of J.
+template <int MM, class Eval>
+BG_HDI void eval_jac_scaled(Eval& ev, const double* q, const double* dscl, int m, double* JtJ, double* Jte) {
+    if (!dscl) {
+        ev.jac(q, JtJ, Jte);
+        return;
+    }
+    double ps[MM];
+    for (int i = m; i-- > 0;) ps[i] = q[i] * dscl[i];
+    ev.jac(ps, JtJ, Jte);
+    for (int i = 0; i < m; ++i) {
+        Jte[i] *= dscl[i];
+        for (int j = 0; j < m; ++j) JtJ[i * m + j] *= dscl[i] * dscl[j];
+    }
+}
+
+template <int MM, class Eval>
+BG_HDI double eval_cost_scaled(Eval& ev, const double* q, const double* dscl, int m, bool& bad) {
+    if (!dscl) return ev.cost(q, bad);
+    double ps[MM];
+    for (int i = m; i-- > 0;) ps[i] = q[i] * dscl[i];
+    return ev.cost(ps, bad);
+}
+
+// info[] of lmbc_core.c:978-991 / lm_core.c:405-418
+BG_HDI void lm_fill_info(double* info, const double* JtJ, int m, double e0, double e, double ginf,
+                         double dp2, double mu, int k, int stop, const LmCounters& c) {
+    if (!info) return;
+    double big = -DBL_MAX;
+    for (int i = 0; i < m; ++i)
+        if (big < JtJ[i * m + i]) big = JtJ[i * m + i];
+    info[0] = e0; info[1] = e; info[2] = ginf; info[3] = dp2; info[4] = mu / big;
+    info[5] = (double)k; info[6] = (double)stop; info[7] = (double)c.nfev;
+    info[8] = (double)c.njev; info[9] = (double)c.nlss;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Schnabel/Koontz/Weiss backtracking line search with box projection (lmbc_core.c:179-337).
+// `step` may be shortened in place.  Returns iretcd (0 = acceptable point in xnew / fnew).
+// ---------------------------------------------------------------------------------------------
+template <int MM, class Eval>
+BG_HDI int lm_line_search(Eval& ev, int m, const double* xc, double fc, const double* g, double* step,
+                          double alpha, double* xnew, double& fnew_sumsq, const Box& box,
+                          const double* dscl, double stepmx, double steptl, LmCounters& cnt) {
+    bool firstback = true, bad;
+    double sln, slp, rln, rmnlmb, lambda, tlmbda = 0.0, plmbda = 0.0, pfpls = 0.0, fpls, t;
+
+    fc *= 0.5;
+    t = 0.0;
+    for (int i = m; i-- > 0;) t += step[i] * step[i];
+    sln = sqrt(t);
+    if (sln > stepmx) {
+        const double scl = stepmx / sln;
+        for (int i = m; i-- > 0;) step[i] *= scl;
+        sln = stepmx;
+    }
+    slp = rln = 0.0;
+    for (int i = m; i-- > 0;) {
+        slp += g[i] * step[i];
+        const double a = (lm_abs(xc[i]) >= 1.0) ? lm_abs(xc[i]) : 1.0;
+        const double b = lm_abs(step[i]) / a;
+        if (rln < b) rln = b;
+    }
+    rmnlmb = steptl / rln;
+    lambda = 1.0;
+
+    for (int it = kLsItMax; it-- > 0;) {
+        for (int i = m; i-- > 0;) xnew[i] = xc[i] + lambda * step[i];
+        box_project(xnew, box, m);
+
+        if (!dscl) {
+            t = ev.cost(xnew, bad);
+        } else {  // :262-266 scales the point in place and back (not an exact round trip)
+            for (int i = m; i-- > 0;) xnew[i] *= dscl[i];
+            t = ev.cost(xnew, bad);
+            for (int i = m; i-- > 0;) xnew[i] /= dscl[i];
+        }
+        ++cnt.nfev;
+        fpls = 0.5 * t;
+        fnew_sumsq = t;
+
+        if (fpls <= fc + slp * alpha * lambda) return 0;
+        if (lambda < rmnlmb) return 1;
+
+        if (!lm_finite(fpls)) {
+            lambda *= 0.1;
+            firstback = true;
+        } else {
+            if (firstback) {
+                tlmbda = -lambda * slp / ((fpls - fc - slp) * 2.0);
+                firstback = false;
+            } else {
+                const double t1 = fpls - fc - lambda * slp;
+                const double t2 = pfpls - fc - plmbda * slp;
+                const double t3 = 1.0 / (lambda - plmbda);
+                const double a3 = 3.0 * t3 * (t1 / (lambda * lambda) - t2 / (plmbda * plmbda));
+                const double b = t3 * (t2 * lambda / (plmbda * plmbda) - t1 * plmbda / (lambda * lambda));
+                const double disc = b * b - a3 * slp;
+                if (disc > b * b)
+                    tlmbda = (-b + ((a3 < 0) ? -sqrt(disc) : sqrt(disc))) / a3;
+                else
+                    tlmbda = (-b + ((a3 < 0) ? sqrt(disc) : -sqrt(disc))) / a3;
+                if (tlmbda > lambda * 0.5) tlmbda = lambda * 0.5;
+            }
+            plmbda = lambda;
+            pfpls = fpls;
+            if (tlmbda < lambda * 0.1) lambda *= 0.1;
+            else lambda = tlmbda;
+        }
+    }
+    return 1;
+}
+
+// =============================================================================================
+// Box-constrained LM (projected LM step / line search / projected gradient), lmbc_core.c:369-1022.
+// p: in/out (m).  lb/ub/dscl may be nullptr.  JtJ_out (m*m, may be nullptr) receives the
+// unaugmented normal matrix at exit (for the covariance).  Returns #iterations or kLmError.
+// The start must already have been range-checked by the caller (n >= m, lb <= ub, dscl > 0).
+// `lbs/ubs`: when dscl is given the caller passes bounds already divided by dscl (:536-540).
+// =============================================================================================
+template <int MM, class Eval>
+BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double* ub, const double* dscl,
+                     const LmOptions& o, double* info, double* JtJ_out) {
+    const double alpha = 1e-4, beta = 0.9, gamma = 0.99995, rho = 1e-8;
+    const double tini = 1.0, tming = 1e-18;
+    double JtJ[MM * MM], Jte[MM], Dp[MM], diag[MM], pDp[MM];
+    double mu = 0.0, ginf = 0.0, t = 0.0, t0, tmp;
+    double e_cur, e_new = 0.0, e_init, p_L2 = 0.0, Dp_L2 = DBL_MAX, dF, dL, gTd;
+    int k, stop = 0, nu = 2, gprevtaken = 0, numactive, j;
+    bool bad = false;
+    LmCounters cnt = {0, 0, 0};
+    const Box box = {lb, ub};
+
+    for (int i = 0; i < m * m; ++i) JtJ[i] = 0.0;
+    for (int i = 0; i < m; ++i) diag[i] = 0.0;
+
+    // e = x - f(p) at the (projected) start, :522-534.  p is still in caller coordinates here.
+    e_cur = ev.cost(p, bad);
+    cnt.nfev = 1;
+    e_init = e_cur;
+    if (!lm_finite(e_cur)) stop = 7;
+
+    if (dscl)
+        for (int i = m; i-- > 0;) p[i] /= dscl[i];
+
+    for (k = 0; k < o.itmax && !stop; ++k) {
+        if (e_cur <= o.eps3) { stop = 6; break; }
+
+        eval_jac_scaled<MM>(ev, p, dscl, m, JtJ, Jte);
+        ++cnt.njev;
+
+        // ||J^T e||_inf over free variables, ||p||^2 (:639-646)
+        j = numactive = 0;
+        p_L2 = ginf = 0.0;
+        for (int i = 0; i < m; ++i) {
+            if (ub && p[i] == ub[i]) { ++numactive; if (Jte[i] > 0.0) ++j; }
+            else if (lb && p[i] == lb[i]) { ++numactive; if (Jte[i] < 0.0) ++j; }
+            else if (ginf < (tmp = lm_abs(Jte[i]))) ginf = tmp;
+            diag[i] = JtJ[i * m + i];
+            p_L2 += p[i] * p[i];
+        }
+        if (j == numactive && ginf <= o.eps1) { Dp_L2 = 0.0; stop = 1; break; }
+
+        if (k == 0) {  // :666-674
+            if (!lb && !ub) {
+                tmp = -DBL_MAX;
+                for (int i = 0; i < m; ++i)
+                    if (diag[i] > tmp) tmp = diag[i];
+                mu = o.tau * tmp;
+            } else {
+                mu = 0.5 * o.tau * e_cur;  // Kanzow's starting mu
+            }
+        }
+
+        for (;;) {
+            bool use_pg = false;
+
+            for (int i = 0; i < m; ++i) JtJ[i * m + i] += mu;
+            const int solved = solve_lu<MM>(JtJ, Jte, Dp, m);
+            ++cnt.nlss;
+
+            if (!solved) {  // :788-804
+                mu *= nu;
+                const int nu2 = (int)((unsigned)nu << 1);
+                if (nu2 <= nu) { stop = 5; break; }
+                nu = nu2;
+                for (int i = 0; i < m; ++i) JtJ[i * m + i] = diag[i];
+                continue;
+            }
+
+            for (int i = 0; i < m; ++i) pDp[i] = p[i] + Dp[i];
+            box_project(pDp, box, m);
+            Dp_L2 = 0.0;
+            for (int i = 0; i < m; ++i) {
+                Dp[i] = tmp = pDp[i] - p[i];
+                Dp_L2 += tmp * tmp;
+            }
+            if (Dp_L2 <= o.eps2_sq * p_L2) { stop = 2; break; }
+            if (Dp_L2 >= (p_L2 + o.eps2) / (kEpsilon * kEpsilon)) { stop = 4; break; }
+
+            e_new = eval_cost_scaled<MM>(ev, pDp, dscl, m, bad);
+            ++cnt.nfev;
+            // :748 -- overflow of the sum alone is tolerated, non-finite residuals are not
+            if (!lm_finite(e_new) && bad) { stop = 7; break; }
+
+            if (e_new <= gamma * e_cur) {  // LM step accepted, :753-785
+                dL = 0.0;
+                for (int i = 0; i < m; ++i) dL += Dp[i] * (mu * Dp[i] + Jte[i]);
+                if (dL > 0.0) {
+                    dF = e_cur - e_new;
+                    tmp = (2.0 * dF / dL - 1.0);
+                    tmp = 1.0 - tmp * tmp * tmp;
+                    mu = mu * ((tmp >= kOneThird) ? tmp : kOneThird);
+                } else {
+                    tmp = 0.1 * e_new;
+                    mu = (mu >= tmp) ? tmp : mu;
+                }
+                nu = 2;
+                for (int i = 0; i < m; ++i) p[i] = pDp[i];
+                e_cur = e_new;
+                gprevtaken = 0;
+                break;
+            }
+
+            // rejected: descent direction? (:810-816)
+            gTd = 0.0;
+            for (int i = 0; i < m; ++i) {
+                Jte[i] = -Jte[i];
+                gTd += Jte[i] * Dp[i];
+            }
+            if (gTd <= -rho * pow(Dp_L2, kPow / 2.0)) {
+                const double steptl = 1e3 * sqrt(DBL_EPSILON);
+                tmp = sqrt(p_L2);
+                const double stepmx = 1e3 * ((tmp >= 1.0) ? tmp : 1.0);
+                const int rc = lm_line_search<MM>(ev, m, p, e_cur, Jte, Dp, alpha, pDp, e_new, box, dscl,
+                                                  stepmx, steptl, cnt);
+                if (rc != 0 || !lm_finite(e_new)) use_pg = true;
+                else gprevtaken = 0;
+            } else {
+                use_pg = true;
+            }
+
+            if (use_pg) {  // projected gradient search, :871-946
+                bool found = false, fatal = false;
+                tmp = 0.0;
+                for (int i = 0; i < m; ++i) tmp += Jte[i] * Jte[i];
+                tmp = sqrt(tmp);
+                tmp = 100.0 / (1.0 + tmp);
+                t0 = (tmp <= tini) ? tmp : tini;
+
+                for (t = gprevtaken ? t : t0; t > tming; t *= beta) {
+                    for (int i = 0; i < m; ++i) pDp[i] = p[i] - t * Jte[i];
+                    box_project(pDp, box, m);
+                    Dp_L2 = 0.0;
+                    for (int i = 0; i < m; ++i) {
+                        Dp[i] = tmp = pDp[i] - p[i];
+                        Dp_L2 += tmp * tmp;
+                    }
+                    e_new = eval_cost_scaled<MM>(ev, pDp, dscl, m, bad);
+                    ++cnt.nfev;
+                    if (!lm_finite(e_new) && bad) { stop = 7; fatal = true; break; }
+
+                    gTd = 0.0;
+                    for (int i = 0; i < m; ++i) gTd += Jte[i] * Dp[i];
+
+                    if (gprevtaken && e_new <= e_cur + 2.0 * 0.99999 * gTd) {  // starting t too small
+                        t = t0;
+                        gprevtaken = 0;
+                        continue;  // the loop increment still applies t *= beta (:926-930)
+                    }
+                    if (e_new <= e_cur + 2.0 * alpha * gTd) { found = true; break; }
+                }
+                if (fatal) goto done;
+                if (!found) { gprevtaken = 0; break; }
+                gprevtaken = 1;
+            }
+
+            // take the line-search / projected-gradient point (:948-967)
+            Dp_L2 = 0.0;
+            for (int i = 0; i < m; ++i) {
+                tmp = pDp[i] - p[i];
+                Dp_L2 += tmp * tmp;
+            }
+            if (Dp_L2 <= o.eps2_sq * p_L2) { stop = 2; break; }
+            for (int i = 0; i < m; ++i) p[i] = pDp[i];
+            e_cur = e_new;
+            break;
+        }
+    }
+
+done:
+    if (k >= o.itmax) stop = 3;
+    for (int i = 0; i < m; ++i) JtJ[i * m + i] = diag[i];
+    lm_fill_info(info, JtJ, m, e_init, e_cur, ginf, Dp_L2, mu, k, stop, cnt);
+    if (JtJ_out)
+        for (int i = 0; i < m * m; ++i) JtJ_out[i] = JtJ[i];
+    if (dscl)
+        for (int i = 0; i < m; ++i) p[i] *= dscl[i];
+    return (stop != 4 && stop != 7) ? k : kLmError;
+}
+
+// =============================================================================================
+// Unconstrained LM with a full Jacobian evaluation per outer iteration, lm_core.c:64-432.
+// =============================================================================================
+template <int MM, class Eval>
+BG_HDI int lm_der(Eval& ev, int m, double* p, const LmOptions& o, double* info, double* JtJ_out) {
+    double JtJ[MM * MM], Jte[MM], Dp[MM], diag[MM], pDp[MM];
+    double mu = 0.0, ginf = 0.0, tmp, e_cur, e_new, e_init, p_L2 = 0.0, Dp_L2 = DBL_MAX, dF, dL;
+    int k, stop = 0, nu = 2;
+    bool bad = false;
+    LmCounters cnt = {0, 0, 0};
+
+    for (int i = 0; i < m * m; ++i) JtJ[i] = 0.0;
+    for (int i = 0; i < m; ++i) diag[i] = 0.0;
+
+    e_cur = ev.cost(p, bad);
+    cnt.nfev = 1;
+    e_init = e_cur;
+    if (!lm_finite(e_cur)) stop = 7;
+
+    for (k = 0; k < o.itmax && !stop; ++k) {
+        if (e_cur <= o.eps3) { stop = 6; break; }
+
+        ev.jac(p, JtJ, Jte);
+        ++cnt.njev;
+
+        p_L2 = ginf = 0.0;
+        for (int i = 0; i < m; ++i) {
+            if (ginf < (tmp = lm_abs(Jte[i]))) ginf = tmp;
+            diag[i] = JtJ[i * m + i];
+            p_L2 += p[i] * p[i];
+        }
+        if (ginf <= o.eps1) { Dp_L2 = 0.0; stop = 1; break; }
+
+        if (k == 0) {
+            tmp = -DBL_MAX;
+            for (int i = 0; i < m; ++i)
+                if (diag[i] > tmp) tmp = diag[i];
+            mu = o.tau * tmp;
+        }
+
+        for (;;) {
+            for (int i = 0; i < m; ++i) JtJ[i * m + i] += mu;
+            ++cnt.nlss;
+            if (solve_lu<MM>(JtJ, Jte, Dp, m)) {
+                Dp_L2 = 0.0;
+                for (int i = 0; i < m; ++i) {
+                    pDp[i] = p[i] + (tmp = Dp[i]);
+                    Dp_L2 += tmp * tmp;
+                }
+                if (Dp_L2 <= o.eps2_sq * p_L2) { stop = 2; break; }
+                if (Dp_L2 >= (p_L2 + o.eps2) / (kEpsilon * kEpsilon)) { stop = 4; break; }
+
+                e_new = ev.cost(pDp, bad);
+                ++cnt.nfev;
+                if (!lm_finite(e_new)) { stop = 7; break; }
+
+                dL = 0.0;
+                for (int i = 0; i < m; ++i) dL += Dp[i] * (mu * Dp[i] + Jte[i]);
+                dF = e_cur - e_new;
+                if (dL > 0.0 && dF > 0.0) {
+                    tmp = (2.0 * dF / dL - 1.0);
+                    tmp = 1.0 - tmp * tmp * tmp;
+                    mu = mu * ((tmp >= kOneThird) ? tmp : kOneThird);
+                    nu = 2;
+                    for (int i = 0; i < m; ++i) p[i] = pDp[i];
+                    e_cur = e_new;
+                    break;
+                }
+            }
+            mu *= nu;
+            const int nu2 = (int)((unsigned)nu << 1);
+            if (nu2 <= nu) { stop = 5; break; }
+            nu = nu2;
+            for (int i = 0; i < m; ++i) JtJ[i * m + i] = diag[i];
+        }
+    }
+    if (k >= o.itmax) stop = 3;
+    for (int i = 0; i < m; ++i) JtJ[i * m + i] = diag[i];
+    lm_fill_info(info, JtJ, m, e_init, e_cur, ginf, Dp_L2, mu, k, stop, cnt);
+    if (JtJ_out)
+        for (int i = 0; i < m * m; ++i) JtJ_out[i] = JtJ[i];
+    return (stop != 4 && stop != 7) ? k : kLmError;
+}
+
+}  // namespace brdfgpu
