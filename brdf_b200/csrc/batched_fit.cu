@@ -1,0 +1,214 @@
+// batched_fit.cu -- batched mode: thousands of independent small BRDF fits in one launch.
+//
+// Replaces the per-pixel loop of CBRDFdata::CalcBRDFEquation (brdfdata.cpp:1195-1221), which calls
+// SolveEquation -> dlevmar_bc_dif (brdfdata.cpp:1119) once per mapped face and colour channel.
+// One lane group (a full warp, or a half warp for <= 16 samples) owns one fit: its samples live in
+// registers for the whole solve, every evaluation is a few model evaluations per lane plus a
+// butterfly reduction over the group, and every lane of the group runs the same levmar control
+// code (lm_engine.cuh) on the same sums, so there is no divergence inside a group and no
+// communication between groups.  Fits diverge freely from each other (different iteration counts,
+// line searches, projected-gradient probes).
+#include "brdf_model.cuh"
+#include "common.cuh"
+
+namespace brdfgpu {
+
+constexpr int kBatchThreads = 128;
+
+struct BatchSpec {
+    int itmax, jkind, has_lb, has_ub, dif_accounting;
+    double delta;
+    double p0[3], lb[3], ub[3];
+    LmOptions opt;
+};
+
+// G lanes per fit, S samples per lane held in registers (S == 0: samples re-read from memory)
+template <int G, int S>
+struct GroupEval {
+    static constexpr int SR = S > 0 ? S : 1;
+    double c[SR], L[SR], x[SR];
+    const double *gc, *gL, *gx, *traw;  // this fit's rows
+    int nper, lane, model, jkind;
+    unsigned mask;
+    double delta;
+
+    __device__ __forceinline__ double group_sum(double v) const {
+#pragma unroll
+        for (int off = G / 2; off; off >>= 1) v += __shfl_xor_sync(mask, v, off, G);
+        return v;
+    }
+
+    template <int JAC>
+    __device__ __forceinline__ void jac_body(const PassParams& q, double* acc) const {
+        if (S > 0) {
+#pragma unroll
+            for (int s = 0; s < SR; ++s) {
+                const int idx = s * G + lane;
+                if (idx < nper) accumulate_jac<JAC>(q, c[s], L[s], x[s], traw, idx, acc);
+            }
+        } else {
+            for (int idx = lane; idx < nper; idx += G) accumulate_jac<JAC>(q, gc[idx], gL[idx], gx[idx], traw, idx, acc);
+        }
+    }
+
+    __device__ __noinline__ void jac(const double* p, double* JtJ, double* Jte) const {
+        const PassParams q = make_pass_params(p, model, delta, jkind);
+        double acc[NACC];
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+        if (jkind == kJacForward) jac_body<kJacForward>(q, acc);
+        else if (jkind == kJacCentral) jac_body<kJacCentral>(q, acc);
+        else jac_body<kJacAnalytic>(q, acc);
+#pragma unroll
+        for (int k = 0; k < NBAD; ++k) acc[k] = group_sum(acc[k]);
+        JtJ[0] = acc[A00]; JtJ[1] = acc[A01]; JtJ[2] = acc[A02];
+        JtJ[3] = acc[A01]; JtJ[4] = acc[A11]; JtJ[5] = acc[A12];
+        JtJ[6] = acc[A02]; JtJ[7] = acc[A12]; JtJ[8] = acc[A22];
+        Jte[0] = acc[G0]; Jte[1] = acc[G1]; Jte[2] = acc[G2];
+    }
+
+    __device__ __noinline__ double cost(const double* p, bool& bad) const {
+        const PassParams q = make_pass_params(p, model, 1.0, kJacAnalytic);
+        double acc[2] = {0.0, 0.0};
+        if (S > 0) {
+#pragma unroll
+            for (int s = 0; s < SR; ++s) {
+                const int idx = s * G + lane;
+                if (idx < nper) accumulate_cost(q, c[s], L[s], x[s], traw, idx, acc);
+            }
+        } else {
+            for (int idx = lane; idx < nper; idx += G) accumulate_cost(q, gc[idx], gL[idx], gx[idx], traw, idx, acc);
+        }
+        const double e = group_sum(acc[0]);
+        bad = group_sum(acc[1]) != 0.0;
+        return e;
+    }
+};
+
+template <int G, int S>
+__global__ void __launch_bounds__(kBatchThreads) k_batched_fit(const double* __restrict__ c, const double* __restrict__ L,
+                                                                const double* __restrict__ x,
+                                                                const double* __restrict__ traw, long nfit, int nper,
+                                                                int model, BatchSpec spec, double* __restrict__ p_out,
+                                                                double* __restrict__ info_out, int* __restrict__ ret_out) {
+    const long fit = ((long)blockIdx.x * kBatchThreads + threadIdx.x) / G;
+    if (fit >= nfit) return;
+    const int lane = threadIdx.x % G;
+    const long base = fit * nper;
+
+    GroupEval<G, S> ev;
+    ev.gc = c + base; ev.gL = L + base; ev.gx = x + base; ev.traw = traw + base;
+    ev.nper = nper; ev.lane = lane; ev.model = model; ev.jkind = spec.jkind; ev.delta = spec.delta;
+    ev.mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+    if (S > 0) {
+#pragma unroll
+        for (int s = 0; s < (S > 0 ? S : 1); ++s) {
+            const int idx = s * G + lane;
+            const bool in = idx < nper;
+            ev.c[s] = in ? c[base + idx] : 0.0;
+            ev.L[s] = in ? L[base + idx] : 0.0;
+            ev.x[s] = in ? x[base + idx] : 0.0;
+        }
+    }
+
+    double p[3] = {spec.p0[0], spec.p0[1], spec.p0[2]};
+    double info[10];
+    const double* lb = spec.has_lb ? spec.lb : nullptr;
+    const double* ub = spec.has_ub ? spec.ub : nullptr;
+    const Box box{lb, ub};
+    box_project(p, box, 3);  // lmbc_core.c:516
+    const int ret = lm_bc_der<3>(ev, 3, p, lb, ub, nullptr, spec.opt, info, nullptr);
+    if (lane == 0) {
+        if (spec.dif_accounting) info[7] += info[8] * (spec.jkind == kJacCentral ? 6.0 : 4.0);  // lmbc_core.c:1119-1124
+        for (int i = 0; i < 3; ++i) p_out[fit * 3 + i] = p[i];
+        if (info_out)
+            for (int i = 0; i < 10; ++i) info_out[fit * 10 + i] = info[i];
+        if (ret_out) ret_out[fit] = ret;
+    }
+}
+
+__global__ void k_prepare_batch(const double* __restrict__ traw, double* __restrict__ L, long n) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        L[i] = log_or_flag(traw[i]);
+}
+
+int batch_alloc(brdfgpu_ctx* ctx, long nfit, int nper, int model, brdfgpu_batch** out) {
+    if (nfit < 0 || nper < 3 || (model != 0 && model != 1)) {
+        set_error(ctx, "batch: bad sizes or model (need nper >= 3 samples per fit)");
+        return BRDFGPU_LM_ERROR;
+    }
+    brdfgpu_batch* b = new brdfgpu_batch;
+    b->nfit = nfit; b->nper = nper; b->model = model;
+    const size_t nb = sizeof(double) * (size_t)(nfit > 0 ? nfit * nper : 1);
+    cudaError_t e = cudaMalloc(&b->c, nb);
+    if (e == cudaSuccess) e = cudaMalloc(&b->L, nb);
+    if (e == cudaSuccess) e = cudaMalloc(&b->x, nb);
+    if (e == cudaSuccess) e = cudaMalloc(&b->traw, nb);
+    if (e == cudaSuccess) e = cudaMalloc(&b->p, sizeof(double) * 3 * (size_t)(nfit > 0 ? nfit : 1));
+    if (e == cudaSuccess) e = cudaMalloc(&b->info, sizeof(double) * 10 * (size_t)(nfit > 0 ? nfit : 1));
+    if (e == cudaSuccess) e = cudaMalloc(&b->ret, sizeof(int) * (size_t)(nfit > 0 ? nfit : 1));
+    if (e != cudaSuccess) {
+        cudaFree(b->c); cudaFree(b->L); cudaFree(b->x); cudaFree(b->traw); cudaFree(b->p); cudaFree(b->info); cudaFree(b->ret);
+        delete b;
+        set_error(ctx, std::string("batch: cudaMalloc: ") + cudaGetErrorString(e));
+        return BRDFGPU_LM_ERROR;
+    }
+    *out = b;
+    return 0;
+}
+
+int batch_prepare(brdfgpu_ctx* ctx, brdfgpu_batch* b) {
+    const long n = b->nfit * b->nper;
+    if (n == 0) return 0;
+    long blocks = (n + 255) / 256;
+    if (blocks > (long)ctx->sm_count * 16) blocks = (long)ctx->sm_count * 16;
+    k_prepare_batch<<<(int)blocks, 256, 0, ctx->stream>>>(b->traw, b->L, n);
+    ++ctx->launches;
+    BG_CUDA_OK(ctx, cudaGetLastError());
+    return 0;
+}
+
+template <int G, int S>
+static void launch_batch(brdfgpu_ctx* ctx, brdfgpu_batch* b, const BatchSpec& spec) {
+    const long threads = b->nfit * G;
+    const long blocks = (threads + kBatchThreads - 1) / kBatchThreads;
+    k_batched_fit<G, S><<<(unsigned)blocks, kBatchThreads, 0, ctx->stream>>>(b->c, b->L, b->x, b->traw, b->nfit, b->nper,
+                                                                            b->model, spec, b->p, b->info, b->ret);
+}
+
+int batch_fit(brdfgpu_ctx* ctx, brdfgpu_batch* b, const double* p0, const double* lb, const double* ub, int itmax,
+              const double* opts, int jac_mode) {
+    if (b->nfit == 0) return 0;
+    if (lb && ub)
+        for (int i = 0; i < 3; ++i)
+            if (lb[i] > ub[i]) {
+                fprintf(stderr, "brdfgpu batch fit: at least one lower bound exceeds the upper one\n");
+                return BRDFGPU_LM_ERROR;
+            }
+    BatchSpec spec;
+    const double delta_signed = opts ? opts[4] : kDiffDelta;
+    spec.itmax = itmax;
+    spec.jkind = jac_mode == BRDFGPU_JAC_ANALYTIC ? kJacAnalytic : (delta_signed < 0.0 ? kJacCentral : kJacForward);
+    spec.dif_accounting = jac_mode == BRDFGPU_JAC_FD;
+    spec.delta = lm_abs(delta_signed);
+    spec.has_lb = lb != nullptr;
+    spec.has_ub = ub != nullptr;
+    for (int i = 0; i < 3; ++i) {
+        spec.p0[i] = p0[i];
+        spec.lb[i] = lb ? lb[i] : 0.0;
+        spec.ub[i] = ub ? ub[i] : 0.0;
+    }
+    spec.opt = lm_options(opts, itmax);
+
+    const int n = b->nper;
+    if (n <= 16) launch_batch<16, 1>(ctx, b, spec);
+    else if (n <= 32) launch_batch<32, 1>(ctx, b, spec);
+    else if (n <= 64) launch_batch<32, 2>(ctx, b, spec);
+    else if (n <= 128) launch_batch<32, 4>(ctx, b, spec);
+    else launch_batch<32, 0>(ctx, b, spec);
+    ++ctx->launches;
+    BG_CUDA_OK(ctx, cudaGetLastError());
+    return 0;
+}
+
+}  // namespace brdfgpu

@@ -1,0 +1,502 @@
+// capi.cu -- the C-ABI of include/brdfgpu.h: contexts, the levmar-signature entry points, resident
+// sample sets, the reference's fit drivers with raw pointers, and the reduced-evaluator LM loop.
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace brdfgpu;
+
+namespace brdfgpu {
+
+static std::string g_create_error;
+
+void set_error(brdfgpu_ctx* ctx, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    else g_create_error = msg;
+    fprintf(stderr, "brdfgpu: %s\n", msg.c_str());
+}
+
+brdfgpu_ctx* default_ctx() {
+    static brdfgpu_ctx* ctx = nullptr;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!ctx && brdfgpu_create(-1, &ctx) != 0) ctx = nullptr;
+    return ctx;
+}
+
+}  // namespace brdfgpu
+
+static brdfgpu_ctx* ctx_or_default(brdfgpu_ctx* ctx) { return ctx ? ctx : default_ctx(); }
+
+extern "C" const char* brdfgpu_version(void) { return "brdfgpu 0.1 (sm_100a)"; }
+
+extern "C" int brdfgpu_create(int device, brdfgpu_ctx** out) {
+    if (!out) return BRDFGPU_LM_ERROR;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count < 1) {
+        // no CPU fallback by design: the library is CUDA only
+        set_error(nullptr, std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count = 0"));
+        return BRDFGPU_LM_ERROR;
+    }
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) device = 0;
+    if (device >= count) {
+        set_error(nullptr, "device index out of range");
+        return BRDFGPU_LM_ERROR;
+    }
+    brdfgpu_ctx* ctx = new brdfgpu_ctx;
+    ctx->device = device;
+    e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->coop, cudaDevAttrCooperativeLaunch, device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_partials, sizeof(double) * 2 * kMaxPassBlocks * kResultDoubles);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_sync, sizeof(unsigned) * 16);
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_sync, 0, sizeof(unsigned) * 16);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_result, sizeof(double) * kResultDoubles);
+    if (e == cudaSuccess) e = cudaHostAlloc(&ctx->h_result, sizeof(double) * kResultDoubles, cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer(&ctx->h_result_dev, ctx->h_result, 0);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->h_seq, sizeof(unsigned long long), cudaHostAllocMapped);
+    if (e == cudaSuccess) {
+        *ctx->h_seq = 0;
+        e = cudaHostGetDevicePointer(&ctx->h_seq_dev, (void*)ctx->h_seq, 0);
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_fitio, sizeof(GlobalFitOut));
+    if (e == cudaSuccess) e = cudaHostAlloc(&ctx->h_fitio, sizeof(GlobalFitOut), cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        set_error(nullptr, std::string("context creation failed: ") + cudaGetErrorString(e));
+        brdfgpu_destroy(ctx);
+        return BRDFGPU_LM_ERROR;
+    }
+    *out = ctx;
+    return 0;
+}
+
+extern "C" void brdfgpu_destroy(brdfgpu_ctx* ctx) {
+    if (!ctx) return;
+    brdfgpu_comm_destroy(ctx);
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_partials); cudaFree(ctx->d_sync); cudaFree(ctx->d_result); cudaFree(ctx->d_fitio);
+    if (ctx->h_result) cudaFreeHost(ctx->h_result);
+    if (ctx->h_seq) cudaFreeHost((void*)ctx->h_seq);
+    if (ctx->h_fitio) cudaFreeHost(ctx->h_fitio);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* brdfgpu_last_error(brdfgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+extern "C" unsigned long long brdfgpu_launch_count(brdfgpu_ctx* ctx) {
+    ctx = ctx_or_default(ctx);
+    return ctx ? ctx->launches : 0ull;
+}
+extern "C" void* brdfgpu_stream(brdfgpu_ctx* ctx) {
+    ctx = ctx_or_default(ctx);
+    return ctx ? (void*)ctx->stream : nullptr;
+}
+extern "C" int brdfgpu_synchronize(brdfgpu_ctx* ctx) {
+    ctx = ctx_or_default(ctx);
+    if (!ctx) return BRDFGPU_LM_ERROR;
+    BG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// resident sample sets
+// ------------------------------------------------------------------------------------------------
+static int samples_fill(brdfgpu_ctx* ctx, brdfgpu_samples* s, const double* c, const double* t, const double* x,
+                        cudaMemcpyKind kind) {
+    const size_t nb = sizeof(double) * (size_t)s->n;
+    if (s->n == 0) return 0;
+    BG_CUDA_OK(ctx, cudaMemcpyAsync(s->c, c, nb, kind, ctx->stream));
+    BG_CUDA_OK(ctx, cudaMemcpyAsync(s->traw, t, nb, kind, ctx->stream));
+    if (x) BG_CUDA_OK(ctx, cudaMemcpyAsync(s->x, x, nb, kind, ctx->stream));
+    else BG_CUDA_OK(ctx, cudaMemsetAsync(s->x, 0, nb, ctx->stream));  // x == NULL: zeros, lmbc_core.c:373
+    if (samples_prepare(ctx, s) != 0) return BRDFGPU_LM_ERROR;
+    BG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int brdfgpu_samples_upload(brdfgpu_ctx* ctx, long n, const double* cosphi, const double* t, const double* x,
+                                      int model, brdfgpu_samples** out) {
+    ctx = ctx_or_default(ctx);
+    if (!ctx || !out || (n > 0 && (!cosphi || !t))) return BRDFGPU_LM_ERROR;
+    BG_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    brdfgpu_samples* s = nullptr;
+    if (samples_alloc(ctx, n, model, &s) != 0) return BRDFGPU_LM_ERROR;
+    if (samples_fill(ctx, s, cosphi, t, x, cudaMemcpyHostToDevice) != 0) {
+        brdfgpu_samples_free(ctx, s);
+        return BRDFGPU_LM_ERROR;
+    }
+    *out = s;
+    return 0;
+}
+
+extern "C" int brdfgpu_samples_from_device(brdfgpu_ctx* ctx, long n, const double* d_cosphi, const double* d_t,
+                                           const double* d_x, int model, brdfgpu_samples** out) {
+    ctx = ctx_or_default(ctx);
+    if (!ctx || !out || (n > 0 && (!d_cosphi || !d_t))) return BRDFGPU_LM_ERROR;
+    BG_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    brdfgpu_samples* s = nullptr;
+    if (samples_alloc(ctx, n, model, &s) != 0) return BRDFGPU_LM_ERROR;
+    if (samples_fill(ctx, s, d_cosphi, d_t, d_x, cudaMemcpyDeviceToDevice) != 0) {
+        brdfgpu_samples_free(ctx, s);
+        return BRDFGPU_LM_ERROR;
+    }
+    *out = s;
+    return 0;
+}
+
+extern "C" int brdfgpu_samples_synth(brdfgpu_ctx* ctx, long n, unsigned long long seed, long start, const double truth[3],
+                                     int model, brdfgpu_samples** out) {
+    ctx = ctx_or_default(ctx);
+    if (!ctx || !out || !truth) return BRDFGPU_LM_ERROR;
+    BG_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    brdfgpu_samples* s = nullptr;
+    if (samples_alloc(ctx, n, model, &s) != 0) return BRDFGPU_LM_ERROR;
+    if (synth_samples(ctx, s, seed, start, truth) != 0 || cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        brdfgpu_samples_free(ctx, s);
+        return BRDFGPU_LM_ERROR;
+    }
+    *out = s;
+    return 0;
+}
+
+extern "C" long brdfgpu_samples_count(const brdfgpu_samples* s) { return s ? s->n : 0; }
+
+extern "C" int brdfgpu_samples_download(brdfgpu_ctx* ctx, const brdfgpu_samples* s, double* cosphi, double* t, double* x) {
+    ctx = ctx_or_default(ctx);
+    if (!ctx || !s) return BRDFGPU_LM_ERROR;
+    const size_t nb = sizeof(double) * (size_t)s->n;
+    if (cosphi) BG_CUDA_OK(ctx, cudaMemcpyAsync(cosphi, s->c, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (t) BG_CUDA_OK(ctx, cudaMemcpyAsync(t, s->traw, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (x) BG_CUDA_OK(ctx, cudaMemcpyAsync(x, s->x, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    BG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" void brdfgpu_samples_free(brdfgpu_ctx* ctx, brdfgpu_samples* s) {
+    (void)ctx;
+    if (!s) return;
+    cudaFree(s->c); cudaFree(s->L); cudaFree(s->x); cudaFree(s->traw); cudaFree(s->jac);
+    delete s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// global fits and single evaluations on resident samples
+// ------------------------------------------------------------------------------------------------
+extern "C" int brdfgpu_fit_global(brdfgpu_ctx* ctx, const brdfgpu_samples* s, double* p, int m, const double* lb,
+                                  const double* ub, const double* dscl, int itmax, const double* opts, double* info,
+                                  double* covar, int drive, int jac_mode) {
+    ctx = ctx_or_default(ctx);
+    if (!ctx || !s || !p) return BRDFGPU_LM_ERROR;
+    BG_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    return global_fit(ctx, s, p, m, lb, ub, dscl, itmax, opts, info, covar, drive, jac_mode, 0);
+}
+
+extern "C" int brdfgpu_fit_global_unc(brdfgpu_ctx* ctx, const brdfgpu_samples* s, double* p, int m, int itmax,
+                                      const double* opts, double* info, double* covar, int jac_mode) {
+    ctx = ctx_or_default(ctx);
+    if (!ctx || !s || !p) return BRDFGPU_LM_ERROR;
+    BG_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    if (jac_mode == BRDFGPU_JAC_ANALYTIC)
+        return global_fit(ctx, s, p, m, nullptr, nullptr, nullptr, itmax, opts, info, covar, BRDFGPU_DRIVE_PERSISTENT,
+                          jac_mode, 1);
+    return global_fit_secant(ctx, const_cast<brdfgpu_samples*>(s), p, m, itmax, opts, info, covar);
+}
+
+extern "C" int brdfgpu_eval_residuals(brdfgpu_ctx* ctx, const brdfgpu_samples* s, const double* p, double* e) {
+    ctx = ctx_or_default(ctx);
+    if (!ctx || !s || !p || !e) return BRDFGPU_LM_ERROR;
+    return global_residuals(ctx, s, p, e);
+}
+extern "C" int brdfgpu_eval_normal_eq(brdfgpu_ctx* ctx, const brdfgpu_samples* s, const double* p, double delta,
+                                      int jac_mode, double* out11) {
+    ctx = ctx_or_default(ctx);
+    if (!ctx || !s || !p || !out11) return BRDFGPU_LM_ERROR;
+    return global_normal_eq(ctx, s, p, delta, jac_mode, out11);
+}
+extern "C" int brdfgpu_eval_cost(brdfgpu_ctx* ctx, const brdfgpu_samples* s, const double* p, double* out2) {
+    ctx = ctx_or_default(ctx);
+    if (!ctx || !s || !p || !out2) return BRDFGPU_LM_ERROR;
+    return global_cost(ctx, s, p, out2);
+}
+extern "C" int brdfgpu_eval_repeat(brdfgpu_ctx* ctx, const brdfgpu_samples* s, const double* p, double delta, int kind,
+                                   int reps) {
+    ctx = ctx_or_default(ctx);
+    if (!ctx || !s || !p) return BRDFGPU_LM_ERROR;
+    return global_repeat(ctx, s, p, delta, kind, reps);
+}
+
+// ------------------------------------------------------------------------------------------------
+// levmar-signature entry points
+// ------------------------------------------------------------------------------------------------
+extern "C" void brdfgpu_BRDFFunc(double* p, double* hx, int m, int n, void* adata) {
+    (void)m;
+    brdfgpu_ctx* ctx = default_ctx();
+    const brdfgpu_extraData* d = static_cast<const brdfgpu_extraData*>(adata);
+    if (!ctx || !d || !d->angles) {
+        fprintf(stderr, "brdfgpu_BRDFFunc: no CUDA device or no data -- hx left untouched (there is no CPU path)\n");
+        return;
+    }
+    model_predict(ctx, p, d->angles, d->modelInfo, n, hx);
+}
+
+extern "C" void brdfgpu_BRDFJac(double* p, double* jac, int m, int n, void* adata) {
+    brdfgpu_ctx* ctx = default_ctx();
+    const brdfgpu_extraData* d = static_cast<const brdfgpu_extraData*>(adata);
+    if (!ctx || !d || !d->angles || m < 3) {
+        fprintf(stderr, "brdfgpu_BRDFJac: no CUDA device or bad arguments -- jac left untouched\n");
+        return;
+    }
+    model_jacobian(ctx, p, d->angles, d->modelInfo, n, m, jac);
+}
+
+// shared body of the four levmar-signature fits
+static int levmar_entry(const char* name, brdfgpu_func_t func, brdfgpu_jacf_t jacf, bool need_jacf, double* p, double* x,
+                        int m, int n, double* lb, double* ub, double* dscl, int itmax, double* opts, double* info,
+                        double* covar, void* adata, bool constrained) {
+    if (func != brdfgpu_BRDFFunc || (need_jacf && jacf != brdfgpu_BRDFJac)) {
+        fprintf(stderr, "%s: only the brdfgpu_BRDFFunc / brdfgpu_BRDFJac callbacks are supported (GPU path, no CPU fallback)\n",
+                name);
+        return BRDFGPU_LM_ERROR;
+    }
+    const brdfgpu_extraData* d = static_cast<const brdfgpu_extraData*>(adata);
+    if (!d || !d->angles || !p) {
+        fprintf(stderr, "%s: adata must point to a brdfgpu_extraData with angles\n", name);
+        return BRDFGPU_LM_ERROR;
+    }
+    if (n < m) {  // lmbc_core.c:440-443 / lm_core.c:113-116
+        fprintf(stderr, "%s: cannot solve a problem with fewer measurements [%d] than unknowns [%d]\n", name, n, m);
+        return BRDFGPU_LM_ERROR;
+    }
+    if (d->modelInfo != 0 && d->modelInfo != 1) {
+        fprintf(stderr, "%s: unknown model id %d\n", name, d->modelInfo);
+        return BRDFGPU_LM_ERROR;
+    }
+    brdfgpu_ctx* ctx = default_ctx();
+    if (!ctx) return BRDFGPU_LM_ERROR;
+    brdfgpu_samples* s = nullptr;
+    const double* t = d->angles + (d->modelInfo == 1 ? (size_t)n : 2 * (size_t)n);
+    if (brdfgpu_samples_upload(ctx, n, d->angles, t, x, d->modelInfo, &s) != 0) return BRDFGPU_LM_ERROR;
+    int ret;
+    const int jm = need_jacf ? BRDFGPU_JAC_ANALYTIC : BRDFGPU_JAC_FD;
+    if (constrained) ret = brdfgpu_fit_global(ctx, s, p, m, lb, ub, dscl, itmax, opts, info, covar, BRDFGPU_DRIVE_PERSISTENT, jm);
+    else ret = brdfgpu_fit_global_unc(ctx, s, p, m, itmax, opts, info, covar, jm);
+    brdfgpu_samples_free(ctx, s);
+    return ret;
+}
+
+extern "C" int brdfgpu_dlevmar_bc_dif(brdfgpu_func_t func, double* p, double* x, int m, int n, double* lb, double* ub,
+                                      double* dscl, int itmax, double* opts, double* info, double* work, double* covar,
+                                      void* adata) {
+    (void)work;
+    return levmar_entry("brdfgpu_dlevmar_bc_dif", func, nullptr, false, p, x, m, n, lb, ub, dscl, itmax, opts, info, covar,
+                        adata, true);
+}
+extern "C" int brdfgpu_dlevmar_bc_der(brdfgpu_func_t func, brdfgpu_jacf_t jacf, double* p, double* x, int m, int n,
+                                      double* lb, double* ub, double* dscl, int itmax, double* opts, double* info,
+                                      double* work, double* covar, void* adata) {
+    (void)work;
+    return levmar_entry("brdfgpu_dlevmar_bc_der", func, jacf, true, p, x, m, n, lb, ub, dscl, itmax, opts, info, covar,
+                        adata, true);
+}
+extern "C" int brdfgpu_dlevmar_dif(brdfgpu_func_t func, double* p, double* x, int m, int n, int itmax, double* opts,
+                                   double* info, double* work, double* covar, void* adata) {
+    (void)work;
+    return levmar_entry("brdfgpu_dlevmar_dif", func, nullptr, false, p, x, m, n, nullptr, nullptr, nullptr, itmax, opts,
+                        info, covar, adata, false);
+}
+extern "C" int brdfgpu_dlevmar_der(brdfgpu_func_t func, brdfgpu_jacf_t jacf, double* p, double* x, int m, int n, int itmax,
+                                   double* opts, double* info, double* work, double* covar, void* adata) {
+    (void)work;
+    return levmar_entry("brdfgpu_dlevmar_der", func, jacf, true, p, x, m, n, nullptr, nullptr, nullptr, itmax, opts, info,
+                        covar, adata, false);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the reference's fit drivers (brdfdata.cpp:991-1136) with raw pointers
+// ------------------------------------------------------------------------------------------------
+extern "C" int brdfgpu_solve_equation(const double* phi, const double* thetaDash, const double* theta, const double* I,
+                                      int nimg, int model, double* p, double* info) {
+    int ret = BRDFGPU_LM_ERROR;
+    if (brdfgpu_solve_equation_batch(nullptr, 1, nimg, phi, thetaDash, theta, I, model, p, info, &ret) != 0)
+        return BRDFGPU_LM_ERROR;
+    return ret;
+}
+
+extern "C" int brdfgpu_solve_equation_single(const double* phi, const double* thetaDash, const double* theta,
+                                             const double* I, long nsamples, int model, double* p, double* info) {
+    brdfgpu_ctx* ctx = default_ctx();
+    if (!ctx || !phi || !I || !p) return BRDFGPU_LM_ERROR;
+    const double* t = model == 1 ? thetaDash : theta;
+    if (!t) return BRDFGPU_LM_ERROR;
+    static const double lb[3] = {0, 0, 0}, ub[3] = {100, 100, 100};
+    static const double opts[5] = {1E-03, 1E-15, 1E-10, 1E-50, 1.0};  // brdfdata.cpp:1055-1056
+    brdfgpu_samples* s = nullptr;
+    if (brdfgpu_samples_upload(ctx, nsamples, phi, t, I, model, &s) != 0) return BRDFGPU_LM_ERROR;
+    p[0] = p[1] = p[2] = 0.0;  // brdfdata.cpp:1002
+    const int ret = brdfgpu_fit_global(ctx, s, p, 3, lb, ub, nullptr, 2000, opts, info, nullptr, BRDFGPU_DRIVE_PERSISTENT,
+                                       BRDFGPU_JAC_FD);
+    brdfgpu_samples_free(ctx, s);
+    return ret;
+}
+
+extern "C" int brdfgpu_solve_equation_batch(brdfgpu_ctx* ctx, long nfit, int nper, const double* phi,
+                                            const double* thetaDash, const double* theta, const double* I, int model,
+                                            double* p_out, double* info_out, int* ret_out) {
+    ctx = ctx_or_default(ctx);
+    if (!ctx || !phi || !I || !p_out) return BRDFGPU_LM_ERROR;
+    const double* t = model == 1 ? thetaDash : theta;
+    if (!t) return BRDFGPU_LM_ERROR;
+    static const double p0[3] = {0.5, 1.0, 1.0}, lb[3] = {0, 0, 0}, ub[3] = {100, 100, 100};  // brdfdata.cpp:1085,1112-1113
+    static const double opts[5] = {1E-03, 1E-15, 1E-15, 1E-20, 1E-06};                        // brdfdata.cpp:1116-1117
+    brdfgpu_batch* b = nullptr;
+    if (brdfgpu_batch_upload(ctx, nfit, nper, phi, t, I, model, &b) != 0) return BRDFGPU_LM_ERROR;
+    int rc = brdfgpu_batch_fit(ctx, b, p0, lb, ub, 100, opts, BRDFGPU_JAC_FD);
+    if (rc == 0) rc = brdfgpu_batch_results(ctx, b, p_out, info_out, ret_out);
+    brdfgpu_batch_free(ctx, b);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-resident batched problem sets
+// ------------------------------------------------------------------------------------------------
+extern "C" int brdfgpu_batch_upload(brdfgpu_ctx* ctx, long nfit, int nper, const double* cosphi, const double* t,
+                                    const double* x, int model, brdfgpu_batch** out) {
+    ctx = ctx_or_default(ctx);
+    if (!ctx || !out || (nfit > 0 && (!cosphi || !t))) return BRDFGPU_LM_ERROR;
+    BG_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    brdfgpu_batch* b = nullptr;
+    if (batch_alloc(ctx, nfit, nper, model, &b) != 0) return BRDFGPU_LM_ERROR;
+    const size_t nb = sizeof(double) * (size_t)nfit * nper;
+    cudaError_t e = cudaSuccess;
+    if (nb) {
+        e = cudaMemcpyAsync(b->c, cosphi, nb, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(b->traw, t, nb, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess)
+            e = x ? cudaMemcpyAsync(b->x, x, nb, cudaMemcpyHostToDevice, ctx->stream) : cudaMemsetAsync(b->x, 0, nb, ctx->stream);
+    }
+    if (e != cudaSuccess || batch_prepare(ctx, b) != 0 || cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        if (e != cudaSuccess) set_error(ctx, std::string("batch_upload: ") + cudaGetErrorString(e));
+        brdfgpu_batch_free(ctx, b);
+        return BRDFGPU_LM_ERROR;
+    }
+    *out = b;
+    return 0;
+}
+
+extern "C" int brdfgpu_batch_synth(brdfgpu_ctx* ctx, long nfit, int nper, unsigned long long seed, long first_fit,
+                                   int model, brdfgpu_batch** out) {
+    ctx = ctx_or_default(ctx);
+    if (!ctx || !out) return BRDFGPU_LM_ERROR;
+    BG_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    brdfgpu_batch* b = nullptr;
+    if (batch_alloc(ctx, nfit, nper, model, &b) != 0) return BRDFGPU_LM_ERROR;
+    if (synth_batch(ctx, b, seed, first_fit) != 0 || cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        brdfgpu_batch_free(ctx, b);
+        return BRDFGPU_LM_ERROR;
+    }
+    *out = b;
+    return 0;
+}
+
+extern "C" int brdfgpu_batch_fit(brdfgpu_ctx* ctx, brdfgpu_batch* b, const double* p0, const double* lb, const double* ub,
+                                 int itmax, const double* opts, int jac_mode) {
+    ctx = ctx_or_default(ctx);
+    if (!ctx || !b || !p0) return BRDFGPU_LM_ERROR;
+    BG_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    return batch_fit(ctx, b, p0, lb, ub, itmax, opts, jac_mode);
+}
+
+extern "C" int brdfgpu_batch_results(brdfgpu_ctx* ctx, const brdfgpu_batch* b, double* p_out, double* info_out,
+                                     int* ret_out) {
+    ctx = ctx_or_default(ctx);
+    if (!ctx || !b) return BRDFGPU_LM_ERROR;
+    const size_t nf = (size_t)b->nfit;
+    if (p_out && nf) BG_CUDA_OK(ctx, cudaMemcpyAsync(p_out, b->p, sizeof(double) * 3 * nf, cudaMemcpyDeviceToHost, ctx->stream));
+    if (info_out && nf)
+        BG_CUDA_OK(ctx, cudaMemcpyAsync(info_out, b->info, sizeof(double) * 10 * nf, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ret_out && nf) BG_CUDA_OK(ctx, cudaMemcpyAsync(ret_out, b->ret, sizeof(int) * nf, cudaMemcpyDeviceToHost, ctx->stream));
+    BG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" long brdfgpu_batch_count(const brdfgpu_batch* b) { return b ? b->nfit : 0; }
+
+extern "C" void brdfgpu_batch_free(brdfgpu_ctx* ctx, brdfgpu_batch* b) {
+    (void)ctx;
+    if (!b) return;
+    cudaFree(b->c); cudaFree(b->L); cudaFree(b->x); cudaFree(b->traw); cudaFree(b->p); cudaFree(b->info); cudaFree(b->ret);
+    delete b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the LM control loop on caller-supplied reduced evaluators (host instantiation of lm_engine.cuh)
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct CallbackEval {
+    brdfgpu_reduced_jac_t jac_cb;
+    brdfgpu_reduced_cost_t cost_cb;
+    void* user;
+    int m;
+    void jac(const double* p, double* JtJ, double* Jte) { jac_cb(p, m, JtJ, Jte, user); }
+    double cost(const double* p, bool& bad) {
+        double nonfinite = 0.0;
+        const double e = cost_cb(p, m, &nonfinite, user);
+        bad = nonfinite != 0.0;
+        return e;
+    }
+};
+}  // namespace
+
+extern "C" int brdfgpu_lm_bc_reduced(brdfgpu_reduced_jac_t jac_cb, brdfgpu_reduced_cost_t cost_cb, void* user, double* p,
+                                     int m, long n, const double* lb, const double* ub, const double* dscl, int itmax,
+                                     const double* opts, double* info, double* covar) {
+    if (!jac_cb || !cost_cb || !p || m < 1 || m > kMaxM || n < m) return BRDFGPU_LM_ERROR;
+    if (lb && ub)
+        for (int i = 0; i < m; ++i)
+            if (lb[i] > ub[i]) return BRDFGPU_LM_ERROR;
+    if (dscl)
+        for (int i = 0; i < m; ++i)
+            if (dscl[i] <= 0.0) return BRDFGPU_LM_ERROR;
+    double lbs[kMaxM], ubs[kMaxM], JtJ[kMaxM * kMaxM], fit_info[10];
+    for (int i = 0; i < m; ++i) {
+        if (lb) lbs[i] = dscl ? lb[i] / dscl[i] : lb[i];
+        if (ub) ubs[i] = dscl ? ub[i] / dscl[i] : ub[i];
+    }
+    const Box box{lb, ub};
+    box_project(p, box, m);
+    CallbackEval ev{jac_cb, cost_cb, user, m};
+    const int ret = lm_bc_der<kMaxM>(ev, m, p, lb ? lbs : nullptr, ub ? ubs : nullptr, dscl, lm_options(opts, itmax),
+                                     fit_info, JtJ);
+    if (info)
+        for (int i = 0; i < 10; ++i) info[i] = fit_info[i];
+    if (covar) {
+        lm_covar<kMaxM>(JtJ, covar, fit_info[1], m, n);
+        if (dscl)
+            for (int i = 0; i < m; ++i)
+                for (int j = 0; j < m; ++j) covar[i * m + j] *= dscl[i] * dscl[j];
+    }
+    return ret;
+}
+
+extern "C" int brdfgpu_lm_unc_reduced(brdfgpu_reduced_jac_t jac_cb, brdfgpu_reduced_cost_t cost_cb, void* user, double* p,
+                                      int m, long n, int itmax, const double* opts, double* info, double* covar) {
+    if (!jac_cb || !cost_cb || !p || m < 1 || m > kMaxM || n < m) return BRDFGPU_LM_ERROR;
+    double JtJ[kMaxM * kMaxM], fit_info[10];
+    CallbackEval ev{jac_cb, cost_cb, user, m};
+    const int ret = lm_der<kMaxM>(ev, m, p, lm_options(opts, itmax), fit_info, JtJ);
+    if (info)
+        for (int i = 0; i < 10; ++i) info[i] = fit_info[i];
+    if (covar) lm_covar<kMaxM>(JtJ, covar, fit_info[1], m, n);
+    return ret;
+}
+
+extern "C" int brdfgpu_Ax_eq_b_LU(const double* A, const double* B, double* x, int m) {
+    if (!A || !B || !x || m < 1 || m > kMaxM) return 0;
+    return solve_lu<kMaxM>(A, B, x, m);
+}

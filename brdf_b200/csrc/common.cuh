@@ -12,11 +12,9 @@
 namespace brdfgpu {
 
 constexpr int kMaxM = BRDFGPU_MAX_PARAMS;
-constexpr int kPassThreads = 256;     // threads per CTA of the streaming passes
-constexpr int kMaxPassBlocks = 2048;  // upper bound on CTAs of one pass (partials buffer)
-constexpr int kResultDoubles = 16;    // >= NACC
-
-struct NcclApi;  // comm.cu
+constexpr int kPassThreads = 256;    // threads per CTA of the streaming passes
+constexpr int kMaxPassBlocks = 2048; // upper bound on CTAs of one pass (partials buffer)
+constexpr int kResultDoubles = 16;   // >= NACC
 
 }  // namespace brdfgpu
 
@@ -24,22 +22,30 @@ struct NcclApi;  // comm.cu
 struct brdfgpu_ctx {
     int device = 0;
     int sm_count = 0;
+    int coop = 0;  // cooperative launch supported
     cudaStream_t stream = nullptr;
     std::string err;
     unsigned long long launches = 0;
 
     // reduction scratch of the streaming passes
-    double* d_partials = nullptr;  // kMaxPassBlocks x kResultDoubles
-    unsigned* d_sync = nullptr;    // [0] ticket, [1] flag, ...
-    double* d_result = nullptr;    // kResultDoubles (+ fit output block)
-    double* h_result = nullptr;    // pinned mirror
+    double* d_partials = nullptr;  // 2 x kMaxPassBlocks x kResultDoubles (double-buffered)
+    unsigned* d_sync = nullptr;    // [0] ticket of the "last block done" reduction
+    double* d_result = nullptr;    // kResultDoubles
+    double* h_result = nullptr;    // pinned + mapped mirror the last block writes directly
+    double* h_result_dev = nullptr;           // device alias of h_result
+    volatile unsigned long long* h_seq = nullptr;  // pinned + mapped completion ticket
+    unsigned long long* h_seq_dev = nullptr;
+    unsigned long long seq = 0;
     // persistent-fit in/out block
     void* d_fitio = nullptr;
     void* h_fitio = nullptr;  // pinned
+    int persistent_blocks_per_sm = 0;
 
     // multi-GPU
     void* nccl_comm = nullptr;
     int rank = 0, nranks = 1;
+    // peer-memory exchange (fused one-shot all-reduce inside the fit kernels)
+    void* peer = nullptr;
 };
 
 struct brdfgpu_samples {
@@ -49,7 +55,8 @@ struct brdfgpu_samples {
     double* L = nullptr;     // log(t), NaN = take the pow() path
     double* x = nullptr;     // measurements
     double* traw = nullptr;  // raw model cosine (read only on the pow() path)
-    bool owns = true;
+    // secant (dlevmar_dif) state: stored Jacobian, 3 columns SoA, allocated on first use
+    double* jac = nullptr;
 };
 
 struct brdfgpu_batch {
@@ -60,7 +67,6 @@ struct brdfgpu_batch {
     double* p = nullptr;     // nfit x 3
     double* info = nullptr;  // nfit x 10
     int* ret = nullptr;      // nfit
-    bool owns = true;
 };
 
 namespace brdfgpu {
@@ -87,11 +93,12 @@ inline int pass_blocks(const brdfgpu_ctx* ctx, long n, int ctas_per_sm) {
     return (int)(want < cap ? want : cap);
 }
 
-// ---- implemented in global_fit.cu ----
+// ---- global_fit.cu ----
 struct GlobalFitSpec {
-    int m, itmax, jac_mode, has_lb, has_ub, has_dscl, has_opts;
-    double delta;
-    double p[kMaxM], lb[kMaxM], ub[kMaxM], dscl[kMaxM], opts[5];
+    int m, itmax, jac_mode, has_lb, has_ub, has_dscl, unconstrained;
+    double delta;  // |opts[4]|
+    double p[kMaxM], lb[kMaxM], ub[kMaxM], dscl[kMaxM];
+    LmOptions opt;
 };
 struct GlobalFitOut {
     int ret;
@@ -102,15 +109,16 @@ struct GlobalFitOut {
 
 int samples_alloc(brdfgpu_ctx* ctx, long n, int model, brdfgpu_samples** out);
 int samples_prepare(brdfgpu_ctx* ctx, brdfgpu_samples* s);  // L from traw
-int global_normal_eq(brdfgpu_ctx* ctx, const brdfgpu_samples* s, const double* p, double delta,
-                     int jac_mode, double* out11, bool sync);
-int global_cost(brdfgpu_ctx* ctx, const brdfgpu_samples* s, const double* p, double* out2, bool sync);
+int global_normal_eq(brdfgpu_ctx* ctx, const brdfgpu_samples* s, const double* p, double delta, int jac_mode,
+                     double* out11);
+int global_cost(brdfgpu_ctx* ctx, const brdfgpu_samples* s, const double* p, double* out2);
+int global_repeat(brdfgpu_ctx* ctx, const brdfgpu_samples* s, const double* p, double delta, int kind, int reps);
 int global_residuals(brdfgpu_ctx* ctx, const brdfgpu_samples* s, const double* p, double* e_host);
-int global_fit_bc(brdfgpu_ctx* ctx, const brdfgpu_samples* s, double* p, int m, const double* lb,
-                  const double* ub, const double* dscl, int itmax, const double* opts, double* info,
-                  double* covar, int drive, int jac_mode);
-int global_fit_unc(brdfgpu_ctx* ctx, const brdfgpu_samples* s, double* p, int m, int itmax,
-                   const double* opts, double* info, double* covar, int jac_mode);
+int global_fit(brdfgpu_ctx* ctx, const brdfgpu_samples* s, double* p, int m, const double* lb, const double* ub,
+               const double* dscl, int itmax, const double* opts, double* info, double* covar, int drive,
+               int jac_mode, int unconstrained);
+int global_fit_secant(brdfgpu_ctx* ctx, brdfgpu_samples* s, double* p, int m, int itmax, const double* opts,
+                      double* info, double* covar);
 int model_predict(brdfgpu_ctx* ctx, const double* p, const double* angles_host, int model, int n, double* hx_host);
 int model_jacobian(brdfgpu_ctx* ctx, const double* p, const double* angles_host, int model, int n, int m,
                    double* jac_host);
@@ -122,8 +130,8 @@ int synth_batch(brdfgpu_ctx* ctx, brdfgpu_batch* b, unsigned long long seed, lon
 // ---- batched_fit.cu ----
 int batch_alloc(brdfgpu_ctx* ctx, long nfit, int nper, int model, brdfgpu_batch** out);
 int batch_prepare(brdfgpu_ctx* ctx, brdfgpu_batch* b);
-int batch_fit(brdfgpu_ctx* ctx, brdfgpu_batch* b, const double* p0, const double* lb, const double* ub,
-              int itmax, const double* opts, int jac_mode);
+int batch_fit(brdfgpu_ctx* ctx, brdfgpu_batch* b, const double* p0, const double* lb, const double* ub, int itmax,
+              const double* opts, int jac_mode);
 
 // ---- comm.cu ----
 int comm_allreduce_device(brdfgpu_ctx* ctx, double* d_buf, int count);

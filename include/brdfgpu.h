@@ -94,6 +94,8 @@ const char *brdfgpu_last_error(brdfgpu_ctx *ctx);
 unsigned long long brdfgpu_launch_count(brdfgpu_ctx *ctx);
 /* CUDA stream (cudaStream_t) the context launches on, for timing with CUDA events */
 void *brdfgpu_stream(brdfgpu_ctx *ctx);
+/* wait for everything queued on that stream */
+int brdfgpu_synchronize(brdfgpu_ctx *ctx);
 
 /* Sample set for a global fit: n samples (cosphi_i, t_i, x_i) with t = costhetadash (Blinn-Phong)
  * or costheta (Phong), i.e. the two angle blocks BRDFFunc reads for `model`
@@ -182,6 +184,7 @@ int brdfgpu_batch_fit(brdfgpu_ctx *ctx, brdfgpu_batch *b, const double *p0, cons
                       const double *ub, int itmax, const double *opts, int jac_mode);
 int brdfgpu_batch_results(brdfgpu_ctx *ctx, const brdfgpu_batch *b, double *p_out, double *info_out,
                           int *ret_out);
+long brdfgpu_batch_count(const brdfgpu_batch *b);
 void brdfgpu_batch_free(brdfgpu_ctx *ctx, brdfgpu_batch *b);
 
 /* ------------------------------------------------------------------------------------------------
@@ -192,6 +195,9 @@ typedef struct brdfgpu_scene brdfgpu_scene;
 /* camera = {cx, cy, f, sx, nx,ny,nz, ox,oy,oz, ax,ay,az, px,py,pz}: the .cal fields
  * CBRDFdata::WriteValue keeps (brdfdata.cpp:195-247) */
 #define BRDFGPU_CAM_SZ 16
+
+/* CBRDFdata::InitLEDs (brdfdata.cpp:683-756): the 16 hard-coded LED positions, 16 x 3 row-major */
+void brdfgpu_led_table(double *led16x3);
 
 /* Mesh + photographs resident on the device.  V: nV x 3 fp64 row-major, F: nF x 3 int32 vertex
  * ids (m_vertices/m_faces of brdfdata.h), images: nimg pointers to H x W x 3 u8 BGR (cv::imread
