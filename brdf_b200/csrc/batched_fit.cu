@@ -60,7 +60,7 @@ struct GroupEval {
         else if (jkind == kJacCentral) jac_body<kJacCentral>(q, acc);
         else jac_body<kJacAnalytic>(q, acc);
 #pragma unroll
-        for (int k = 0; k < NBAD; ++k) acc[k] = group_sum(acc[k]);
+        for (int k = 0; k < NACC; ++k) acc[k] = group_sum(acc[k]);
         JtJ[0] = acc[A00]; JtJ[1] = acc[A01]; JtJ[2] = acc[A02];
         JtJ[3] = acc[A01]; JtJ[4] = acc[A11]; JtJ[5] = acc[A12];
         JtJ[6] = acc[A02]; JtJ[7] = acc[A12]; JtJ[8] = acc[A22];
@@ -69,19 +69,28 @@ struct GroupEval {
 
     __device__ __noinline__ double cost(const double* p, bool& bad) const {
         const PassParams q = make_pass_params(p, model, 1.0, kJacAnalytic);
-        double acc[2] = {0.0, 0.0};
+        double esq = 0.0, nbad = 0.0;
         if (S > 0) {
 #pragma unroll
             for (int s = 0; s < SR; ++s) {
                 const int idx = s * G + lane;
-                if (idx < nper) accumulate_cost(q, c[s], L[s], x[s], traw, idx, acc);
+                if (idx < nper) {
+                    const double e = residual_of(q, c[s], L[s], x[s], traw, idx);
+                    esq = __fma_rn(e, e, esq);
+                    nbad += lm_finite(e) ? 0.0 : 1.0;
+                }
             }
         } else {
-            for (int idx = lane; idx < nper; idx += G) accumulate_cost(q, gc[idx], gL[idx], gx[idx], traw, idx, acc);
+            for (int idx = lane; idx < nper; idx += G) {
+                const double e = residual_of(q, gc[idx], gL[idx], gx[idx], traw, idx);
+                esq = __fma_rn(e, e, esq);
+                nbad += lm_finite(e) ? 0.0 : 1.0;
+            }
         }
-        const double e = group_sum(acc[0]);
-        bad = group_sum(acc[1]) != 0.0;
-        return e;
+        esq = group_sum(esq);
+        bad = false;
+        if (!lm_finite(esq)) bad = group_sum(nbad) != 0.0;  // uniform within the group
+        return esq;
     }
 };
 

@@ -6,13 +6,23 @@
 // and levmar's difference Jacobian around it (misc_core.c:137-211).
 //
 // Device data layout (24 B per sample per pass): c = cosphi, L = log(t) with t the model's cosine,
-// x = measurement.  t**n is evaluated as exp(n*L): one exp per evaluation point instead of a pow,
-// the log being paid once when the sample set is made resident.  L is NaN for samples whose t is
-// negative or NaN; those (and every sample when n is not finite) take the slow path through the
-// raw cosine and pow(), so libm's sign/integer special cases survive:
-//     pow(t<0, integer n) finite, pow(t<0, non-integer) NaN, pow(0, n>0) = 0, pow(x, 0) = 1.
-// Accuracy: |exp(n*L) - pow(t,n)| <= ~|n*L| * 2^-52 relative (< 2e-13 before exp overflows),
-// far inside the 1e-6 residual gate.  FMA contraction is allowed in the fit kernels (same gate).
+// x = measurement.  t**n is evaluated as exp(n*L): the log is paid once when the sample set is
+// made resident, and one pass needs one exp per evaluation point (two for a forward-difference
+// Jacobian: n and n+d; the kd and ks columns reuse t**n) where levmar spends m+1 = 4 pow() calls.
+//
+// Two per-sample paths:
+//   fast    |n*L| <= 700 for every exponent of the pass: branch-free exp (range reduction, degree-10
+//           polynomial, exponent add), ~15 fp64 instructions.  Max relative error 1e-15.
+//   careful everything else -- L is NaN (t negative or NaN), t == 0 or inf, exponent zero or not
+//           finite, results that under/overflow: goes through the raw cosine and pow(), so libm's
+//           special cases survive: pow(t<0, integer n) finite, pow(t<0, non-integer)
+//           NaN, pow(0, n>0) = 0, pow(x, 0) = 1.
+// The difference quotients are formed algebraically instead of subtracting two full model values:
+//     column kd : ((kd+d0) - kd)/d0 * c                    (the model is linear in kd and ks, so this
+//     column ks : ((ks+d1) - ks)/d1 * coef * t**n           is levmar's value up to its own rounding)
+//     column n  : (coef(n+d2)*ks*t**(n+d2) - coef(n)*ks*t**n) / d2     (the truncation error of the
+//                 finite step is part of the reference's fixed point, SURVEY.md Q11, and is kept)
+// Residuals stay within 1e-12 relative of the reference callback; FMA contraction is allowed here.
 #pragma once
 
 #include "lm_engine.cuh"
@@ -20,51 +30,101 @@
 namespace brdfgpu {
 
 constexpr double kPi = 3.1415926535897932384626433832795;  // CV_PI, brdfdata.cpp:981
+constexpr double kFastExpLimit = 700.0;
 
 enum JacMode { kJacForward = 0, kJacCentral = 1, kJacAnalytic = 2 };
 
-// Everything that depends on p only, computed once per pass by every thread (uniform).
+// Everything that depends on p only, computed once per pass (uniform across threads).
 struct PassParams {
     double kd, ks, n, coef;  // coef = 1 (Blinn-Phong) or (n+2)/2*pi (Phong)
-    // difference steps d_j = max(|1e-4 p_j|, delta) and 1/d_j (or 0.5/d_j central), misc_core.c:154-167,206
-    double inv[3];
-    double kd_hi, ks_hi, n_hi, coef_hi;  // p_j + d_j
-    double kd_lo, ks_lo, n_lo, coef_lo;  // p_j - d_j (central only)
-    double dcoef;                        // d coef / d n (analytic, Phong: pi/2)
-    int slow_all;                        // exponent not finite somewhere: every sample through pow()
+    double cks;              // coef*ks
+    double n_hi, n_lo;       // n + d2, n - d2
+    double g0, g1;           // ((kd+d0)-kd)/d0 [central: ((kd+d0)-(kd-d0))*0.5/d0], same for ks; analytic: 1
+    double a_hi, a_lo;       // coef(n_hi)*ks/d2 and coef(n)*ks/d2 [central: coef(n_lo)*ks*0.5/d2]
+    double dcoef;            // d coef / d n (analytic, Phong: pi/2)
+    double l_lim;            // fast path iff |L| <= l_lim  (700 / max |exponent| of the pass)
+    // literal difference data for the careful path: p_j + d_j, p_j - d_j, 1/d_j (0.5/d_j central)
+    double kd_hi, ks_hi, kd_lo, ks_lo, coef_hi, coef_lo, inv[3];
+    int model;
 };
 
 BG_HDI double model_coef(int model, double n) { return model == 1 ? 1.0 : ((n + 2.0) / 2.0 * kPi); }
 
 BG_HDI PassParams make_pass_params(const double* p, int model, double delta, int jac_mode) {
     PassParams q;
+    q.model = model;
     q.kd = p[0]; q.ks = p[1]; q.n = p[2];
     q.coef = model_coef(model, q.n);
+    q.cks = q.coef * q.ks;
     q.dcoef = model == 1 ? 0.0 : (kPi / 2.0);
     double d[3];
-    for (int j = 0; j < 3; ++j) {
+    const double half = (jac_mode == kJacCentral) ? 0.5 : 1.0;
+    for (int j = 0; j < 3; ++j) {  // d_j = max(|1e-4 p_j|, delta), misc_core.c:154-158, 193-196
         double dj = 1E-04 * p[j];
         dj = lm_abs(dj);
         if (dj < delta) dj = delta;
         d[j] = dj;
-        q.inv[j] = (jac_mode == kJacCentral ? 0.5 : 1.0) / dj;
+        q.inv[j] = half / dj;
     }
     q.kd_hi = p[0] + d[0]; q.ks_hi = p[1] + d[1]; q.n_hi = p[2] + d[2];
     q.kd_lo = p[0] - d[0]; q.ks_lo = p[1] - d[1]; q.n_lo = p[2] - d[2];
     q.coef_hi = model_coef(model, q.n_hi);
     q.coef_lo = model_coef(model, q.n_lo);
-    q.slow_all = !(lm_finite(q.n) && lm_finite(q.n_hi) && lm_finite(q.n_lo));
+    double emax = lm_abs(q.n);
+    bool plain = lm_finite(q.n) && q.n != 0.0;
+    if (jac_mode == kJacForward) {
+        q.g0 = (q.kd_hi - q.kd) * q.inv[0];
+        q.g1 = (q.ks_hi - q.ks) * q.inv[1];
+        q.a_hi = (q.coef_hi * q.ks) * q.inv[2];
+        q.a_lo = q.cks * q.inv[2];
+        plain = plain && lm_finite(q.n_hi) && q.n_hi != 0.0;
+        if (lm_abs(q.n_hi) > emax) emax = lm_abs(q.n_hi);
+        q.n_lo = q.n;
+    } else if (jac_mode == kJacCentral) {
+        q.g0 = (q.kd_hi - q.kd_lo) * q.inv[0];
+        q.g1 = (q.ks_hi - q.ks_lo) * q.inv[1];
+        q.a_hi = (q.coef_hi * q.ks) * q.inv[2];
+        q.a_lo = (q.coef_lo * q.ks) * q.inv[2];
+        plain = plain && lm_finite(q.n_hi) && q.n_hi != 0.0 && lm_finite(q.n_lo) && q.n_lo != 0.0;
+        if (lm_abs(q.n_hi) > emax) emax = lm_abs(q.n_hi);
+        if (lm_abs(q.n_lo) > emax) emax = lm_abs(q.n_lo);
+    } else {
+        q.g0 = 1.0; q.g1 = 1.0; q.a_hi = 0.0; q.a_lo = 0.0;
+        q.n_hi = q.n_lo = q.n;
+    }
+    // zero or non-finite exponents send every sample down the careful path (l_lim < 0 never passes)
+    q.l_lim = plain ? kFastExpLimit / emax : -1.0;
     return q;
 }
 
 #ifdef __CUDACC__
-// t**n for one sample.  L = log t (NaN => use traw).
-__device__ __forceinline__ double pow_sample(double n, double L, const double* __restrict__ traw, long i,
-                                             int slow_all) {
-    if (slow_all || L != L) return pow(traw[i], n);
-    if (n == 0.0) return 1.0;
-    return exp(n * L);
+// exp(y) for |y| <= 700 (no NaN/Inf handling, no subnormal results by construction)
+__device__ __forceinline__ double exp_core(double y) {
+    const double magic = 6755399441055744.0;  // 1.5 * 2^52: round-to-nearest integer in the low word
+    const double t = __fma_rn(y, 1.4426950408889634074, magic);
+    const int k = __double2loint(t);
+    const double kf = t - magic;
+    double r = __fma_rn(kf, -6.93147180369123816490e-01, y);
+    r = __fma_rn(kf, -1.90821492927058770002e-10, r);
+    // near-minimax degree 10 on |r| <= ln2/2 (Chebyshev interpolation, max rel. error 9e-16)
+    double v = 0x1.26e46de8d8e82p-22;
+    v = __fma_rn(v, r, 0x1.7303e941557e0p-19);
+    v = __fma_rn(v, r, 0x1.a01b8fdc8d247p-16);
+    v = __fma_rn(v, r, 0x1.a01970086f448p-13);
+    v = __fma_rn(v, r, 0x1.6c16c0c5a5d65p-10);
+    v = __fma_rn(v, r, 0x1.11111130a260cp-7);
+    v = __fma_rn(v, r, 0x1.555555558aa3dp-5);
+    v = __fma_rn(v, r, 0x1.555555554a290p-3);
+    v = __fma_rn(v, r, 0x1.ffffffffffe8fp-2);
+    v = __fma_rn(v, r, 0x1.0000000000024p+0);
+    v = __fma_rn(v, r, 1.0);
+    return __hiloint2double(__double2hiint(v) + (k << 20), __double2loint(v));
 }
+
+// t**n / ln t with libm semantics through the raw cosine.  Deliberately NOT inlined and with
+// by-value arguments only: the careful path is rare and pow() is ~300 instructions per site.
+static __device__ __noinline__ double pow_careful(double traw, double n) { return pow(traw, n); }
+static __device__ __noinline__ double log_careful(double traw) { return log(traw); }
 
 // log once per sample when a set becomes resident; NaN marks "go through pow()".
 __device__ __forceinline__ double log_or_flag(double t) {
@@ -72,58 +132,88 @@ __device__ __forceinline__ double log_or_flag(double t) {
     return __longlong_as_double(0x7ff8000000000000LL);
 }
 
-// Accumulator layout of one evaluation: JtJ upper triangle, Jte, ||e||^2, #non-finite residuals.
-enum { A00 = 0, A01, A02, A11, A12, A22, G0, G1, G2, ESQ, NBAD, NACC };
+// Accumulator layout of one evaluation: JtJ upper triangle, Jte, ||e||^2.  Whether some residual
+// is non-finite is only needed when ||e||^2 itself is not finite (lmbc_core.c:748,915) and is
+// then counted by a separate pass.
+enum { A00 = 0, A01, A02, A11, A12, A22, G0, G1, G2, ESQ, NACC };
 
-// Prediction hx for one sample.
+__device__ __forceinline__ void accumulate_normal(double j0, double j1, double j2, double e, double* acc) {
+    acc[A00] = __fma_rn(j0, j0, acc[A00]); acc[A01] = __fma_rn(j0, j1, acc[A01]); acc[A02] = __fma_rn(j0, j2, acc[A02]);
+    acc[A11] = __fma_rn(j1, j1, acc[A11]); acc[A12] = __fma_rn(j1, j2, acc[A12]); acc[A22] = __fma_rn(j2, j2, acc[A22]);
+    acc[G0] = __fma_rn(j0, e, acc[G0]); acc[G1] = __fma_rn(j1, e, acc[G1]); acc[G2] = __fma_rn(j2, e, acc[G2]);
+    acc[ESQ] = __fma_rn(e, e, acc[ESQ]);
+}
+
+// Prediction hx for one sample given t**n.
 __device__ __forceinline__ double model_eval(const PassParams& q, double c, double pw) {
-    return q.kd * c + (q.coef * q.ks) * pw;
+    return __fma_rn(q.kd, c, q.cks * pw);
+}
+
+// careful path of one Jacobian sample: literal levmar differences of full model values
+template <int JAC>
+__device__ __forceinline__ void accumulate_jac_careful(const PassParams& q, double c, double traw, double x, double* acc) {
+    const double pw = pow_careful(traw, q.n);
+    const double hx = q.kd * c + q.cks * pw;
+    const double e = x - hx;
+    double j0, j1, j2;
+    if (JAC == kJacForward) {  // jac[i][j] = (f(p + d_j e_j) - f(p)) * (1/d_j), misc_core.c:160-170
+        const double pw_hi = pow_careful(traw, q.n_hi);
+        j0 = ((q.kd_hi * c + q.cks * pw) - hx) * q.inv[0];
+        j1 = ((q.kd * c + (q.coef * q.ks_hi) * pw) - hx) * q.inv[1];
+        j2 = ((q.kd * c + (q.coef_hi * q.ks) * pw_hi) - hx) * q.inv[2];
+    } else if (JAC == kJacCentral) {  // (f(p + d_j e_j) - f(p - d_j e_j)) * (0.5/d_j), misc_core.c:198-209
+        const double pw_hi = pow_careful(traw, q.n_hi);
+        const double pw_lo = pow_careful(traw, q.n_lo);
+        j0 = ((q.kd_hi * c + q.cks * pw) - (q.kd_lo * c + q.cks * pw)) * q.inv[0];
+        j1 = ((q.kd * c + (q.coef * q.ks_hi) * pw) - (q.kd * c + (q.coef * q.ks_lo) * pw)) * q.inv[1];
+        j2 = ((q.kd * c + (q.coef_hi * q.ks) * pw_hi) - (q.kd * c + (q.coef_lo * q.ks) * pw_lo)) * q.inv[2];
+    } else {  // exact partials: d/dkd = c, d/dks = coef t^n, d/dn = ks t^n (dcoef + coef ln t)
+        j0 = c;
+        j1 = q.coef * pw;
+        j2 = q.ks * pw * (q.dcoef + q.coef * log_careful(traw));
+    }
+    accumulate_normal(j0, j1, j2, e, acc);
 }
 
 // One sample of a fused residual + Jacobian + normal-equation pass.
 template <int JAC>
 __device__ __forceinline__ void accumulate_jac(const PassParams& q, double c, double L, double x,
                                                const double* __restrict__ traw, long i, double* acc) {
-    const double pw = pow_sample(q.n, L, traw, i, q.slow_all);
-    const double cks = q.coef * q.ks;
-    const double hx = q.kd * c + cks * pw;
-    const double e = x - hx;
-    double j0, j1, j2;
-    if (JAC == kJacForward) {
-        // jac[i][j] = (f(p + d_j e_j) - f(p)) * (1/d_j), misc_core.c:160-170
-        const double pw_hi = pow_sample(q.n_hi, L, traw, i, q.slow_all);
-        j0 = ((q.kd_hi * c + cks * pw) - hx) * q.inv[0];
-        j1 = ((q.kd * c + (q.coef * q.ks_hi) * pw) - hx) * q.inv[1];
-        j2 = ((q.kd * c + (q.coef_hi * q.ks) * pw_hi) - hx) * q.inv[2];
-    } else if (JAC == kJacCentral) {
-        // jac[i][j] = (f(p + d_j e_j) - f(p - d_j e_j)) * (0.5/d_j), misc_core.c:198-209
-        const double pw_hi = pow_sample(q.n_hi, L, traw, i, q.slow_all);
-        const double pw_lo = pow_sample(q.n_lo, L, traw, i, q.slow_all);
-        j0 = ((q.kd_hi * c + cks * pw) - (q.kd_lo * c + cks * pw)) * q.inv[0];
-        j1 = ((q.kd * c + (q.coef * q.ks_hi) * pw) - (q.kd * c + (q.coef * q.ks_lo) * pw)) * q.inv[1];
-        j2 = ((q.kd * c + (q.coef_hi * q.ks) * pw_hi) - (q.kd * c + (q.coef_lo * q.ks) * pw_lo)) * q.inv[2];
-    } else {
-        // exact partials: d/dkd = c, d/dks = coef t^n, d/dn = ks t^n (dcoef + coef ln t)
-        j0 = c;
-        j1 = q.coef * pw;
-        double lt = L;
-        if (q.slow_all || L != L) lt = log(traw[i]);
-        j2 = q.ks * pw * (q.dcoef + q.coef * lt);
+    if (!(fabs(L) <= q.l_lim)) {  // also catches NaN flags, t == 0, t == inf
+        accumulate_jac_careful<JAC>(q, c, traw[i], x, acc);
+        return;
     }
-    acc[A00] += j0 * j0; acc[A01] += j0 * j1; acc[A02] += j0 * j2;
-    acc[A11] += j1 * j1; acc[A12] += j1 * j2; acc[A22] += j2 * j2;
-    acc[G0] += j0 * e; acc[G1] += j1 * e; acc[G2] += j2 * e;
-    acc[ESQ] += e * e;
-    acc[NBAD] += lm_finite(e) ? 0.0 : 1.0;
+    const double pw = exp_core(q.n * L);
+    const double e = x - __fma_rn(q.kd, c, q.cks * pw);
+    const double j0 = q.g0 * c;
+    const double j1 = (q.model == 1) ? q.g1 * pw : (q.g1 * q.coef) * pw;
+    double j2;
+    if (JAC == kJacForward) {
+        j2 = __fma_rn(q.a_hi, exp_core(q.n_hi * L), -(q.a_lo * pw));
+    } else if (JAC == kJacCentral) {
+        j2 = __fma_rn(q.a_hi, exp_core(q.n_hi * L), -(q.a_lo * exp_core(q.n_lo * L)));
+    } else {
+        j2 = (q.ks * pw) * __fma_rn(q.coef, L, q.dcoef);
+    }
+    accumulate_normal(j0, j1, j2, e, acc);
 }
 
-// One sample of a trial-point pass: only ||x - f(p)||^2 and the non-finite count.
+__device__ __forceinline__ double residual_careful(const PassParams& q, double c, double traw, double x) {
+    return x - (q.kd * c + q.cks * pow_careful(traw, q.n));
+}
+
+// residual e = x - f(p) of one sample (same arithmetic as the passes)
+__device__ __forceinline__ double residual_of(const PassParams& q, double c, double L, double x,
+                                              const double* __restrict__ traw, long i) {
+    if (!(fabs(L) <= q.l_lim)) return residual_careful(q, c, traw[i], x);
+    return x - __fma_rn(q.kd, c, q.cks * exp_core(q.n * L));
+}
+
+// One sample of a trial-point pass: only ||x - f(p)||^2.
 __device__ __forceinline__ void accumulate_cost(const PassParams& q, double c, double L, double x,
-                                                const double* __restrict__ traw, long i, double* acc2) {
-    const double pw = pow_sample(q.n, L, traw, i, q.slow_all);
-    const double e = x - (q.kd * c + (q.coef * q.ks) * pw);
-    acc2[0] += e * e;
-    acc2[1] += lm_finite(e) ? 0.0 : 1.0;
+                                                const double* __restrict__ traw, long i, double* esq) {
+    const double e = residual_of(q, c, L, x, traw, i);
+    *esq = __fma_rn(e, e, *esq);
 }
 #endif  // __CUDACC__
 

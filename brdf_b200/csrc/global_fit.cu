@@ -40,6 +40,20 @@ static SampleView view_of(const brdfgpu_samples* s) { return SampleView{s->c, s-
 // ------------------------------------------------------------------------------------------------
 // streaming bodies: grid-stride over sample PAIRS (16-byte loads), unrolled for loads in flight
 // ------------------------------------------------------------------------------------------------
+// Loads run one grid-stride step ahead of the arithmetic (register double buffer), so every warp
+// always has 3 x 16 B in flight while it works through ~100 fp64 instructions of the current pair.
+struct Pair {
+    double2 c, l, x;
+};
+__device__ __forceinline__ Pair load_pair(const double2* __restrict__ c2, const double2* __restrict__ l2,
+                                          const double2* __restrict__ x2, long i) {
+    Pair p;
+    p.c = __ldg(c2 + i);
+    p.l = __ldg(l2 + i);
+    p.x = __ldg(x2 + i);
+    return p;
+}
+
 template <int JAC>
 __device__ __forceinline__ void stream_jac(const SampleView& v, const PassParams& q, long tid, long nthreads,
                                            double* acc) {
@@ -47,37 +61,55 @@ __device__ __forceinline__ void stream_jac(const SampleView& v, const PassParams
     const double2* __restrict__ l2 = reinterpret_cast<const double2*>(v.L);
     const double2* __restrict__ x2 = reinterpret_cast<const double2*>(v.x);
     const long npair = v.n >> 1;
-#pragma unroll 2
-    for (long i = tid; i < npair; i += nthreads) {
-        const double2 cc = __ldg(c2 + i);
-        const double2 ll = __ldg(l2 + i);
-        const double2 xx = __ldg(x2 + i);
-        accumulate_jac<JAC>(q, cc.x, ll.x, xx.x, v.traw, 2 * i, acc);
-        accumulate_jac<JAC>(q, cc.y, ll.y, xx.y, v.traw, 2 * i + 1, acc);
+    long i = tid;
+    Pair cur;
+    if (i < npair) cur = load_pair(c2, l2, x2, i);
+    while (i < npair) {
+        const long nxt = i + nthreads;
+        Pair ahead = cur;
+        if (nxt < npair) ahead = load_pair(c2, l2, x2, nxt);
+        accumulate_jac<JAC>(q, cur.c.x, cur.l.x, cur.x.x, v.traw, 2 * i, acc);
+        accumulate_jac<JAC>(q, cur.c.y, cur.l.y, cur.x.y, v.traw, 2 * i + 1, acc);
+        cur = ahead;
+        i = nxt;
     }
     if ((v.n & 1) && tid == 0) {
-        const long i = v.n - 1;
-        accumulate_jac<JAC>(q, v.c[i], v.L[i], v.x[i], v.traw, i, acc);
+        const long j = v.n - 1;
+        accumulate_jac<JAC>(q, v.c[j], v.L[j], v.x[j], v.traw, j, acc);
     }
 }
 
 __device__ __forceinline__ void stream_cost(const SampleView& v, const PassParams& q, long tid, long nthreads,
-                                            double* acc2) {
+                                            double* acc2 /* [0] = sum e^2 */) {
     const double2* __restrict__ c2 = reinterpret_cast<const double2*>(v.c);
     const double2* __restrict__ l2 = reinterpret_cast<const double2*>(v.L);
     const double2* __restrict__ x2 = reinterpret_cast<const double2*>(v.x);
     const long npair = v.n >> 1;
-#pragma unroll 4
-    for (long i = tid; i < npair; i += nthreads) {
-        const double2 cc = __ldg(c2 + i);
-        const double2 ll = __ldg(l2 + i);
-        const double2 xx = __ldg(x2 + i);
-        accumulate_cost(q, cc.x, ll.x, xx.x, v.traw, 2 * i, acc2);
-        accumulate_cost(q, cc.y, ll.y, xx.y, v.traw, 2 * i + 1, acc2);
+    long i = tid;
+    Pair cur;
+    if (i < npair) cur = load_pair(c2, l2, x2, i);
+    while (i < npair) {
+        const long nxt = i + nthreads;
+        Pair ahead = cur;
+        if (nxt < npair) ahead = load_pair(c2, l2, x2, nxt);
+        accumulate_cost(q, cur.c.x, cur.l.x, cur.x.x, v.traw, 2 * i, acc2);
+        accumulate_cost(q, cur.c.y, cur.l.y, cur.x.y, v.traw, 2 * i + 1, acc2);
+        cur = ahead;
+        i = nxt;
     }
     if ((v.n & 1) && tid == 0) {
-        const long i = v.n - 1;
-        accumulate_cost(q, v.c[i], v.L[i], v.x[i], v.traw, i, acc2);
+        const long j = v.n - 1;
+        accumulate_cost(q, v.c[j], v.L[j], v.x[j], v.traw, j, acc2);
+    }
+}
+
+// number of non-finite residuals: only run when ||e||^2 came out non-finite, to tell an overflow of
+// the sum from invalid model values (lmbc_core.c:748, 915: VECNORM is non-finite iff some element is)
+__device__ __forceinline__ void stream_count_bad(const SampleView& v, const PassParams& q, long tid, long nthreads,
+                                                 double* cnt) {
+    for (long i = tid; i < v.n; i += nthreads) {
+        const double e = residual_of(q, v.c[i], v.L[i], v.x[i], v.traw, i);
+        *cnt += lm_finite(e) ? 0.0 : 1.0;
     }
 }
 
@@ -146,7 +178,7 @@ __device__ __forceinline__ void last_block_finish(double* partials, unsigned* ti
 }
 
 template <int JAC>
-__global__ void __launch_bounds__(kPassThreads) k_normal_eq(SampleView v, PassParams q, double* partials,
+__global__ void __launch_bounds__(kPassThreads, 3) k_normal_eq(SampleView v, PassParams q, double* partials,
                                                              unsigned* ticket, Publish pub) {
     __shared__ double red[(kPassThreads / 32) * NACC];
     double acc[NACC];
@@ -157,20 +189,21 @@ __global__ void __launch_bounds__(kPassThreads) k_normal_eq(SampleView v, PassPa
     last_block_finish<NACC>(partials, ticket, red, pub);
 }
 
-__global__ void __launch_bounds__(kPassThreads) k_cost(SampleView v, PassParams q, double* partials, unsigned* ticket,
+template <bool COUNT_BAD>
+__global__ void __launch_bounds__(kPassThreads, 4) k_cost(SampleView v, PassParams q, double* partials, unsigned* ticket,
                                                         Publish pub) {
-    __shared__ double red[(kPassThreads / 32) * 2];
-    double acc[2] = {0.0, 0.0};
-    stream_cost(v, q, (long)blockIdx.x * blockDim.x + threadIdx.x, (long)gridDim.x * blockDim.x, acc);
-    block_reduce_to<2>(acc, red, partials + (long)blockIdx.x * 2);
-    last_block_finish<2>(partials, ticket, red, pub);
+    __shared__ double red[(kPassThreads / 32)];
+    double acc[1] = {0.0};
+    if (COUNT_BAD) stream_count_bad(v, q, (long)blockIdx.x * blockDim.x + threadIdx.x, (long)gridDim.x * blockDim.x, acc);
+    else stream_cost(v, q, (long)blockIdx.x * blockDim.x + threadIdx.x, (long)gridDim.x * blockDim.x, acc);
+    block_reduce_to<1>(acc, red, partials + (long)blockIdx.x);
+    last_block_finish<1>(partials, ticket, red, pub);
 }
 
 // e_i = x_i - f(p)_i, the vector levmar keeps in `e` (lmbc_core.c:526)
 __global__ void k_residuals(SampleView v, PassParams q, double* e) {
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < v.n; i += (long)gridDim.x * blockDim.x) {
-        const double pw = pow_sample(q.n, v.L[i], v.traw, i, q.slow_all);
-        e[i] = v.x[i] - model_eval(q, v.c[i], pw);
+        e[i] = residual_of(q, v.c[i], v.L[i], v.x[i], v.traw, i);
     }
 }
 
@@ -245,7 +278,7 @@ static int to_jac_kind(int jac_mode, double delta_signed) {
 static int launch_normal_eq(brdfgpu_ctx* ctx, const brdfgpu_samples* s, const double* p, double delta, int jkind,
                             bool publish) {
     const PassParams q = make_pass_params(p, s->model, delta, jkind);
-    const int blocks = pass_blocks(ctx, s->n, 4);
+    const int blocks = pass_blocks(ctx, s->n, 3);
     Publish pub{ctx->d_result, nullptr, nullptr, 0};
     if (publish) pub = Publish{ctx->d_result, ctx->h_result_dev, ctx->h_seq_dev, ++ctx->seq};
     const SampleView v = view_of(s);
@@ -265,14 +298,23 @@ static int launch_normal_eq(brdfgpu_ctx* ctx, const brdfgpu_samples* s, const do
     return 0;
 }
 
-static int launch_cost(brdfgpu_ctx* ctx, const brdfgpu_samples* s, const double* p, bool publish) {
+static int launch_cost(brdfgpu_ctx* ctx, const brdfgpu_samples* s, const double* p, bool publish, bool count_bad = false) {
     const PassParams q = make_pass_params(p, s->model, 1.0, kJacAnalytic);
-    const int blocks = pass_blocks(ctx, s->n, 8);
+    const int blocks = pass_blocks(ctx, s->n, 4);
     Publish pub{ctx->d_result, nullptr, nullptr, 0};
     if (publish) pub = Publish{ctx->d_result, ctx->h_result_dev, ctx->h_seq_dev, ++ctx->seq};
-    k_cost<<<blocks, kPassThreads, 0, ctx->stream>>>(view_of(s), q, ctx->d_partials, ctx->d_sync, pub);
+    if (count_bad) k_cost<true><<<blocks, kPassThreads, 0, ctx->stream>>>(view_of(s), q, ctx->d_partials, ctx->d_sync, pub);
+    else k_cost<false><<<blocks, kPassThreads, 0, ctx->stream>>>(view_of(s), q, ctx->d_partials, ctx->d_sync, pub);
     ++ctx->launches;
     BG_CUDA_OK(ctx, cudaGetLastError());
+    return 0;
+}
+
+// number of non-finite residuals at p over all ranks
+static int count_bad(brdfgpu_ctx* ctx, const brdfgpu_samples* s, const double* p, double* count) {
+    const bool pub = ctx->nranks == 1;
+    if (launch_cost(ctx, s, p, pub, true) != 0 || fetch_result(ctx, 1, pub) != 0) return BRDFGPU_LM_ERROR;
+    *count = ctx->h_result[0];
     return 0;
 }
 
@@ -282,16 +324,15 @@ int global_normal_eq(brdfgpu_ctx* ctx, const brdfgpu_samples* s, const double* p
     if (launch_normal_eq(ctx, s, p, lm_abs(delta), to_jac_kind(jac_mode, delta), pub) != 0) return BRDFGPU_LM_ERROR;
     if (fetch_result(ctx, NACC, pub) != 0) return BRDFGPU_LM_ERROR;
     for (int k = 0; k < NACC; ++k) out11[k] = ctx->h_result[k];
-    return 0;
+    return count_bad(ctx, s, p, out11 + NACC);
 }
 
 int global_cost(brdfgpu_ctx* ctx, const brdfgpu_samples* s, const double* p, double* out2) {
     const bool pub = ctx->nranks == 1;
     if (launch_cost(ctx, s, p, pub) != 0) return BRDFGPU_LM_ERROR;
-    if (fetch_result(ctx, 2, pub) != 0) return BRDFGPU_LM_ERROR;
+    if (fetch_result(ctx, 1, pub) != 0) return BRDFGPU_LM_ERROR;
     out2[0] = ctx->h_result[0];
-    out2[1] = ctx->h_result[1];
-    return 0;
+    return count_bad(ctx, s, p, out2 + 1);
 }
 
 int global_repeat(brdfgpu_ctx* ctx, const brdfgpu_samples* s, const double* p, double delta, int kind, int reps) {
@@ -408,20 +449,43 @@ struct HostEval {
     }
     double cost(const double* p, bool& bad) {
         const bool pub = ctx->nranks == 1;
-        if (failed || launch_cost(ctx, s, p, pub) != 0 || fetch_result(ctx, 2, pub) != 0) {
+        if (failed || launch_cost(ctx, s, p, pub) != 0 || fetch_result(ctx, 1, pub) != 0) {
             failed = true;
             bad = true;
             return NAN;
         }
-        bad = ctx->h_result[1] != 0.0;
-        return ctx->h_result[0];
+        const double esq = ctx->h_result[0];
+        bad = false;
+        if (!lm_finite(esq)) {  // rare: tell an overflowed sum from invalid residuals
+            double cnt = 0.0;
+            if (count_bad(ctx, s, p, &cnt) != 0) failed = true;
+            bad = failed || cnt != 0.0;
+        }
+        return esq;
     }
 };
 
 // ------------------------------------------------------------------------------------------------
 // persistent driver: the whole fit inside one cooperative kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int kPersistThreads = 512;
+constexpr int kPersistThreads = 512;  // one CTA per SM, 16 warps, <= 128 registers per thread
+
+// Grid-wide barrier for the cooperative kernel: one atomic per CTA on a monotonically increasing
+// counter, everybody spins on an acquire load.  (Cheaper than cooperative_groups' grid.sync(): the
+// partial sums ride on the same release/acquire, so one barrier per evaluation is all there is.)
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target) {
+    target += gridDim.x;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+        } while (seen < target);
+    }
+    __syncthreads();
+}
 
 struct GridEval {
     SampleView v;
@@ -431,21 +495,28 @@ struct GridEval {
     double* red;       // shared [(kPersistThreads/32) * NACC]
     double* res;       // shared [NACC]
     int parity;
+    unsigned* bar;     // grid barrier counter (zeroed before the launch)
+    unsigned bar_target;
 
-    __device__ __noinline__ void jac(const double* p, double* JtJ, double* Jte) {
-        const PassParams q = make_pass_params(p, model, delta, jkind);
+    // one noinline instance per Jacobian kind: each gets its own register allocation
+    template <int JAC>
+    __device__ __noinline__ void jac_pass(const PassParams& q) {
         double acc[NACC];
 #pragma unroll
         for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
-        const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long)gridDim.x * blockDim.x;
-        if (jkind == kJacForward) stream_jac<kJacForward>(v, q, tid, nth, acc);
-        else if (jkind == kJacCentral) stream_jac<kJacCentral>(v, q, tid, nth, acc);
-        else stream_jac<kJacAnalytic>(v, q, tid, nth, acc);
+        stream_jac<JAC>(v, q, (long)blockIdx.x * blockDim.x + threadIdx.x, (long)gridDim.x * blockDim.x, acc);
+        double* buf = partials + (long)parity * kMaxPassBlocks * NACC;
+        block_reduce_to<NACC>(acc, red, buf + (long)blockIdx.x * NACC);
+    }
+
+    __device__ __forceinline__ void jac(const double* p, double* JtJ, double* Jte) {
+        const PassParams q = make_pass_params(p, model, delta, jkind);
+        if (jkind == kJacForward) jac_pass<kJacForward>(q);
+        else if (jkind == kJacCentral) jac_pass<kJacCentral>(q);
+        else jac_pass<kJacAnalytic>(q);
         double* buf = partials + (long)parity * kMaxPassBlocks * NACC;
         parity ^= 1;
-        block_reduce_to<NACC>(acc, red, buf + (long)blockIdx.x * NACC);
-        __threadfence();
-        cg::this_grid().sync();
+        grid_barrier(bar, bar_target);
         final_reduce<NACC>(buf, gridDim.x, res);
         __syncthreads();
         JtJ[0] = res[A00]; JtJ[1] = res[A01]; JtJ[2] = res[A02];
@@ -454,27 +525,35 @@ struct GridEval {
         Jte[0] = res[G0]; Jte[1] = res[G1]; Jte[2] = res[G2];
     }
 
-    __device__ __noinline__ double cost(const double* p, bool& bad) {
-        const PassParams q = make_pass_params(p, model, 1.0, kJacAnalytic);
-        double acc[2] = {0.0, 0.0};
-        stream_cost(v, q, (long)blockIdx.x * blockDim.x + threadIdx.x, (long)gridDim.x * blockDim.x, acc);
+    __device__ __forceinline__ double scalar_pass(const PassParams& q, bool count_bad) {
+        double acc[1] = {0.0};
+        const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long)gridDim.x * blockDim.x;
+        if (count_bad) stream_count_bad(v, q, tid, nth, acc);
+        else stream_cost(v, q, tid, nth, acc);
         double* buf = partials + (long)parity * kMaxPassBlocks * NACC;
         parity ^= 1;
-        block_reduce_to<2>(acc, red, buf + (long)blockIdx.x * 2);
-        __threadfence();
-        cg::this_grid().sync();
-        final_reduce<2>(buf, gridDim.x, res);
+        block_reduce_to<1>(acc, red, buf + (long)blockIdx.x);
+        grid_barrier(bar, bar_target);
+        final_reduce<1>(buf, gridDim.x, res);
         __syncthreads();
-        bad = res[1] != 0.0;
         return res[0];
+    }
+
+    __device__ __noinline__ double cost(const double* p, bool& bad) {
+        const PassParams q = make_pass_params(p, model, 1.0, kJacAnalytic);
+        const double esq = scalar_pass(q, false);
+        bad = false;
+        if (!lm_finite(esq)) bad = scalar_pass(q, true) != 0.0;  // uniform across the grid: same sums everywhere
+        return esq;
     }
 };
 
 __global__ void __launch_bounds__(kPersistThreads, 1) k_persistent_fit(SampleView v, int model, GlobalFitSpec spec,
-                                                                        double* partials, GlobalFitOut* out) {
+                                                                        double* partials, unsigned* barrier,
+                                                                        GlobalFitOut* out) {
     __shared__ double red[(kPersistThreads / 32) * NACC];
     __shared__ double res[NACC];
-    GridEval ev{v, model, spec.jac_mode, spec.delta, partials, red, res, 0};
+    GridEval ev{v, model, spec.jac_mode, spec.delta, partials, red, res, 0, barrier, 0u};
     double p[3], info[10], JtJ[9];
     for (int i = 0; i < 3; ++i) p[i] = spec.p[i];
     int ret;
@@ -583,7 +662,9 @@ int global_fit(brdfgpu_ctx* ctx, const brdfgpu_samples* s, double* p, int m, con
         int model = s->model;
         double* partials = ctx->d_partials;
         GlobalFitOut* d_out = static_cast<GlobalFitOut*>(ctx->d_fitio);
-        void* args[] = {&v, &model, &spec, &partials, &d_out};
+        unsigned* barrier = ctx->d_sync + 4;
+        BG_CUDA_OK(ctx, cudaMemsetAsync(barrier, 0, sizeof(unsigned), ctx->stream));
+        void* args[] = {&v, &model, &spec, &partials, &barrier, &d_out};
         BG_CUDA_OK(ctx, cudaLaunchCooperativeKernel((const void*)k_persistent_fit, dim3(grid), dim3(kPersistThreads), args,
                                                      0, ctx->stream));
         ++ctx->launches;

@@ -22,30 +22,31 @@ def ctx():
 
 
 def _compare(p, info, ret, want_p, want_info, want_ret, min_agree, determined=True):
-    """Fits that converged on both sides must agree to tolerance.  Fits that hit itmax=100 or stop
-    with 'no further reduction' are chaotic in the summation order even on the CPU
-    and only have to end at a cost that is not worse."""
+    """Per-fit parity classes.
+    strict : parameters within 1e-4 and final cost within 1e-6 relative of levmar's -- required for
+             at least `min_agree` of the fits;
+    loose  : every fit must at least end at levmar's cost to 1e-3 relative (or lower): fits that
+             hit itmax=100, stop with 'no further reduction', or crawl along an active bound with
+             ks = 0 (flat in n) end wherever rounding takes them -- on the CPU as well when the
+             summation order changes."""
     nfit = len(want_ret)
-    agree = 0
+    strict = 0
     for f in range(nfit):
-        both = int(info[f][6]) in CONVERGED and int(want_info[f][6]) in CONVERGED
         ok_p = np.allclose(p[f], want_p[f], rtol=PAR_RTOL, atol=1e-9)
         ok_c = np.isclose(info[f][1], want_info[f][1], rtol=COST_RTOL, atol=1e-18)
-        if both and determined:
-            assert ok_c and ok_p, (f, p[f], want_p[f], info[f], want_info[f])
-        else:
-            assert (ret[f] >= 0) == (want_ret[f] >= 0)
-            assert info[f][1] <= want_info[f][1] * (1 + 1e-3) + 1e-15, (f, info[f], want_info[f])
-        agree += bool(ok_p and ok_c)
+        strict += bool(ok_c and (ok_p or not determined))
+        assert (ret[f] >= 0) == (want_ret[f] >= 0)
+        assert info[f][1] <= want_info[f][1] * (1 + 1e-3) + 1e-15, (f, p[f], want_p[f], info[f], want_info[f])
         assert np.isclose(info[f][0], want_info[f][0], rtol=1e-9)
-    assert agree >= min_agree * nfit, (agree, nfit)
+    assert strict >= min_agree * nfit, (strict, nfit)
+    return strict
 
 
 @pytest.mark.parametrize("case", GOLD["batch"], ids=[c["name"] for c in GOLD["batch"]])
 def test_batched_fits_match_reference_golden(ctx, case):
     c, td, th, x, _ = G.batch_inputs(case)
     p, info, ret = ctx.solve_equation_batch(c, td, th, x, case["model"])
-    _compare(p, info, ret, case["p"], case["info"], case["ret"], 0.8)
+    _compare(p, info, ret, case["p"], case["info"], case["ret"], 0.85)
 
 
 @pytest.mark.parametrize("nper", [3, 16, 17, 32, 64, 100, 200])
@@ -58,7 +59,7 @@ def test_batched_fits_match_oracle_fresh(ctx, nper):
         wr[f], wp[f], wi[f] = O.brdf_fit(O.oracle(), "oracle_", c[f], td[f], th[f], x[f], 1, O.REF_PERFACE)
     # nper == 3 == m is an exactly determined system: the minimiser is not unique to 1e-4 when a bound
     # is active (cost ~1e-20 on both sides), so only the cost is compared there
-    _compare(p, info, ret, wp, wi, wr, 0.75 if nper >= 16 else 0.3, determined=nper > 3)
+    _compare(p, info, ret, wp, wi, wr, 0.85 if nper >= 16 else 0.5, determined=nper > 3)
 
 
 def test_solve_equation_single_fit_entry():
