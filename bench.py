@@ -167,6 +167,10 @@ def run_gpu_arm(args):
         ids = [A.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         ctx.comm_init(ids[0], rank, world)
+        # peer buffers for the fused in-kernel exchange (CUDA IPC handles travel through torch.distributed)
+        handles = [None] * world
+        dist.all_gather_object(handles, ctx.peer_export())
+        ctx.peer_attach(handles, rank, world)
 
     def barrier():
         ctx.synchronize()
@@ -179,7 +183,8 @@ def run_gpu_arm(args):
     n = N_PER_GPU
     n_total = n * world
     s = ctx.synth(n, SEED, start=rank * n)
-    drive = A.DRIVE_PERSISTENT if world == 1 else A.DRIVE_HOST
+    # BRDF_BENCH_DRIVE=host: one kernel + one NCCL all-reduce per evaluation instead of the persistent kernel
+    drive = A.DRIVE_HOST if os.environ.get("BRDF_BENCH_DRIVE") == "host" else A.DRIVE_PERSISTENT
 
     def fit():
         return ctx.fit_global(s, A.REF_GLOBAL, drive=drive)
@@ -211,8 +216,9 @@ def run_gpu_arm(args):
 
     # ---- dominant kernel of the step and its roofline ----
     peak, peak_src = peaks()
-    if world == 1:
-        # the step IS one persistent kernel launch (+ an 800-byte result copy)
+    if drive == A.DRIVE_PERSISTENT:
+        # the step IS one persistent kernel launch per rank (+ an 800-byte result copy); at N>1 the
+        # cross-GPU exchange of the sums happens inside it (peer stores over NVLink)
         kernel, launches_per_step, kern_ms = "k_persistent_fit", 1, ms / args.steps
         algo_bytes = 24.0 * n * passes / args.steps
     else:
@@ -308,7 +314,8 @@ def run_gpu_arm(args):
                "config": {"workload": "synthetic single global BRDF fit, 10^6 samples, fp64 (BASELINE configs[1])",
                           "samples_per_gpu": n, "samples_total": n_total, "preset": "REF_GLOBAL", "model": "blinn-phong",
                           "jacobian": "forward differences, delta=1 (levmar-exact)",
-                          "driver": "persistent cooperative kernel" if world == 1 else "host loop + NCCL all-reduce(11 f64) per evaluation",
+                          "driver": ("persistent cooperative kernel" + ("" if world == 1 else ", fused peer-memory all-reduce of the 10 sums per evaluation"))
+                          if drive == A.DRIVE_PERSISTENT else "host loop + NCCL all-reduce(10 f64) per evaluation",
                           "l2": "inputs (24 MB/GPU) are smaller than L2 by definition of the workload; roofline_hbm uses 2.4 GB inputs",
                           "iterations_per_fit": float(info[5]), "nfev_per_fit": float(info[7]), "stop_reason": int(info[6])},
                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}

@@ -103,6 +103,9 @@ SIGNATURES = {
     "brdfgpu_comm_init": (C.c_int, [_V, C.c_char_p, C.c_int, C.c_int]),
     "brdfgpu_comm_destroy": (None, [_V]),
     "brdfgpu_comm_allreduce": (C.c_int, [_V, dptr, C.c_int]),
+    "brdfgpu_peer_export": (C.c_int, [_V, C.c_char_p]),
+    "brdfgpu_peer_attach": (C.c_int, [_V, C.c_char_p, C.c_int, C.c_int]),
+    "brdfgpu_peer_detach": (None, [_V]),
     "brdfgpu_lm_bc_reduced": (C.c_int, [_V, _V, _V, dptr, C.c_int, C.c_long, dptr, dptr, dptr, C.c_int, dptr, dptr, dptr]),
     "brdfgpu_lm_unc_reduced": (C.c_int, [_V, _V, _V, dptr, C.c_int, C.c_long, C.c_int, dptr, dptr, dptr]),
     "brdfgpu_Ax_eq_b_LU": (C.c_int, [dptr, dptr, dptr, C.c_int]),
@@ -399,6 +402,15 @@ class Context:
     def comm_init(self, unique_id, rank, nranks):
         self._ok(lib().brdfgpu_comm_init(self.handle, unique_id, rank, nranks))
 
+    def peer_export(self):
+        buf = C.create_string_buffer(64)
+        self._ok(lib().brdfgpu_peer_export(self.handle, buf))
+        return buf.raw
+
+    def peer_attach(self, handles, rank, nranks):
+        """handles: the 64-byte exports of all ranks in rank order"""
+        self._ok(lib().brdfgpu_peer_attach(self.handle, b"".join(handles), rank, nranks))
+
     def allreduce(self, values):
         buf = _arr(values).copy()
         self._ok(lib().brdfgpu_comm_allreduce(self.handle, _d(buf), buf.size))
@@ -406,6 +418,7 @@ class Context:
 
     def close(self):
         if self.handle:
+            lib().brdfgpu_peer_detach(self.handle)
             lib().brdfgpu_destroy(self.handle)
             self.handle = None
 

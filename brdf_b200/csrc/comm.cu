@@ -129,3 +129,74 @@ extern "C" int brdfgpu_comm_allreduce(brdfgpu_ctx* ctx, double* buf, int count) 
     BG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// peer-memory exchange buffers for the fused in-kernel all-reduce (global_fit.cu: peer_exchange).
+// Each rank exports one small cudaMalloc'ed buffer through CUDA IPC; the launcher moves the 64-byte
+// handles between the processes (any transport) and every rank maps all the others.  Stores to a
+// mapped peer pointer travel over NVLink / NVSwitch.
+// ------------------------------------------------------------------------------------------------
+static size_t peer_buffer_bytes() { return sizeof(uint4) * 2 * kMaxRanks * kPeerCellsPerRank; }
+
+extern "C" int brdfgpu_peer_export(brdfgpu_ctx* ctx, char* handle64) {
+    if (!ctx) ctx = default_ctx();
+    if (!ctx || !handle64) return BRDFGPU_LM_ERROR;
+    static_assert(sizeof(cudaIpcMemHandle_t) == BRDFGPU_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+    BG_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->peer_local) {
+        BG_CUDA_OK(ctx, cudaMalloc(&ctx->peer_local, peer_buffer_bytes()));
+        BG_CUDA_OK(ctx, cudaMemset(ctx->peer_local, 0, peer_buffer_bytes()));
+    }
+    cudaIpcMemHandle_t h;
+    BG_CUDA_OK(ctx, cudaIpcGetMemHandle(&h, ctx->peer_local));
+    memcpy(handle64, &h, sizeof(h));
+    return 0;
+}
+
+extern "C" int brdfgpu_peer_attach(brdfgpu_ctx* ctx, const char* handles, int rank, int nranks) {
+    if (!ctx) ctx = default_ctx();
+    if (!ctx || !handles) return BRDFGPU_LM_ERROR;
+    if (nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks) {
+        set_error(ctx, "peer_attach: need 1 <= nranks <= 8 and 0 <= rank < nranks");
+        return BRDFGPU_LM_ERROR;
+    }
+    if (!ctx->peer_local) {
+        set_error(ctx, "peer_attach: call brdfgpu_peer_export first");
+        return BRDFGPU_LM_ERROR;
+    }
+    if (ctx->nccl_comm && (ctx->rank != rank || ctx->nranks != nranks)) {
+        set_error(ctx, "peer_attach: rank/nranks differ from the communicator's");
+        return BRDFGPU_LM_ERROR;
+    }
+    BG_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    for (int r = 0; r < nranks; ++r) {
+        if (r == rank) {
+            ctx->peer_remote[r] = ctx->peer_local;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * sizeof(h), sizeof(h));
+        void* ptr = nullptr;
+        BG_CUDA_OK(ctx, cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->peer_remote[r] = static_cast<uint4*>(ptr);
+    }
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+    ctx->peer_epoch = 0;
+    ctx->peer_attached = nranks > 1;
+    return 0;
+}
+
+extern "C" void brdfgpu_peer_detach(brdfgpu_ctx* ctx) {
+    if (!ctx) ctx = default_ctx();
+    if (!ctx) return;
+    for (int r = 0; r < kMaxRanks; ++r) {
+        if (ctx->peer_remote[r] && ctx->peer_remote[r] != ctx->peer_local) cudaIpcCloseMemHandle(ctx->peer_remote[r]);
+        ctx->peer_remote[r] = nullptr;
+    }
+    ctx->peer_attached = false;
+    if (!ctx->nccl_comm) {
+        ctx->rank = 0;
+        ctx->nranks = 1;
+    }
+}

@@ -15,6 +15,18 @@ constexpr int kMaxM = BRDFGPU_MAX_PARAMS;
 constexpr int kPassThreads = 256;    // threads per CTA of the streaming passes
 constexpr int kMaxPassBlocks = 2048; // upper bound on CTAs of one pass (partials buffer)
 constexpr int kResultDoubles = 16;   // >= NACC
+constexpr int kMaxRanks = 8;         // GPUs of one NVSwitch domain
+constexpr int kPeerCellsPerRank = 16;  // >= NACC flagged cells per (parity, rank)
+
+// Exchange buffer of the fused in-kernel all-reduce: [2 parities][kMaxRanks][kPeerCellsPerRank]
+// 16-byte cells {value.lo, tag, value.hi, tag}.  Every 8-byte half is written atomically, so a
+// reader that sees the current tag in both halves has the whole double (no fences, no flags).
+struct PeerView {
+    uint4* local;
+    uint4* remote[kMaxRanks];  // remote[rank] == local
+    int rank, nranks;
+    unsigned epoch;            // tag of the last exchange
+};
 
 }  // namespace brdfgpu
 
@@ -45,7 +57,10 @@ struct brdfgpu_ctx {
     void* nccl_comm = nullptr;
     int rank = 0, nranks = 1;
     // peer-memory exchange (fused one-shot all-reduce inside the fit kernels)
-    void* peer = nullptr;
+    uint4* peer_local = nullptr;            // this rank's exchange buffer (cudaMalloc, IPC-exported)
+    uint4* peer_remote[brdfgpu::kMaxRanks] = {nullptr};
+    bool peer_attached = false;
+    unsigned peer_epoch = 0;
 };
 
 struct brdfgpu_samples {
@@ -102,6 +117,8 @@ struct GlobalFitSpec {
 };
 struct GlobalFitOut {
     int ret;
+    unsigned peer_epoch;  // exchange tag after the fit (all ranks advance in lock step)
+    int peer_timeout;     // a peer never delivered: the fit was abandoned
     double p[kMaxM];
     double info[10];
     double JtJ[kMaxM * kMaxM];

@@ -473,16 +473,77 @@ constexpr int kPersistThreads = 512;  // one CTA per SM, 16 warps, <= 128 regist
 // Grid-wide barrier for the cooperative kernel: one atomic per CTA on a monotonically increasing
 // counter, everybody spins on an acquire load.  (Cheaper than cooperative_groups' grid.sync(): the
 // partial sums ride on the same release/acquire, so one barrier per evaluation is all there is.)
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target) {
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target, const int* abort_flag) {
     target += gridDim.x;
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(counter, 1u);
-        unsigned seen;
+        unsigned seen, spins = 0;
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+            // a CTA that gave up on a peer rank (peer_exchange) leaves the control loop early: do not
+            // wait for it forever
+            if (abort_flag && (++spins & 0x3ffu) == 0 && *(volatile const int*)abort_flag) break;
         } while (seen < target);
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused cross-GPU all-reduce (global mode on several GPUs): the exchange step of an evaluation
+// happens INSIDE the fit kernel over NVLink peer memory, so a multi-GPU fit is still one launch per
+// rank.  After the local grid reduction CTA 0 of every rank stores its rank's sums as flagged
+// cells into slot [parity][rank] of EVERY rank's exchange buffer (peer stores through NVSwitch);
+// every CTA then polls its own rank's buffer until all slots carry the current tag and adds them in
+// rank order -- identical bits on all ranks, so all ranks take identical LM decisions with no
+// broadcast.  Two parities: a rank can run at most one exchange ahead of the slowest CTA of any peer.
+// ------------------------------------------------------------------------------------------------
+constexpr long long kPeerSpinCycles = 6000000000LL;  // ~3 s at 2 GHz, then the fit is abandoned
+
+__device__ __forceinline__ void peer_store_cell(uint4* dst, double v, unsigned tag) {
+    const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(lo), "r"(tag), "r"(hi), "r"(tag)
+                 : "memory");
+}
+__device__ __forceinline__ uint4 peer_load_cell(const uint4* src) {
+    uint4 c;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w) : "l"(src)
+                 : "memory");
+    return c;
+}
+
+// in: res[0..NV) = this rank's sums (shared, complete); out: res[0..NV) = sums over all ranks
+template <int NV>
+__device__ __forceinline__ void peer_exchange(PeerView& pv, double* res, double* stage /*shared [kMaxRanks*NV]*/,
+                                              int* timeout_flag) {
+    if (pv.nranks <= 1) return;
+    pv.epoch = pv.epoch + 1u ? pv.epoch + 1u : 1u;  // never 0: the buffers start zeroed
+    const unsigned tag = pv.epoch;
+    const int par = (int)(tag & 1u);
+    const int r = threadIdx.x / NV, k = threadIdx.x % NV;
+    if (threadIdx.x < NV * pv.nranks) {
+        if (blockIdx.x == 0)  // (also after a timeout: the peers must not wait for this rank in turn)
+            peer_store_cell(pv.remote[r] + ((long)(par * kMaxRanks + pv.rank) * kPeerCellsPerRank + k), res[k], tag);
+        const uint4* src = pv.local + ((long)(par * kMaxRanks + r) * kPeerCellsPerRank + k);
+        const long long t0 = clock64();
+        unsigned spins = 0;
+        uint4 c = peer_load_cell(src);
+        while (c.y != tag || c.w != tag) {
+            if ((++spins & 0xffu) == 0 && (clock64() - t0 > kPeerSpinCycles || *(volatile int*)timeout_flag)) {
+                *timeout_flag = 1;
+                c.x = 0u; c.z = 0x7ff80000u;  // NaN: the control loop stops with reason 7
+                break;
+            }
+            c = peer_load_cell(src);
+        }
+        stage[r * NV + k] = __hiloint2double((int)c.z, (int)c.x);
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double sum = 0.0;
+        for (int q = 0; q < pv.nranks; ++q) sum += stage[q * NV + threadIdx.x];
+        res[threadIdx.x] = sum;
     }
     __syncthreads();
 }
@@ -497,6 +558,9 @@ struct GridEval {
     int parity;
     unsigned* bar;     // grid barrier counter (zeroed before the launch)
     unsigned bar_target;
+    PeerView peer;     // nranks == 1: no exchange
+    double* stage;     // shared [kMaxRanks * NACC]
+    int* timeout_flag; // global
 
     // one noinline instance per Jacobian kind: each gets its own register allocation
     template <int JAC>
@@ -516,13 +580,15 @@ struct GridEval {
         else jac_pass<kJacAnalytic>(q);
         double* buf = partials + (long)parity * kMaxPassBlocks * NACC;
         parity ^= 1;
-        grid_barrier(bar, bar_target);
+        grid_barrier(bar, bar_target, peer.nranks > 1 ? timeout_flag : nullptr);
         final_reduce<NACC>(buf, gridDim.x, res);
         __syncthreads();
+        peer_exchange<NACC>(peer, res, stage, timeout_flag);
         JtJ[0] = res[A00]; JtJ[1] = res[A01]; JtJ[2] = res[A02];
         JtJ[3] = res[A01]; JtJ[4] = res[A11]; JtJ[5] = res[A12];
         JtJ[6] = res[A02]; JtJ[7] = res[A12]; JtJ[8] = res[A22];
         Jte[0] = res[G0]; Jte[1] = res[G1]; Jte[2] = res[G2];
+        __syncthreads();  // res is rewritten by the next pass's exchange before its barrier
     }
 
     __device__ __forceinline__ double scalar_pass(const PassParams& q, bool count_bad) {
@@ -533,10 +599,13 @@ struct GridEval {
         double* buf = partials + (long)parity * kMaxPassBlocks * NACC;
         parity ^= 1;
         block_reduce_to<1>(acc, red, buf + (long)blockIdx.x);
-        grid_barrier(bar, bar_target);
+        grid_barrier(bar, bar_target, peer.nranks > 1 ? timeout_flag : nullptr);
         final_reduce<1>(buf, gridDim.x, res);
         __syncthreads();
-        return res[0];
+        peer_exchange<1>(peer, res, stage, timeout_flag);
+        const double out = res[0];
+        __syncthreads();  // res is rewritten by the next pass's exchange before its barrier
+        return out;
     }
 
     __device__ __noinline__ double cost(const double* p, bool& bad) {
@@ -550,10 +619,12 @@ struct GridEval {
 
 __global__ void __launch_bounds__(kPersistThreads, 1) k_persistent_fit(SampleView v, int model, GlobalFitSpec spec,
                                                                         double* partials, unsigned* barrier,
-                                                                        GlobalFitOut* out) {
+                                                                        PeerView peer, GlobalFitOut* out) {
     __shared__ double red[(kPersistThreads / 32) * NACC];
     __shared__ double res[NACC];
-    GridEval ev{v, model, spec.jac_mode, spec.delta, partials, red, res, 0, barrier, 0u};
+    __shared__ double stage[kMaxRanks * NACC];
+    if (blockIdx.x == 0 && threadIdx.x == 0) out->peer_timeout = 0;
+    GridEval ev{v, model, spec.jac_mode, spec.delta, partials, red, res, 0, barrier, 0u, peer, stage, &out->peer_timeout};
     double p[3], info[10], JtJ[9];
     for (int i = 0; i < 3; ++i) p[i] = spec.p[i];
     int ret;
@@ -564,6 +635,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_persistent_fit(SampleVie
                            spec.has_dscl ? spec.dscl : nullptr, spec.opt, info, JtJ);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         out->ret = ret;
+        out->peer_epoch = ev.peer.epoch;
         for (int i = 0; i < 3; ++i) out->p[i] = p[i];
         for (int i = 0; i < 10; ++i) out->info[i] = info[i];
         for (int i = 0; i < 9; ++i) out->JtJ[i] = JtJ[i];
@@ -645,7 +717,8 @@ int global_fit(brdfgpu_ctx* ctx, const brdfgpu_samples* s, double* p, int m, con
 
     double fit_info[10], JtJ[9];
     int ret;
-    const int grid = (drive == BRDFGPU_DRIVE_PERSISTENT && ctx->coop && ctx->nranks == 1) ? persistent_grid(ctx, s->n) : 0;
+    const bool can_persist = ctx->coop && (ctx->nranks == 1 || ctx->peer_attached);
+    const int grid = (drive == BRDFGPU_DRIVE_PERSISTENT && can_persist) ? persistent_grid(ctx, s->n) : 0;
     if (grid > 0) {
         GlobalFitSpec spec;
         memset(&spec, 0, sizeof(spec));
@@ -664,13 +737,30 @@ int global_fit(brdfgpu_ctx* ctx, const brdfgpu_samples* s, double* p, int m, con
         GlobalFitOut* d_out = static_cast<GlobalFitOut*>(ctx->d_fitio);
         unsigned* barrier = ctx->d_sync + 4;
         BG_CUDA_OK(ctx, cudaMemsetAsync(barrier, 0, sizeof(unsigned), ctx->stream));
-        void* args[] = {&v, &model, &spec, &partials, &barrier, &d_out};
+        PeerView peer;
+        memset(&peer, 0, sizeof(peer));
+        peer.nranks = 1;
+        if (ctx->nranks > 1) {
+            peer.local = ctx->peer_local;
+            for (int r = 0; r < ctx->nranks; ++r) peer.remote[r] = ctx->peer_remote[r];
+            peer.rank = ctx->rank;
+            peer.nranks = ctx->nranks;
+            peer.epoch = ctx->peer_epoch;
+        }
+        void* args[] = {&v, &model, &spec, &partials, &barrier, &peer, &d_out};
         BG_CUDA_OK(ctx, cudaLaunchCooperativeKernel((const void*)k_persistent_fit, dim3(grid), dim3(kPersistThreads), args,
                                                      0, ctx->stream));
         ++ctx->launches;
         BG_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_fitio, d_out, sizeof(GlobalFitOut), cudaMemcpyDeviceToHost, ctx->stream));
         BG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
         const GlobalFitOut* h = static_cast<const GlobalFitOut*>(ctx->h_fitio);
+        if (ctx->nranks > 1) {
+            ctx->peer_epoch = h->peer_epoch;
+            if (h->peer_timeout) {
+                set_error(ctx, "multi-GPU fit abandoned: a peer rank never delivered its sums (peer exchange timeout)");
+                return BRDFGPU_LM_ERROR;
+            }
+        }
         ret = h->ret;
         for (int i = 0; i < 3; ++i) p[i] = h->p[i];
         for (int i = 0; i < 10; ++i) fit_info[i] = h->info[i];

@@ -258,6 +258,15 @@ void brdfgpu_comm_destroy(brdfgpu_ctx *ctx);
  * step of the global fit, exposed for tests */
 int brdfgpu_comm_allreduce(brdfgpu_ctx *ctx, double *buf, int count);
 
+/* Fused in-kernel exchange: with peer buffers attached the persistent fit kernel all-reduces its
+ * sums itself, by peer stores over NVLink / NVSwitch inside the same launch (no NCCL call, no host
+ * round trip per evaluation).  Every rank exports one 64-byte CUDA-IPC handle, the launcher
+ * gathers them (rank order) and every rank attaches all of them.  One process per GPU. */
+#define BRDFGPU_IPC_HANDLE_BYTES 64
+int brdfgpu_peer_export(brdfgpu_ctx *ctx, char *handle64);
+int brdfgpu_peer_attach(brdfgpu_ctx *ctx, const char *handles /* nranks x 64 */, int rank, int nranks);
+void brdfgpu_peer_detach(brdfgpu_ctx *ctx);
+
 /* ------------------------------------------------------------------------------------------------
  * 6. The LM control loop on caller-supplied REDUCED evaluators (host logic of the global mode;
  *    lets the exact product control code run wherever the sums come from, e.g. CPU tests with

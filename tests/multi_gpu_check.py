@@ -1,0 +1,88 @@
+"""Multi-GPU global fit check, one process per GPU:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port 29533 tests/multi_gpu_check.py [n_total]
+
+Every rank holds a contiguous shard of ONE sample set.  The fit runs twice:
+  * host loop + NCCL all-reduce of the 10 sums per evaluation (DRIVE_HOST)
+  * the persistent kernel with the fused in-kernel peer-memory exchange (DRIVE_PERSISTENT)
+and both must (a) give bit-identical p / info on every rank, (b) agree with the single-GPU fit of the
+whole set on rank 0 and with the CPU oracle within the parity tolerances (1e-4 params, 1e-6 cost).
+Prints "MULTI_GPU_OK ..." on rank 0; any failure raises (non-zero exit).  Used by
+tests/test_gpu_multi.py and by hand under gpurun --gpus N.
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+
+    import oracle_lib as O
+    import synth
+    from brdf_b200 import api as A
+
+    rank, world, local = (int(os.environ[k]) for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"))
+    n_total = int(sys.argv[1]) if len(sys.argv) > 1 else 200_001
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = A.Context(local)
+
+    ids = [A.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    ctx.comm_init(ids[0], rank, world)
+    handles = [None] * world
+    dist.all_gather_object(handles, ctx.peer_export())
+    ctx.peer_attach(handles, rank, world)
+
+    c, td, th, x = synth.samples(n_total, seed=77)
+    lo, hi = rank * n_total // world, (rank + 1) * n_total // world   # ragged shards on purpose
+    s = ctx.upload(c[lo:hi], td[lo:hi], x[lo:hi], A.BLINN_PHONG)
+
+    results = {}
+    for name, drive in (("nccl-host", A.DRIVE_HOST), ("peer-persistent", A.DRIVE_PERSISTENT)):
+        for preset_name, preset in (("REF_GLOBAL", A.REF_GLOBAL), ("REF_PERFACE", A.REF_PERFACE)):
+            dist.barrier()
+            t0 = time.perf_counter()
+            ret, p, info = ctx.fit_global(s, preset, drive=drive)
+            dt = time.perf_counter() - t0
+            blob = np.concatenate([[ret], p, info])
+            all_blobs = [None] * world
+            dist.all_gather_object(all_blobs, blob.tobytes())
+            assert all(b == all_blobs[0] for b in all_blobs), "%s/%s: ranks disagree" % (name, preset_name)
+            results[(name, preset_name)] = (ret, p, info, dt)
+
+    if rank == 0:
+        single = A.Context(local)
+        s1 = single.upload(c, td, x, A.BLINN_PHONG)
+        for preset_name, preset, opreset in (("REF_GLOBAL", A.REF_GLOBAL, O.REF_GLOBAL), ("REF_PERFACE", A.REF_PERFACE, O.REF_PERFACE)):
+            r1, p1, i1 = single.fit_global(s1, preset)
+            wret, wp, winfo = O.brdf_fit(O.oracle(), "oracle_", c, td, th, x, 1, opreset)
+            for name in ("nccl-host", "peer-persistent"):
+                ret, p, info, dt = results[(name, preset_name)]
+                assert (ret >= 0) == (wret >= 0) == (r1 >= 0)
+                np.testing.assert_allclose(p, p1, rtol=1e-4, err_msg=name)
+                np.testing.assert_allclose(p, wp, rtol=1e-4, err_msg=name)
+                np.testing.assert_allclose(info[1], winfo[1], rtol=1e-6, err_msg=name)
+                assert int(info[6]) == int(winfo[6]), (name, info[6], winfo[6])
+                print("%-16s %-11s ranks=%d n=%d iters=%d nfev=%d p=%s cost=%.12g  %.2f ms" %
+                      (name, preset_name, world, n_total, info[5], info[7], p, info[1], dt * 1e3), flush=True)
+        s1.free()
+        single.close()
+        print("MULTI_GPU_OK world=%d" % world, flush=True)
+    dist.barrier()
+    s.free()
+    ctx.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
