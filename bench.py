@@ -202,7 +202,8 @@ def run_gpu_arm(args):
     for _ in range(args.steps):
         ret, p, info = fit()
         evals += info[7]
-        passes += info[8] + (info[7] - 4.0 * info[8])   # one fused K2 pass per Jacobian + one K3 pass per other evaluation
+        st = ctx.fit_stats()
+        passes += st["jac_passes"] + st["cost_passes"]   # sweeps over the samples (a batched PG sweep counts once)
     ev1.record(stream)
     barrier()
     launches = ctx.launches - launches0
@@ -236,8 +237,9 @@ def run_gpu_arm(args):
     roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
                 "launch_ms": kern_ms,
-                "note": "24 B/sample/pass; at 10^6 samples (24 MB) the passes are served from the 126 MB L2 after the "
-                        "first one -- see roofline_hbm for the HBM-resident regime"}
+                "note": "24 B/sample/sweep x the sweeps the kernel made; at 10^6 samples/GPU the whole shard is held in "
+                        "shared memory for the fit, so this 'achieved' is on-chip traffic and may exceed the HBM peak -- "
+                        "see roofline_hbm for the HBM-resident regime (10^8 samples)"}
 
     extra = {}
     if rank == 0 and world == 1 and not args.quick:
@@ -317,7 +319,8 @@ def run_gpu_arm(args):
                           "driver": ("persistent cooperative kernel" + ("" if world == 1 else ", fused peer-memory all-reduce of the 10 sums per evaluation"))
                           if drive == A.DRIVE_PERSISTENT else "host loop + NCCL all-reduce(10 f64) per evaluation",
                           "l2": "inputs (24 MB/GPU) are smaller than L2 by definition of the workload; roofline_hbm uses 2.4 GB inputs",
-                          "iterations_per_fit": float(info[5]), "nfev_per_fit": float(info[7]), "stop_reason": int(info[6])},
+                          "iterations_per_fit": float(info[5]), "nfev_per_fit": float(info[7]), "stop_reason": int(info[6]),
+                          "sweeps_per_fit": passes / args.steps, "fit_stats": st},
                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
         out.update(extra)
         print(json.dumps(out))

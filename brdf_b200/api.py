@@ -66,6 +66,8 @@ SIGNATURES = {
     "brdfgpu_destroy": (None, [_V]),
     "brdfgpu_last_error": (C.c_char_p, [_V]),
     "brdfgpu_launch_count": (C.c_ulonglong, [_V]),
+    "brdfgpu_fit_stats": (C.c_int, [_V, C.POINTER(C.c_ulonglong), C.c_int]),
+    "brdfgpu_lm_reduced_batching": (C.c_int, [C.c_int]),
     "brdfgpu_stream": (_V, [_V]),
     "brdfgpu_synchronize": (C.c_int, [_V]),
     "brdfgpu_samples_upload": (C.c_int, [_V, C.c_long, dptr, dptr, dptr, C.c_int, C.POINTER(_V)]),
@@ -296,6 +298,13 @@ class Context:
     @property
     def stream(self):
         return lib().brdfgpu_stream(self.handle)
+
+    def fit_stats(self):
+        """dict(jac_passes, cost_passes, cost_points, resident_samples, ctas) of the last global fit"""
+        buf = (C.c_ulonglong * 8)()
+        self._ok(lib().brdfgpu_fit_stats(self.handle, buf, 8))
+        return dict(jac_passes=int(buf[0]), cost_passes=int(buf[1]), cost_points=int(buf[2]), resident_samples=int(buf[3]),
+                    ctas=int(buf[4]), cyc_sweep=int(buf[5]), cyc_exchange=int(buf[6]), cyc_total=int(buf[7]))
 
     def synchronize(self):
         self._ok(lib().brdfgpu_synchronize(self.handle))

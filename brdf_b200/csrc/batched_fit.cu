@@ -25,6 +25,7 @@ struct BatchSpec {
 // G lanes per fit, S samples per lane held in registers (S == 0: samples re-read from memory)
 template <int G, int S>
 struct GroupEval {
+    static constexpr int kCostBatch = 1;
     static constexpr int SR = S > 0 ? S : 1;
     double c[SR], L[SR], x[SR];
     const double *gc, *gL, *gx, *traw;  // this fit's rows

@@ -97,6 +97,20 @@ BG_HDI PassParams make_pass_params(const double* p, int model, double delta, int
     return q;
 }
 
+// The four numbers a trial-point (cost-only) evaluation needs.
+struct CostPoint {
+    double kd, cks, n, l_lim;
+};
+
+BG_HDI CostPoint make_cost_point(const double* p, int model) {
+    CostPoint q;
+    q.kd = p[0];
+    q.n = p[2];
+    q.cks = model_coef(model, p[2]) * p[1];
+    q.l_lim = (lm_finite(q.n) && q.n != 0.0) ? kFastExpLimit / lm_abs(q.n) : -1.0;
+    return q;
+}
+
 #ifdef __CUDACC__
 // exp(y) for |y| <= 700 (no NaN/Inf handling, no subnormal results by construction)
 __device__ __forceinline__ double exp_core(double y) {
@@ -198,19 +212,22 @@ __device__ __forceinline__ void accumulate_jac(const PassParams& q, double c, do
     accumulate_normal(j0, j1, j2, e, acc);
 }
 
-__device__ __forceinline__ double residual_careful(const PassParams& q, double c, double traw, double x) {
+// residual e = x - f(p) of one sample (same arithmetic in every pass).  Q is PassParams or CostPoint.
+template <class Q>
+__device__ __forceinline__ double residual_careful(const Q& q, double c, double traw, double x) {
     return x - (q.kd * c + q.cks * pow_careful(traw, q.n));
 }
 
-// residual e = x - f(p) of one sample (same arithmetic as the passes)
-__device__ __forceinline__ double residual_of(const PassParams& q, double c, double L, double x,
+template <class Q>
+__device__ __forceinline__ double residual_of(const Q& q, double c, double L, double x,
                                               const double* __restrict__ traw, long i) {
     if (!(fabs(L) <= q.l_lim)) return residual_careful(q, c, traw[i], x);
     return x - __fma_rn(q.kd, c, q.cks * exp_core(q.n * L));
 }
 
 // One sample of a trial-point pass: only ||x - f(p)||^2.
-__device__ __forceinline__ void accumulate_cost(const PassParams& q, double c, double L, double x,
+template <class Q>
+__device__ __forceinline__ void accumulate_cost(const Q& q, double c, double L, double x,
                                                 const double* __restrict__ traw, long i, double* esq) {
     const double e = residual_of(q, c, L, x, traw, i);
     *esq = __fma_rn(e, e, *esq);

@@ -64,6 +64,7 @@ extern "C" int brdfgpu_create(int device, brdfgpu_ctx** out) {
         *ctx->h_seq = 0;
         e = cudaHostGetDevicePointer(&ctx->h_seq_dev, (void*)ctx->h_seq, 0);
     }
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_cells, sizeof(uint4) * 2 * 160 * 16);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_fitio, sizeof(GlobalFitOut));
     if (e == cudaSuccess) e = cudaHostAlloc(&ctx->h_fitio, sizeof(GlobalFitOut), cudaHostAllocDefault);
     if (e != cudaSuccess) {
@@ -80,7 +81,7 @@ extern "C" void brdfgpu_destroy(brdfgpu_ctx* ctx) {
     brdfgpu_comm_destroy(ctx);
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->d_partials); cudaFree(ctx->d_sync); cudaFree(ctx->d_result); cudaFree(ctx->d_fitio);
+    cudaFree(ctx->d_partials); cudaFree(ctx->d_sync); cudaFree(ctx->d_result); cudaFree(ctx->d_fitio); cudaFree(ctx->d_cells);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     if (ctx->h_seq) cudaFreeHost((void*)ctx->h_seq);
     if (ctx->h_fitio) cudaFreeHost(ctx->h_fitio);
@@ -92,6 +93,12 @@ extern "C" const char* brdfgpu_last_error(brdfgpu_ctx* ctx) { return ctx ? ctx->
 extern "C" unsigned long long brdfgpu_launch_count(brdfgpu_ctx* ctx) {
     ctx = ctx_or_default(ctx);
     return ctx ? ctx->launches : 0ull;
+}
+extern "C" int brdfgpu_fit_stats(brdfgpu_ctx* ctx, unsigned long long* out, int count) {
+    ctx = ctx_or_default(ctx);
+    if (!ctx || !out) return BRDFGPU_LM_ERROR;
+    for (int i = 0; i < count && i < 8; ++i) out[i] = ctx->fit_stats[i];
+    return 0;
 }
 extern "C" void* brdfgpu_stream(brdfgpu_ctx* ctx) {
     ctx = ctx_or_default(ctx);
@@ -439,6 +446,7 @@ extern "C" void brdfgpu_batch_free(brdfgpu_ctx* ctx, brdfgpu_batch* b) {
 // ------------------------------------------------------------------------------------------------
 namespace {
 struct CallbackEval {
+    static constexpr int kCostBatch = 1;
     brdfgpu_reduced_jac_t jac_cb;
     brdfgpu_reduced_cost_t cost_cb;
     void* user;
@@ -451,7 +459,24 @@ struct CallbackEval {
         return e;
     }
 };
+// the same callbacks, but the projected-gradient walk hands over its candidates eight at a time,
+// exactly as the persistent fit kernel receives them
+struct CallbackEvalMany : CallbackEval {
+    static constexpr int kCostBatch = 8;
+    int max_batch = 0;
+    void cost_many(const double* pts, int cnt, double* esq, bool* bad) {
+        if (cnt > max_batch) max_batch = cnt;
+        for (int c = 0; c < cnt; ++c) esq[c] = cost(pts + c * m, bad[c]);
+    }
+};
 }  // namespace
+
+static int g_reduced_batched = 0;
+extern "C" int brdfgpu_lm_reduced_batching(int on) {
+    const int prev = g_reduced_batched;
+    g_reduced_batched = on ? 1 : 0;
+    return prev;
+}
 
 extern "C" int brdfgpu_lm_bc_reduced(brdfgpu_reduced_jac_t jac_cb, brdfgpu_reduced_cost_t cost_cb, void* user, double* p,
                                      int m, long n, const double* lb, const double* ub, const double* dscl, int itmax,
@@ -470,9 +495,16 @@ extern "C" int brdfgpu_lm_bc_reduced(brdfgpu_reduced_jac_t jac_cb, brdfgpu_reduc
     }
     const Box box{lb, ub};
     box_project(p, box, m);
-    CallbackEval ev{jac_cb, cost_cb, user, m};
-    const int ret = lm_bc_der<kMaxM>(ev, m, p, lb ? lbs : nullptr, ub ? ubs : nullptr, dscl, lm_options(opts, itmax),
-                                     fit_info, JtJ);
+    int ret;
+    if (g_reduced_batched) {
+        CallbackEvalMany ev;
+        ev.jac_cb = jac_cb; ev.cost_cb = cost_cb; ev.user = user; ev.m = m;
+        ret = lm_bc_der<kMaxM>(ev, m, p, lb ? lbs : nullptr, ub ? ubs : nullptr, dscl, lm_options(opts, itmax), fit_info, JtJ);
+        g_reduced_batched = ev.max_batch > 0 ? ev.max_batch : 1;
+    } else {
+        CallbackEval ev{jac_cb, cost_cb, user, m};
+        ret = lm_bc_der<kMaxM>(ev, m, p, lb ? lbs : nullptr, ub ? ubs : nullptr, dscl, lm_options(opts, itmax), fit_info, JtJ);
+    }
     if (info)
         for (int i = 0; i < 10; ++i) info[i] = fit_info[i];
     if (covar) {

@@ -51,7 +51,12 @@ struct brdfgpu_ctx {
     // persistent-fit in/out block
     void* d_fitio = nullptr;
     void* h_fitio = nullptr;  // pinned
-    int persistent_blocks_per_sm = 0;
+    uint4* d_cells = nullptr;     // flagged exchange cells of the persistent fit: 2 x kMaxPersistBlocks x 16
+    long persist_smem_max = 0;    // dynamic shared memory one CTA of the persistent fit may use (0: not probed, <0: unusable)
+    // what the last global fit did: sweeps with a Jacobian, cost-only sweeps, trial points evaluated
+    // (>= the levmar-counted ones: the projected-gradient walk is evaluated eight points per sweep),
+    // samples resident in shared memory, CTAs
+    unsigned long long fit_stats[8] = {0};
 
     // multi-GPU
     void* nccl_comm = nullptr;
@@ -118,7 +123,9 @@ struct GlobalFitSpec {
 struct GlobalFitOut {
     int ret;
     unsigned peer_epoch;  // exchange tag after the fit (all ranks advance in lock step)
-    int peer_timeout;     // a peer never delivered: the fit was abandoned
+    int aborted;          // an exchange partner never delivered: the fit was abandoned
+    unsigned jac_passes, cost_passes, cost_points;
+    long long cyc_sweep, cyc_exchange, cyc_total;  // SM cycles of CTA 0 / thread 0
     double p[kMaxM];
     double info[10];
     double JtJ[kMaxM * kMaxM];

@@ -55,13 +55,13 @@ __device__ __forceinline__ Pair load_pair(const double2* __restrict__ c2, const 
 }
 
 template <int JAC>
-__device__ __forceinline__ void stream_jac(const SampleView& v, const PassParams& q, long tid, long nthreads,
-                                           double* acc) {
+__device__ __forceinline__ void stream_jac(const SampleView& v, const PassParams& q, long first_pair, long tid,
+                                           long nthreads, double* acc) {
     const double2* __restrict__ c2 = reinterpret_cast<const double2*>(v.c);
     const double2* __restrict__ l2 = reinterpret_cast<const double2*>(v.L);
     const double2* __restrict__ x2 = reinterpret_cast<const double2*>(v.x);
     const long npair = v.n >> 1;
-    long i = tid;
+    long i = first_pair + tid;
     Pair cur;
     if (i < npair) cur = load_pair(c2, l2, x2, i);
     while (i < npair) {
@@ -79,13 +79,14 @@ __device__ __forceinline__ void stream_jac(const SampleView& v, const PassParams
     }
 }
 
-__device__ __forceinline__ void stream_cost(const SampleView& v, const PassParams& q, long tid, long nthreads,
+template <class Q>
+__device__ __forceinline__ void stream_cost(const SampleView& v, const Q& q, long first_pair, long tid, long nthreads,
                                             double* acc2 /* [0] = sum e^2 */) {
     const double2* __restrict__ c2 = reinterpret_cast<const double2*>(v.c);
     const double2* __restrict__ l2 = reinterpret_cast<const double2*>(v.L);
     const double2* __restrict__ x2 = reinterpret_cast<const double2*>(v.x);
     const long npair = v.n >> 1;
-    long i = tid;
+    long i = first_pair + tid;
     Pair cur;
     if (i < npair) cur = load_pair(c2, l2, x2, i);
     while (i < npair) {
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(kPassThreads, 3) k_normal_eq(SampleView v, Pas
     double acc[NACC];
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
-    stream_jac<JAC>(v, q, (long)blockIdx.x * blockDim.x + threadIdx.x, (long)gridDim.x * blockDim.x, acc);
+    stream_jac<JAC>(v, q, 0, (long)blockIdx.x * blockDim.x + threadIdx.x, (long)gridDim.x * blockDim.x, acc);
     block_reduce_to<NACC>(acc, red, partials + (long)blockIdx.x * NACC);
     last_block_finish<NACC>(partials, ticket, red, pub);
 }
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(kPassThreads, 4) k_cost(SampleView v, PassPara
     __shared__ double red[(kPassThreads / 32)];
     double acc[1] = {0.0};
     if (COUNT_BAD) stream_count_bad(v, q, (long)blockIdx.x * blockDim.x + threadIdx.x, (long)gridDim.x * blockDim.x, acc);
-    else stream_cost(v, q, (long)blockIdx.x * blockDim.x + threadIdx.x, (long)gridDim.x * blockDim.x, acc);
+    else stream_cost(v, q, 0, (long)blockIdx.x * blockDim.x + threadIdx.x, (long)gridDim.x * blockDim.x, acc);
     block_reduce_to<1>(acc, red, partials + (long)blockIdx.x);
     last_block_finish<1>(partials, ticket, red, pub);
 }
@@ -427,6 +428,7 @@ int model_jacobian(brdfgpu_ctx* ctx, const double* p, const double* angles_host,
 // host driver: lm_engine on sums produced kernel by kernel
 // ------------------------------------------------------------------------------------------------
 struct HostEval {
+    static constexpr int kCostBatch = 1;
     brdfgpu_ctx* ctx;
     const brdfgpu_samples* s;
     double delta;
@@ -467,164 +469,391 @@ struct HostEval {
 
 // ------------------------------------------------------------------------------------------------
 // persistent driver: the whole fit inside one cooperative kernel
+//
+//   * one CTA of 512 threads per SM; every thread runs the same levmar control code (lm_engine.cuh)
+//     on the same reduced sums, so the grid takes identical decisions with no broadcast;
+//   * the CTA's slice of the sample set is copied ONCE into its shared memory (up to ~210 KB per SM,
+//     148 SMs -> ~1.3 * 10^6 samples stay on chip for the whole fit: BASELINE configs[1] never
+//     touches HBM or L2 again after the first microseconds); samples beyond that capacity are
+//     streamed from global memory every pass (register double buffer);
+//   * one grid-wide exchange per evaluation: every CTA publishes its partial sums as 16-byte
+//     flagged cells {lo, tag, hi, tag} and polls the cells of all CTAs -- the data IS the barrier
+//     (no counter, no second round trip); the sums are then added in a fixed order, so every CTA
+//     (and every rank, below) holds identical bits;
+//   * the projected-gradient walk hands its candidate points to cost_many() eight at a time: one
+//     sweep over the samples and one exchange for eight levmar function evaluations.
 // ------------------------------------------------------------------------------------------------
-constexpr int kPersistThreads = 512;  // one CTA per SM, 16 warps, <= 128 registers per thread
+constexpr int kPersistThreads = 512;    // 16 warps, <= 128 registers per thread
+constexpr int kMaxPersistBlocks = 160;  // >= SM count (148 on B200)
+constexpr int kGridCostBatch = 8;       // trial points per cost_many() sweep (<= NACC)
+constexpr long long kSpinCycles = 6000000000LL;  // ~3 s at 2 GHz, then the fit is abandoned
 
-// Grid-wide barrier for the cooperative kernel: one atomic per CTA on a monotonically increasing
-// counter, everybody spins on an acquire load.  (Cheaper than cooperative_groups' grid.sync(): the
-// partial sums ride on the same release/acquire, so one barrier per evaluation is all there is.)
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target, const int* abort_flag) {
-    target += gridDim.x;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(counter, 1u);
-        unsigned seen, spins = 0;
-        do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
-            // a CTA that gave up on a peer rank (peer_exchange) leaves the control loop early: do not
-            // wait for it forever
-            if (abort_flag && (++spins & 0x3ffu) == 0 && *(volatile const int*)abort_flag) break;
-        } while (seen < target);
-    }
-    __syncthreads();
-}
-
-// ------------------------------------------------------------------------------------------------
-// fused cross-GPU all-reduce (global mode on several GPUs): the exchange step of an evaluation
-// happens INSIDE the fit kernel over NVLink peer memory, so a multi-GPU fit is still one launch per
-// rank.  After the local grid reduction CTA 0 of every rank stores its rank's sums as flagged
-// cells into slot [parity][rank] of EVERY rank's exchange buffer (peer stores through NVSwitch);
-// every CTA then polls its own rank's buffer until all slots carry the current tag and adds them in
-// rank order -- identical bits on all ranks, so all ranks take identical LM decisions with no
-// broadcast.  Two parities: a rank can run at most one exchange ahead of the slowest CTA of any peer.
-// ------------------------------------------------------------------------------------------------
-constexpr long long kPeerSpinCycles = 6000000000LL;  // ~3 s at 2 GHz, then the fit is abandoned
-
-__device__ __forceinline__ void peer_store_cell(uint4* dst, double v, unsigned tag) {
+__device__ __forceinline__ void store_cell(uint4* dst, double v, unsigned tag) {
     const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
     asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(lo), "r"(tag), "r"(hi), "r"(tag)
                  : "memory");
 }
-__device__ __forceinline__ uint4 peer_load_cell(const uint4* src) {
+__device__ __forceinline__ uint4 load_cell(const uint4* src) {
     uint4 c;
     asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w) : "l"(src)
                  : "memory");
     return c;
 }
-
-// in: res[0..NV) = this rank's sums (shared, complete); out: res[0..NV) = sums over all ranks
-template <int NV>
-__device__ __forceinline__ void peer_exchange(PeerView& pv, double* res, double* stage /*shared [kMaxRanks*NV]*/,
-                                              int* timeout_flag) {
-    if (pv.nranks <= 1) return;
-    pv.epoch = pv.epoch + 1u ? pv.epoch + 1u : 1u;  // never 0: the buffers start zeroed
-    const unsigned tag = pv.epoch;
-    const int par = (int)(tag & 1u);
-    const int r = threadIdx.x / NV, k = threadIdx.x % NV;
-    if (threadIdx.x < NV * pv.nranks) {
-        if (blockIdx.x == 0)  // (also after a timeout: the peers must not wait for this rank in turn)
-            peer_store_cell(pv.remote[r] + ((long)(par * kMaxRanks + pv.rank) * kPeerCellsPerRank + k), res[k], tag);
-        const uint4* src = pv.local + ((long)(par * kMaxRanks + r) * kPeerCellsPerRank + k);
+// Spin until both halves of the cell carry `tag`.  Every 8-byte half {word, tag} is written
+// atomically, so matching tags mean the whole double is there (no fence, no separate flag).
+__device__ __forceinline__ double wait_cell(const uint4* src, unsigned tag, int* abort_flag) {
+    uint4 c = load_cell(src);
+    if (c.y != tag || c.w != tag) {
         const long long t0 = clock64();
         unsigned spins = 0;
-        uint4 c = peer_load_cell(src);
-        while (c.y != tag || c.w != tag) {
-            if ((++spins & 0xffu) == 0 && (clock64() - t0 > kPeerSpinCycles || *(volatile int*)timeout_flag)) {
-                *timeout_flag = 1;
-                c.x = 0u; c.z = 0x7ff80000u;  // NaN: the control loop stops with reason 7
-                break;
+        do {
+            if ((++spins & 0xffu) == 0 && (clock64() - t0 > kSpinCycles || *(volatile int*)abort_flag)) {
+                *abort_flag = 1;  // somebody (a peer GPU) never delivered: everybody gives up
+                return __longlong_as_double(0x7ff8000000000000LL);  // NaN: the control loop stops with reason 7
             }
-            c = peer_load_cell(src);
-        }
-        stage[r * NV + k] = __hiloint2double((int)c.z, (int)c.x);
+            c = load_cell(src);
+        } while (c.y != tag || c.w != tag);
     }
-    __syncthreads();
-    if (threadIdx.x < NV) {
-        double sum = 0.0;
-        for (int q = 0; q < pv.nranks; ++q) sum += stage[q * NV + threadIdx.x];
-        res[threadIdx.x] = sum;
-    }
-    __syncthreads();
+    return __hiloint2double((int)c.z, (int)c.x);
 }
+__device__ __forceinline__ unsigned next_tag(unsigned e) { return e + 1u ? e + 1u : 1u; }  // never 0: buffers start zeroed
 
+struct FitStats {
+    unsigned jac_passes, cost_passes, cost_points, pad;
+    long long cyc_sweep, cyc_exchange;  // SM cycles spent streaming samples / in the grid-wide exchange
+};
+
+// What the control warp asks the CTA to do next (shared memory).
+enum SweepKind { kQuit = 0, kSweepJacForward, kSweepJacCentral, kSweepJacAnalytic, kSweepCost, kSweepMany, kSweepBad };
+struct SweepRequest {
+    int kind, cnt;  // cnt: trial points of kSweepMany / index of the point of kSweepBad
+    PassParams q;   // Jacobian sweeps
+    CostPoint pts[kGridCostBatch];
+};
+
+// Per-thread view of the persistent fit.  Warp 0 of every CTA runs the levmar control code
+// (lm_engine.cuh) -- its evaluator calls post a SweepRequest and join the sweep; warps 1..15 only
+// serve sweeps.  (All 512 threads running the control code redundantly cost more than the sweeps:
+// its ~1.5 KB of per-thread stack then overflows L1 next to 180 KB of resident samples.)
 struct GridEval {
+    static constexpr int kCostBatch = kGridCostBatch;
     SampleView v;
     int model, jkind;
     double delta;
-    double* partials;  // 2 x kMaxPassBlocks x NACC, double-buffered across evaluations
-    double* red;       // shared [(kPersistThreads/32) * NACC]
-    double* res;       // shared [NACC]
-    int parity;
-    unsigned* bar;     // grid barrier counter (zeroed before the launch)
-    unsigned bar_target;
-    PeerView peer;     // nranks == 1: no exchange
-    double* stage;     // shared [kMaxRanks * NACC]
-    int* timeout_flag; // global
+    // this CTA's resident slice (shared memory), in sample PAIRS
+    const double2 *sc, *sl, *sx;
+    int res_pairs;      // pairs held by this CTA
+    long res_first;     // global index of its first pair
+    long stream_first;  // pairs >= stream_first are streamed from global memory by the whole grid
+    // grid-wide exchange
+    uint4* cells;       // [2 parities][gridDim.x][NACC]
+    unsigned epoch;
+    double *red, *res, *stage;  // shared: [(threads/32)*NACC], [NACC], [kMaxPersistBlocks*NACC]
+    SweepRequest* req;          // shared
+    // cross-GPU exchange (nranks == 1: none)
+    PeerView peer;
+    double* pstage;             // shared [kMaxRanks*NACC]
+    int* abort_flag;            // global
+    FitStats stats;
+    long long t_mark;  // clock at the start of the current sweep
 
-    // one noinline instance per Jacobian kind: each gets its own register allocation
+    // ---- the sums of all CTAs (and all ranks) in res[0..NV), identical bits everywhere ----
+    template <int NV>
+    __device__ __forceinline__ void all_reduce(const double* acc) {
+        const long long t_in = clock64();
+        stats.cyc_sweep += t_in - t_mark;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double s = acc[k];
+#pragma unroll
+            for (int off = 16; off; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+            if (lane == 0) red[warp * NV + k] = s;
+        }
+        __syncthreads();
+        epoch = next_tag(epoch);
+        const unsigned tag = epoch;
+        uint4* base = cells + (long)(tag & 1u) * gridDim.x * NACC;
+        if (threadIdx.x < NV) {
+            double s = 0.0;
+            for (int w = 0; w < nwarps; ++w) s += red[w * NV + threadIdx.x];
+            store_cell(base + (long)blockIdx.x * NACC + threadIdx.x, s, tag);
+        }
+        // every thread collects up to 4 cells: all loads go out together, late ones are re-polled
+        constexpr int kPerThread = (kMaxPersistBlocks * NACC + kPersistThreads - 1) / kPersistThreads;
+        const int total = gridDim.x * NV;
+        uint4 c[kPerThread];
+        const uint4* src[kPerThread];
+#pragma unroll
+        for (int j = 0; j < kPerThread; ++j) {
+            const int idx = threadIdx.x + j * kPersistThreads;
+            const int b = idx / NV, k = idx - b * NV;
+            src[j] = base + (long)b * NACC + k;
+            if (idx < total) c[j] = load_cell(src[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < kPerThread; ++j) {
+            const int idx = threadIdx.x + j * kPersistThreads;
+            if (idx < total) {
+                double val;
+                if (c[j].y == tag && c[j].w == tag) val = __hiloint2double((int)c[j].z, (int)c[j].x);
+                else val = wait_cell(src[j], tag, abort_flag);
+                stage[idx] = val;
+            }
+        }
+        __syncthreads();
+        for (int k = warp; k < NV; k += nwarps) {  // fixed order: lanes stride the CTAs, butterfly
+            double s = 0.0;
+            for (int b = lane; b < gridDim.x; b += 32) s += stage[b * NV + k];
+#pragma unroll
+            for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            if (lane == 0) res[k] = s;
+        }
+        __syncthreads();
+        if (peer.nranks > 1) peer_exchange<NV>();
+        stats.cyc_exchange += clock64() - t_in;
+    }
+
+    // Cross-GPU step, fused into the same kernel: CTA 0 of every rank stores its rank's sums as
+    // flagged cells into slot [parity][rank] of EVERY rank's exchange buffer (peer stores over
+    // NVLink / NVSwitch); every CTA polls its own rank's buffer until all slots carry the tag and
+    // adds them in rank order -- identical bits on all ranks, so all ranks take identical LM
+    // decisions.  Two parities: a rank can be at most one exchange ahead of any CTA of any peer.
+    template <int NV>
+    __device__ __forceinline__ void peer_exchange() {
+        peer.epoch = next_tag(peer.epoch);
+        const unsigned tag = peer.epoch;
+        const int par = (int)(tag & 1u);
+        const int r = threadIdx.x / NV, k = threadIdx.x - r * NV;
+        if (threadIdx.x < NV * peer.nranks) {
+            if (blockIdx.x == 0)
+                store_cell(peer.remote[r] + ((long)(par * kMaxRanks + peer.rank) * kPeerCellsPerRank + k), res[k], tag);
+            pstage[r * NV + k] = wait_cell(peer.local + ((long)(par * kMaxRanks + r) * kPeerCellsPerRank + k), tag, abort_flag);
+        }
+        __syncthreads();
+        if (threadIdx.x < NV) {
+            double sum = 0.0;
+            for (int q = 0; q < peer.nranks; ++q) sum += pstage[q * NV + threadIdx.x];
+            res[threadIdx.x] = sum;
+        }
+        __syncthreads();
+    }
+
+    // ---- sweeps (all threads of the CTA) ----
     template <int JAC>
-    __device__ __noinline__ void jac_pass(const PassParams& q) {
+    __device__ __noinline__ void jac_sweep() {
+        t_mark = clock64();
+        const PassParams q = req->q;
         double acc[NACC];
 #pragma unroll
         for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
-        stream_jac<JAC>(v, q, (long)blockIdx.x * blockDim.x + threadIdx.x, (long)gridDim.x * blockDim.x, acc);
-        double* buf = partials + (long)parity * kMaxPassBlocks * NACC;
-        block_reduce_to<NACC>(acc, red, buf + (long)blockIdx.x * NACC);
+        for (int i = threadIdx.x; i < res_pairs; i += blockDim.x) {
+            const double2 c = sc[i], l = sl[i], x = sx[i];
+            const long g = 2 * (res_first + i);
+            accumulate_jac<JAC>(q, c.x, l.x, x.x, v.traw, g, acc);
+            accumulate_jac<JAC>(q, c.y, l.y, x.y, v.traw, g + 1, acc);
+        }
+        stream_jac<JAC>(v, q, stream_first, (long)blockIdx.x * blockDim.x + threadIdx.x, (long)gridDim.x * blockDim.x, acc);
+        all_reduce<NACC>(acc);
+    }
+
+    // sum of squared residuals at one point over this thread's share of the samples
+    __device__ __forceinline__ double resident_cost(const CostPoint& q) const {
+        double a0 = 0.0, a1 = 0.0;  // two pairs in flight: four independent exp chains per thread
+        int i = threadIdx.x;
+        for (; i + (int)blockDim.x < res_pairs; i += 2 * blockDim.x) {
+            const int i2 = i + blockDim.x;
+            const double2 c = sc[i], l = sl[i], x = sx[i];
+            const double2 d = sc[i2], m = sl[i2], y = sx[i2];
+            const long g = 2 * (res_first + i), h = 2 * (res_first + i2);
+            accumulate_cost(q, c.x, l.x, x.x, v.traw, g, &a0);
+            accumulate_cost(q, d.x, m.x, y.x, v.traw, h, &a1);
+            accumulate_cost(q, c.y, l.y, x.y, v.traw, g + 1, &a0);
+            accumulate_cost(q, d.y, m.y, y.y, v.traw, h + 1, &a1);
+        }
+        if (i < res_pairs) {
+            const double2 c = sc[i], l = sl[i], x = sx[i];
+            const long g = 2 * (res_first + i);
+            accumulate_cost(q, c.x, l.x, x.x, v.traw, g, &a0);
+            accumulate_cost(q, c.y, l.y, x.y, v.traw, g + 1, &a1);
+        }
+        return a0 + a1;
+    }
+
+    __device__ __noinline__ void cost_sweep() {
+        t_mark = clock64();
+        const CostPoint q = req->pts[0];
+        double acc[1];
+        acc[0] = resident_cost(q);
+        stream_cost(v, q, stream_first, (long)blockIdx.x * blockDim.x + threadIdx.x, (long)gridDim.x * blockDim.x, acc);
+        all_reduce<1>(acc);
+    }
+
+    // number of non-finite residuals at point req->pts[req->cnt] (rare second sweep)
+    __device__ __noinline__ void bad_sweep() {
+        t_mark = clock64();
+        const CostPoint q = req->pts[req->cnt];
+        double cnt[1] = {0.0};
+        for (int i = threadIdx.x; i < res_pairs; i += blockDim.x) {
+            const double2 c = sc[i], l = sl[i], x = sx[i];
+            const long g = 2 * (res_first + i);
+            cnt[0] += lm_finite(residual_of(q, c.x, l.x, x.x, v.traw, g)) ? 0.0 : 1.0;
+            cnt[0] += lm_finite(residual_of(q, c.y, l.y, x.y, v.traw, g + 1)) ? 0.0 : 1.0;
+        }
+        const long nth = (long)gridDim.x * blockDim.x;
+        for (long i = 2 * stream_first + (long)blockIdx.x * blockDim.x + threadIdx.x; i < v.n; i += nth)
+            cnt[0] += lm_finite(residual_of(q, v.c[i], v.L[i], v.x[i], v.traw, i)) ? 0.0 : 1.0;
+        all_reduce<1>(cnt);
+    }
+
+    // up to kGridCostBatch trial points in ONE sweep + ONE exchange
+    __device__ __noinline__ void many_sweep() {
+        t_mark = clock64();
+        const int cnt = req->cnt;
+        double acc[kGridCostBatch];
+#pragma unroll
+        for (int k = 0; k < kGridCostBatch; ++k) acc[k] = 0.0;
+        // resident slice: candidate-outer, parameters in registers, samples re-read from shared memory
+#pragma unroll
+        for (int k = 0; k < kGridCostBatch; ++k)
+            if (k < cnt) acc[k] = resident_cost(req->pts[k]);
+        // streamed remainder: sample-outer (one read of the sample for all candidates)
+        {
+            const double2* __restrict__ c2 = reinterpret_cast<const double2*>(v.c);
+            const double2* __restrict__ l2 = reinterpret_cast<const double2*>(v.L);
+            const double2* __restrict__ x2 = reinterpret_cast<const double2*>(v.x);
+            const long npair = v.n >> 1, nth = (long)gridDim.x * blockDim.x;
+            for (long i = stream_first + (long)blockIdx.x * blockDim.x + threadIdx.x; i < npair; i += nth) {
+                const Pair s = load_pair(c2, l2, x2, i);
+#pragma unroll
+                for (int k = 0; k < kGridCostBatch; ++k) {
+                    if (k < cnt) {
+                        const CostPoint q = req->pts[k];
+                        accumulate_cost(q, s.c.x, s.l.x, s.x.x, v.traw, 2 * i, &acc[k]);
+                        accumulate_cost(q, s.c.y, s.l.y, s.x.y, v.traw, 2 * i + 1, &acc[k]);
+                    }
+                }
+            }
+            if ((v.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+                const long j = v.n - 1;
+#pragma unroll
+                for (int k = 0; k < kGridCostBatch; ++k)
+                    if (k < cnt) accumulate_cost(req->pts[k], v.c[j], v.L[j], v.x[j], v.traw, j, &acc[k]);
+            }
+        }
+        all_reduce<kGridCostBatch>(acc);
+    }
+
+    __device__ __forceinline__ void run_sweep(int kind) {
+        switch (kind) {
+            case kSweepJacForward: jac_sweep<kJacForward>(); break;
+            case kSweepJacCentral: jac_sweep<kJacCentral>(); break;
+            case kSweepJacAnalytic: jac_sweep<kJacAnalytic>(); break;
+            case kSweepCost: cost_sweep(); break;
+            case kSweepMany: many_sweep(); break;
+            default: bad_sweep(); break;
+        }
+    }
+
+    // warps 1..15: serve sweeps until the control warp quits
+    __device__ __forceinline__ void serve() {
+        for (;;) {
+            __syncthreads();  // the request is posted
+            const int kind = req->kind;
+            if (kind == kQuit) return;
+            run_sweep(kind);
+        }
+    }
+
+    // ---- control warp only: the Evaluator of lm_engine.cuh ----
+    __device__ __forceinline__ void post(int kind) {
+        if (threadIdx.x == 0) req->kind = kind;
+        __syncthreads();
+        if (kind != kQuit) run_sweep(kind);
     }
 
     __device__ __forceinline__ void jac(const double* p, double* JtJ, double* Jte) {
-        const PassParams q = make_pass_params(p, model, delta, jkind);
-        if (jkind == kJacForward) jac_pass<kJacForward>(q);
-        else if (jkind == kJacCentral) jac_pass<kJacCentral>(q);
-        else jac_pass<kJacAnalytic>(q);
-        double* buf = partials + (long)parity * kMaxPassBlocks * NACC;
-        parity ^= 1;
-        grid_barrier(bar, bar_target, peer.nranks > 1 ? timeout_flag : nullptr);
-        final_reduce<NACC>(buf, gridDim.x, res);
-        __syncthreads();
-        peer_exchange<NACC>(peer, res, stage, timeout_flag);
+        if (threadIdx.x == 0) req->q = make_pass_params(p, model, delta, jkind);
+        post(jkind == kJacForward ? kSweepJacForward : jkind == kJacCentral ? kSweepJacCentral : kSweepJacAnalytic);
+        ++stats.jac_passes;
         JtJ[0] = res[A00]; JtJ[1] = res[A01]; JtJ[2] = res[A02];
         JtJ[3] = res[A01]; JtJ[4] = res[A11]; JtJ[5] = res[A12];
         JtJ[6] = res[A02]; JtJ[7] = res[A12]; JtJ[8] = res[A22];
         Jte[0] = res[G0]; Jte[1] = res[G1]; Jte[2] = res[G2];
-        __syncthreads();  // res is rewritten by the next pass's exchange before its barrier
     }
 
-    __device__ __forceinline__ double scalar_pass(const PassParams& q, bool count_bad) {
-        double acc[1] = {0.0};
-        const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long)gridDim.x * blockDim.x;
-        if (count_bad) stream_count_bad(v, q, tid, nth, acc);
-        else stream_cost(v, q, tid, nth, acc);
-        double* buf = partials + (long)parity * kMaxPassBlocks * NACC;
-        parity ^= 1;
-        block_reduce_to<1>(acc, red, buf + (long)blockIdx.x);
-        grid_barrier(bar, bar_target, peer.nranks > 1 ? timeout_flag : nullptr);
-        final_reduce<1>(buf, gridDim.x, res);
-        __syncthreads();
-        peer_exchange<1>(peer, res, stage, timeout_flag);
-        const double out = res[0];
-        __syncthreads();  // res is rewritten by the next pass's exchange before its barrier
-        return out;
+    __device__ __forceinline__ double count_bad(int k) {
+        if (threadIdx.x == 0) req->cnt = k;
+        post(kSweepBad);
+        ++stats.cost_passes;
+        return res[0];
     }
 
-    __device__ __noinline__ double cost(const double* p, bool& bad) {
-        const PassParams q = make_pass_params(p, model, 1.0, kJacAnalytic);
-        const double esq = scalar_pass(q, false);
+    __device__ __forceinline__ double cost(const double* p, bool& bad) {
+        if (threadIdx.x == 0) req->pts[0] = make_cost_point(p, model);
+        post(kSweepCost);
+        ++stats.cost_passes;
+        ++stats.cost_points;
+        const double esq = res[0];
         bad = false;
-        if (!lm_finite(esq)) bad = scalar_pass(q, true) != 0.0;  // uniform across the grid: same sums everywhere
+        if (!lm_finite(esq)) bad = count_bad(0) != 0.0;  // uniform across the grid: same sums everywhere
         return esq;
+    }
+
+    __device__ __forceinline__ void cost_many(const double* pts, int cnt, double* esq, bool* bad) {
+        if (threadIdx.x < cnt) req->pts[threadIdx.x] = make_cost_point(pts + 3 * threadIdx.x, model);
+        if (threadIdx.x == 0) req->cnt = cnt;
+        post(kSweepMany);
+        ++stats.cost_passes;
+        stats.cost_points += cnt;
+        for (int k = 0; k < cnt; ++k) esq[k] = res[k];
+        for (int k = 0; k < cnt; ++k) {
+            bad[k] = false;
+            if (!lm_finite(esq[k])) bad[k] = count_bad(k) != 0.0;
+        }
     }
 };
 
 __global__ void __launch_bounds__(kPersistThreads, 1) k_persistent_fit(SampleView v, int model, GlobalFitSpec spec,
-                                                                        double* partials, unsigned* barrier,
+                                                                        uint4* cells, long resident_pairs,
                                                                         PeerView peer, GlobalFitOut* out) {
+    extern __shared__ double2 smem_dyn[];
     __shared__ double red[(kPersistThreads / 32) * NACC];
     __shared__ double res[NACC];
-    __shared__ double stage[kMaxRanks * NACC];
-    if (blockIdx.x == 0 && threadIdx.x == 0) out->peer_timeout = 0;
-    GridEval ev{v, model, spec.jac_mode, spec.delta, partials, red, res, 0, barrier, 0u, peer, stage, &out->peer_timeout};
+    __shared__ double stage[kMaxPersistBlocks * NACC];
+    __shared__ double pstage[kMaxRanks * NACC];
+    __shared__ SweepRequest req;
+
+    // this CTA's resident slice: pairs [first, last) of the first `resident_pairs` pairs, balanced
+    const long first = resident_pairs * blockIdx.x / gridDim.x, last = resident_pairs * (blockIdx.x + 1) / gridDim.x;
+    const int cap = (int)((resident_pairs + gridDim.x - 1) / gridDim.x);
+    const int mine = (int)(last - first);
+    double2 *sc = smem_dyn, *sl = smem_dyn + cap, *sx = smem_dyn + 2 * cap;
+    {
+        const double2* __restrict__ c2 = reinterpret_cast<const double2*>(v.c);
+        const double2* __restrict__ l2 = reinterpret_cast<const double2*>(v.L);
+        const double2* __restrict__ x2 = reinterpret_cast<const double2*>(v.x);
+        for (int i = threadIdx.x; i < mine; i += blockDim.x) {
+            sc[i] = __ldg(c2 + first + i);
+            sl[i] = __ldg(l2 + first + i);
+            sx[i] = __ldg(x2 + first + i);
+        }
+    }
+    __syncthreads();
+
+    GridEval ev;
+    ev.v = v; ev.model = model; ev.jkind = spec.jac_mode; ev.delta = spec.delta;
+    ev.sc = sc; ev.sl = sl; ev.sx = sx; ev.res_pairs = mine; ev.res_first = first; ev.stream_first = resident_pairs;
+    ev.cells = cells; ev.epoch = 0u; ev.red = red; ev.res = res; ev.stage = stage; ev.req = &req;
+    ev.peer = peer; ev.pstage = pstage; ev.abort_flag = &out->aborted;
+    ev.stats = FitStats{0u, 0u, 0u, 0u, 0, 0};
+    ev.t_mark = 0;
+
+    if (threadIdx.x >= 32) {
+        ev.serve();
+        return;
+    }
+    const long long t_start = clock64();
     double p[3], info[10], JtJ[9];
     for (int i = 0; i < 3; ++i) p[i] = spec.p[i];
     int ret;
@@ -633,30 +862,64 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_persistent_fit(SampleVie
     else
         ret = lm_bc_der<3>(ev, 3, p, spec.has_lb ? spec.lb : nullptr, spec.has_ub ? spec.ub : nullptr,
                            spec.has_dscl ? spec.dscl : nullptr, spec.opt, info, JtJ);
+    ev.post(kQuit);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         out->ret = ret;
         out->peer_epoch = ev.peer.epoch;
+        out->jac_passes = ev.stats.jac_passes;
+        out->cost_passes = ev.stats.cost_passes;
+        out->cost_points = ev.stats.cost_points;
+        out->cyc_sweep = ev.stats.cyc_sweep;
+        out->cyc_exchange = ev.stats.cyc_exchange;
+        out->cyc_total = clock64() - t_start;
         for (int i = 0; i < 3; ++i) out->p[i] = p[i];
         for (int i = 0; i < 10; ++i) out->info[i] = info[i];
         for (int i = 0; i < 9; ++i) out->JtJ[i] = JtJ[i];
     }
 }
 
-static int persistent_grid(brdfgpu_ctx* ctx, long n) {
-    if (ctx->persistent_blocks_per_sm == 0) {
-        int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persistent_fit, kPersistThreads, 0) != cudaSuccess ||
-            per_sm < 1)
-            per_sm = -1;
-        ctx->persistent_blocks_per_sm = per_sm;
+// launch geometry of the persistent fit: grid (<= one CTA per SM), resident pairs, dynamic smem bytes
+struct PersistPlan {
+    int grid;
+    long resident_pairs;
+    size_t smem;
+};
+
+static bool persistent_plan(brdfgpu_ctx* ctx, long n, PersistPlan* plan) {
+    if (ctx->persist_smem_max < 0) return false;
+    if (ctx->persist_smem_max == 0) {  // first use: how much dynamic shared memory one CTA can have
+        cudaFuncAttributes fa;
+        int optin = 0;
+        if (cudaFuncGetAttributes(&fa, k_persistent_fit) != cudaSuccess ||
+            cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device) != cudaSuccess) {
+            ctx->persist_smem_max = -1;
+            return false;
+        }
+        long dyn = (long)optin - (long)fa.sharedSizeBytes - 1024;  // 1 KB per CTA is reserved by the system
+        if (dyn < 0) dyn = 0;
+        if (cudaFuncSetAttribute(k_persistent_fit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess) {
+            ctx->persist_smem_max = -1;
+            return false;
+        }
+        ctx->persist_smem_max = dyn > 0 ? dyn : 1;
     }
-    if (ctx->persistent_blocks_per_sm < 1) return 0;
-    long want = (n / 2 + kPersistThreads - 1) / kPersistThreads;
-    const long cap = (long)ctx->sm_count * ctx->persistent_blocks_per_sm;
-    if (want < 1) want = 1;
-    if (want > cap) want = cap;
-    if (want > kMaxPassBlocks) want = kMaxPassBlocks;
-    return (int)want;
+    const long npair = n >> 1;
+    long grid = (npair + kPersistThreads - 1) / kPersistThreads;  // small problems: fewer CTAs, shorter exchange
+    long cap = ctx->sm_count < kMaxPersistBlocks ? ctx->sm_count : kMaxPersistBlocks;
+    if (grid < 1) grid = 1;
+    if (grid > cap) grid = cap;
+    const long cap_pairs = ctx->persist_smem_max / (3 * (long)sizeof(double2));
+    long resident = npair < grid * cap_pairs ? npair : grid * cap_pairs;
+    // a slice is ceil(resident / grid) pairs at most
+    while (resident > 0 && (resident + grid - 1) / grid > cap_pairs) --resident;
+    plan->grid = (int)grid;
+    plan->resident_pairs = resident;
+    plan->smem = (size_t)((resident + grid - 1) / grid) * 3 * sizeof(double2);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persistent_fit, kPersistThreads, plan->smem) != cudaSuccess ||
+        per_sm < 1)
+        return false;
+    return true;
 }
 
 static void finish_info(double* info, const double* fit_info, int m, int jkind, bool dif_accounting) {
@@ -718,8 +981,9 @@ int global_fit(brdfgpu_ctx* ctx, const brdfgpu_samples* s, double* p, int m, con
     double fit_info[10], JtJ[9];
     int ret;
     const bool can_persist = ctx->coop && (ctx->nranks == 1 || ctx->peer_attached);
-    const int grid = (drive == BRDFGPU_DRIVE_PERSISTENT && can_persist) ? persistent_grid(ctx, s->n) : 0;
-    if (grid > 0) {
+    PersistPlan plan{0, 0, 0};
+    const bool persist = drive == BRDFGPU_DRIVE_PERSISTENT && can_persist && persistent_plan(ctx, s->n, &plan);
+    if (persist) {
         GlobalFitSpec spec;
         memset(&spec, 0, sizeof(spec));
         spec.m = m; spec.itmax = itmax; spec.jac_mode = jkind; spec.delta = delta; spec.opt = o;
@@ -733,10 +997,12 @@ int global_fit(brdfgpu_ctx* ctx, const brdfgpu_samples* s, double* p, int m, con
         }
         SampleView v = view_of(s);
         int model = s->model;
-        double* partials = ctx->d_partials;
         GlobalFitOut* d_out = static_cast<GlobalFitOut*>(ctx->d_fitio);
-        unsigned* barrier = ctx->d_sync + 4;
-        BG_CUDA_OK(ctx, cudaMemsetAsync(barrier, 0, sizeof(unsigned), ctx->stream));
+        uint4* cells = ctx->d_cells;
+        long resident_pairs = plan.resident_pairs;
+        // tags restart at 1 every launch: clear the cells this grid will use and the abort flag
+        BG_CUDA_OK(ctx, cudaMemsetAsync(cells, 0, sizeof(uint4) * 2 * (size_t)plan.grid * NACC, ctx->stream));
+        BG_CUDA_OK(ctx, cudaMemsetAsync(d_out, 0, sizeof(GlobalFitOut), ctx->stream));
         PeerView peer;
         memset(&peer, 0, sizeof(peer));
         peer.nranks = 1;
@@ -747,20 +1013,23 @@ int global_fit(brdfgpu_ctx* ctx, const brdfgpu_samples* s, double* p, int m, con
             peer.nranks = ctx->nranks;
             peer.epoch = ctx->peer_epoch;
         }
-        void* args[] = {&v, &model, &spec, &partials, &barrier, &peer, &d_out};
-        BG_CUDA_OK(ctx, cudaLaunchCooperativeKernel((const void*)k_persistent_fit, dim3(grid), dim3(kPersistThreads), args,
-                                                     0, ctx->stream));
+        void* args[] = {&v, &model, &spec, &cells, &resident_pairs, &peer, &d_out};
+        BG_CUDA_OK(ctx, cudaLaunchCooperativeKernel((const void*)k_persistent_fit, dim3(plan.grid), dim3(kPersistThreads), args,
+                                                     plan.smem, ctx->stream));
         ++ctx->launches;
         BG_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_fitio, d_out, sizeof(GlobalFitOut), cudaMemcpyDeviceToHost, ctx->stream));
         BG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
         const GlobalFitOut* h = static_cast<const GlobalFitOut*>(ctx->h_fitio);
-        if (ctx->nranks > 1) {
-            ctx->peer_epoch = h->peer_epoch;
-            if (h->peer_timeout) {
-                set_error(ctx, "multi-GPU fit abandoned: a peer rank never delivered its sums (peer exchange timeout)");
-                return BRDFGPU_LM_ERROR;
-            }
+        if (ctx->nranks > 1) ctx->peer_epoch = h->peer_epoch;
+        if (h->aborted) {
+            ctx->peer_attached = false;  // exchange tags are out of step now: peers must be re-attached
+            set_error(ctx, "fit abandoned: an exchange partner (CTA or peer GPU) never delivered its sums");
+            return BRDFGPU_LM_ERROR;
         }
+        ctx->fit_stats[0] = h->jac_passes; ctx->fit_stats[1] = h->cost_passes; ctx->fit_stats[2] = h->cost_points;
+        ctx->fit_stats[3] = (unsigned long long)plan.resident_pairs * 2; ctx->fit_stats[4] = (unsigned long long)plan.grid;
+        ctx->fit_stats[5] = (unsigned long long)h->cyc_sweep; ctx->fit_stats[6] = (unsigned long long)h->cyc_exchange;
+        ctx->fit_stats[7] = (unsigned long long)h->cyc_total;
         ret = h->ret;
         for (int i = 0; i < 3; ++i) p[i] = h->p[i];
         for (int i = 0; i < 10; ++i) fit_info[i] = h->info[i];
@@ -770,6 +1039,8 @@ int global_fit(brdfgpu_ctx* ctx, const brdfgpu_samples* s, double* p, int m, con
         if (unconstrained) ret = lm_der<3>(ev, 3, p, o, fit_info, JtJ);
         else ret = lm_bc_der<3>(ev, 3, p, lb ? lbs : nullptr, ub ? ubs : nullptr, dscl, o, fit_info, JtJ);
         if (ev.failed) return BRDFGPU_LM_ERROR;
+        ctx->fit_stats[0] = (unsigned long long)fit_info[8]; ctx->fit_stats[1] = (unsigned long long)fit_info[7];
+        ctx->fit_stats[2] = (unsigned long long)fit_info[7]; ctx->fit_stats[3] = ctx->fit_stats[4] = ctx->fit_stats[5] = ctx->fit_stats[6] = ctx->fit_stats[7] = 0;
     }
     finish_info(info, fit_info, m, jkind, jac_mode == BRDFGPU_JAC_FD);
     if (covar) {  // lmbc_core.c:994-1002

@@ -15,6 +15,7 @@
 // Evaluator concept:
 //     void   jac (const double* p, double* JtJ /*m*m row-major, full*/, double* Jte /*m*/);
 //     double cost(const double* p, bool& elems_nonfinite);
+//     static constexpr int kCostBatch;   // > 1: also cost_many(), see eval_cost_many_scaled
 #pragma once
 
 #include <cfloat>
@@ -215,6 +216,25 @@ BG_HDI double eval_cost_scaled(Eval& ev, const double* q, const double* dscl, in
     double ps[MM];
     for (int i = m; i-- > 0;) ps[i] = q[i] * dscl[i];
     return ev.cost(ps, bad);
+}
+
+// several trial points at once (projected-gradient walk): evaluators with kCostBatch > 1 provide
+//     void cost_many(const double* pts /*cnt x m*/, int cnt, double* esq /*cnt*/, bool* bad /*cnt*/);
+template <int MM, class Eval>
+BG_HDI void eval_cost_many_scaled(Eval& ev, const double* pts, int cnt, const double* dscl, int m, double* esq,
+                                  bool* bad) {
+    if constexpr (Eval::kCostBatch > 1) {
+        if (!dscl) {
+            ev.cost_many(pts, cnt, esq, bad);
+        } else {
+            double ps[Eval::kCostBatch * MM];
+            for (int c = 0; c < cnt; ++c)
+                for (int i = m; i-- > 0;) ps[c * m + i] = pts[c * m + i] * dscl[i];
+            ev.cost_many(ps, cnt, esq, bad);
+        }
+    } else {
+        for (int c = 0; c < cnt; ++c) esq[c] = eval_cost_scaled<MM>(ev, pts + c * m, dscl, m, bad[c]);
+    }
 }
 
 // info[] of lmbc_core.c:978-991 / lm_core.c:405-418
@@ -443,27 +463,51 @@ BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double*
                 tmp = 100.0 / (1.0 + tmp);
                 t0 = (tmp <= tini) ? tmp : tini;
 
-                for (t = gprevtaken ? t : t0; t > tming; t *= beta) {
-                    for (int i = 0; i < m; ++i) pDp[i] = p[i] - t * Jte[i];
-                    box_project(pDp, box, m);
-                    Dp_L2 = 0.0;
-                    for (int i = 0; i < m; ++i) {
-                        Dp[i] = tmp = pDp[i] - p[i];
-                        Dp_L2 += tmp * tmp;
+                // levmar walks t, t*beta, t*beta^2, ... one function evaluation at a time (:885-934).
+                // The candidate points of that walk depend only on p and J^T e, so an evaluator may
+                // take up to Eval::kCostBatch of them per call (one sweep over the samples, one
+                // reduction); they are consumed strictly in levmar's order with levmar's tests, and
+                // candidates past the stopping one are discarded and not counted in nfev.
+                constexpr int KB = Eval::kCostBatch;
+                double ts[KB], pts[KB * MM], es[KB];
+                bool bads[KB], pg_done = false;
+                t = gprevtaken ? t : t0;
+                while (t > tming && !pg_done) {
+                    int nc = 0;
+                    double tt = t;
+                    while (nc < KB && tt > tming) {
+                        ts[nc] = tt;
+                        for (int i = 0; i < m; ++i) pts[nc * m + i] = p[i] - tt * Jte[i];
+                        box_project(pts + nc * m, box, m);
+                        ++nc;
+                        tt *= beta;
                     }
-                    e_new = eval_cost_scaled<MM>(ev, pDp, dscl, m, bad);
-                    ++cnt.nfev;
-                    if (!lm_finite(e_new) && bad) { stop = 7; fatal = true; break; }
+                    eval_cost_many_scaled<MM>(ev, pts, nc, dscl, m, es, bads);
+                    bool restarted = false;
+                    for (int c = 0; c < nc; ++c) {
+                        t = ts[c];
+                        Dp_L2 = 0.0;
+                        for (int i = 0; i < m; ++i) {
+                            pDp[i] = pts[c * m + i];
+                            Dp[i] = tmp = pDp[i] - p[i];
+                            Dp_L2 += tmp * tmp;
+                        }
+                        e_new = es[c];
+                        ++cnt.nfev;
+                        if (!lm_finite(e_new) && bads[c]) { stop = 7; fatal = true; pg_done = true; break; }
 
-                    gTd = 0.0;
-                    for (int i = 0; i < m; ++i) gTd += Jte[i] * Dp[i];
+                        gTd = 0.0;
+                        for (int i = 0; i < m; ++i) gTd += Jte[i] * Dp[i];
 
-                    if (gprevtaken && e_new <= e_cur + 2.0 * 0.99999 * gTd) {  // starting t too small
-                        t = t0;
-                        gprevtaken = 0;
-                        continue;  // the loop increment still applies t *= beta (:926-930)
+                        if (gprevtaken && e_new <= e_cur + 2.0 * 0.99999 * gTd) {  // starting t too small
+                            t = t0 * beta;  // t = t0, then the loop increment of :885 still applies (:926-930)
+                            gprevtaken = 0;
+                            restarted = true;
+                            break;
+                        }
+                        if (e_new <= e_cur + 2.0 * alpha * gTd) { found = true; pg_done = true; break; }
                     }
-                    if (e_new <= e_cur + 2.0 * alpha * gTd) { found = true; break; }
+                    if (!pg_done && !restarted) t = tt;
                 }
                 if (fatal) goto done;
                 if (!found) { gprevtaken = 0; break; }

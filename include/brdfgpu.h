@@ -92,6 +92,13 @@ void brdfgpu_destroy(brdfgpu_ctx *ctx);
 const char *brdfgpu_last_error(brdfgpu_ctx *ctx);
 /* number of kernel launches this context has issued so far (bench.py's gpu_launches) */
 unsigned long long brdfgpu_launch_count(brdfgpu_ctx *ctx);
+/* What the last global fit of this context did (bench.py's roofline accounting):
+ * out[0] sweeps over the samples that built a Jacobian, out[1] cost-only sweeps, out[2] trial
+ * points evaluated by those (>= levmar's count: the projected-gradient walk is evaluated eight
+ * candidates per sweep and the unused ones are discarded), out[3] samples held in shared memory for
+ * the whole fit, out[4] CTAs of the persistent kernel (0 = host-driven fit), out[5..7] SM clock cycles CTA 0 spent
+ * sweeping samples / in the grid-wide exchange / in the kernel altogether. */
+int brdfgpu_fit_stats(brdfgpu_ctx *ctx, unsigned long long *out, int count);
 /* CUDA stream (cudaStream_t) the context launches on, for timing with CUDA events */
 void *brdfgpu_stream(brdfgpu_ctx *ctx);
 /* wait for everything queued on that stream */
@@ -283,6 +290,10 @@ int brdfgpu_lm_bc_reduced(brdfgpu_reduced_jac_t jac_cb, brdfgpu_reduced_cost_t c
 int brdfgpu_lm_unc_reduced(brdfgpu_reduced_jac_t jac_cb, brdfgpu_reduced_cost_t cost_cb, void *user,
                            double *p, int m, long n, int itmax, const double *opts, double *info,
                            double *covar);
+/* Test hook: on != 0 makes brdfgpu_lm_bc_reduced hand the projected-gradient candidates to the
+ * evaluator eight at a time, the way the persistent fit kernel receives them (results must not
+ * change).  Returns the previous setting; after a batched run, the largest batch that occurred. */
+int brdfgpu_lm_reduced_batching(int on);
 /* the on-device 3x3..8x8 solve of dAx_eq_b_LU_noLapack (Axb_core.c:1140-1277), host instantiation */
 int brdfgpu_Ax_eq_b_LU(const double *A, const double *B, double *x, int m);
 

@@ -56,8 +56,12 @@ elif what == "micro":
                 ctx.fit_global(s, A.REF_GLOBAL, drive=drive)
                 import time
                 t0 = time.perf_counter(); r = ctx.fit_global(s, A.REF_GLOBAL, drive=drive); dt = time.perf_counter() - t0
-                passes = r[2][8] + r[2][7] - 4 * r[2][8]
+                st = ctx.fit_stats()
+                passes = st["jac_passes"] + st["cost_passes"]
                 line += "  | %s fit %.2f ms, %d passes, %.2f us/pass" % (name, dt * 1e3, passes, dt * 1e6 / passes)
+                if st["cyc_total"]:
+                    line += " [kernel Mcyc: sweep %.2f exchange %.2f total %.2f, points %d]" % (
+                        st["cyc_sweep"] / 1e6, st["cyc_exchange"] / 1e6, st["cyc_total"] / 1e6, st["cost_points"])
         print(line, flush=True)
         del s
 elif what == "gather":

@@ -123,3 +123,25 @@ def test_lu_solver_matches_levmar():
             assert r0 == r1 and x0.tobytes() == x1.tobytes()
     z = np.zeros((3, 3)); z[0, 0] = 1.0
     assert A.lib().brdfgpu_Ax_eq_b_LU(A._d(z), A._d(np.ones(3)), A._d(np.zeros(3)), 3) == 0   # all-zero row
+
+
+@pytest.mark.parametrize("prob", BC, ids=[p["name"] for p in BC])
+def test_bc_engine_batched_projected_gradient_walk(prob):
+    """The persistent fit kernel receives the candidates of the projected-gradient walk
+    (lmbc_core.c:885-934) eight at a time and discards the ones past the stopping point: the
+    trajectory, p and info[0..9] (nfev included) must still be levmar's, bit for bit."""
+    lib, prefix = _ref_or_oracle()
+    f, j = K.callbacks(prob)
+    x = np.array(prob["x"], dtype=np.float64)
+    r_ret, r_p, r_info, _ = O.levmar_bc_der(lib, prefix, f, j, prob["p0"], x, prob["lb"], prob["ub"], prob["itmax"], K.OPTS)
+    jac_cb, cost_cb = _reduced_callbacks(prob)
+    A.lib().brdfgpu_lm_reduced_batching(1)
+    try:
+        ret, p, info, _ = A.lm_bc_reduced(jac_cb, cost_cb, prob["p0"], prob["n"], prob["lb"], prob["ub"], prob["itmax"], K.OPTS)
+    finally:
+        biggest = A.lib().brdfgpu_lm_reduced_batching(0)
+    assert ret == r_ret
+    assert p.tobytes() == r_p.tobytes()
+    assert info.tobytes() == r_info.tobytes()
+    if prob["name"] == "hatfldb":
+        assert biggest == 8   # this problem does walk the projected gradient

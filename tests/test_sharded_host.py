@@ -1,0 +1,105 @@
+"""N>1 host logic of the global mode on CPU: world_size-2 gloo.
+
+Every rank owns a contiguous shard of ONE sample set, forms its shard's partial sums (J^T J, J^T e,
+||e||^2 from levmar's forward-difference Jacobian, computed here with the oracle's BRDFFunc -- the
+checker stands in for the kernels, which need a GPU), all-reduces the 10 numbers through
+torch.distributed (gloo) and runs the PRODUCT control loop (brdfgpu_lm_bc_reduced = lm_engine.cuh
+on the host) redundantly.  All ranks must take identical decisions (bit-identical p / info with no
+broadcast) and land on the reference's answer for the whole set."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _worker(rank, world, port, n_total, out_dir):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    import oracle_lib as O
+    import synth
+    from brdf_b200 import api as A
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    c, td, th, x = synth.samples(n_total, seed=123)
+    lo, hi = rank * n_total // world, (rank + 1) * n_total // world
+    cs, ts, xs = (np.ascontiguousarray(a[lo:hi]) for a in (c, td, x))
+    n = hi - lo
+    angles = np.concatenate([cs, ts, np.zeros(n)])
+    ed = O.make_extra(angles, 1)
+    adata = C.cast(C.pointer(ed), C.c_void_p)
+    lib = O.oracle()
+    delta = A.REF_GLOBAL["opts"][4]
+    calls = {"jac": 0, "cost": 0}
+
+    def hx_at(pv):
+        hx = np.zeros(n)
+        pp = np.array(pv, dtype=np.float64)
+        lib.oracle_BRDFFunc(O.as_d(pp), O.as_d(hx), 3, n, adata)
+        return hx
+
+    def allreduce(v):
+        t = torch.from_numpy(np.array(v, dtype=np.float64))
+        dist.all_reduce(t)
+        return t.numpy()
+
+    def jac_cb(p, m, JtJ, Jte, _):
+        calls["jac"] += 1
+        pv = [p[i] for i in range(3)]
+        hx = hx_at(pv)
+        jac = np.zeros((n, 3))
+        for j in range(3):          # misc_core.c:153-170
+            d = max(abs(1e-4 * pv[j]), delta)
+            q = list(pv); q[j] += d
+            jac[:, j] = (hx_at(q) - hx) * (1.0 / d)
+        e = xs - hx
+        a = jac.T @ jac
+        sums = allreduce(np.concatenate([a.ravel(), jac.T @ e]))
+        for i in range(9):
+            JtJ[i] = sums[i]
+        for i in range(3):
+            Jte[i] = sums[9 + i]
+
+    def cost_cb(p, m, nonfinite, _):
+        calls["cost"] += 1
+        e = xs - hx_at([p[i] for i in range(3)])
+        s = allreduce([float(e @ e), float(np.count_nonzero(~np.isfinite(e)))])
+        nonfinite[0] = s[1]
+        return float(s[0])
+
+    g = A.REF_GLOBAL
+    ret, p, info, _ = A.lm_bc_reduced(jac_cb, cost_cb, g["p0"], n_total, g["lb"], g["ub"], g["itmax"], g["opts"])
+    np.save(os.path.join(out_dir, "r%d.npy" % rank), np.concatenate([[ret], p, info, [calls["jac"], calls["cost"]]]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_sharded_global_fit_two_ranks_gloo(tmp_path):
+    import torch.multiprocessing as mp
+
+    import oracle_lib as O
+    import synth
+
+    n_total, world = 4001, 2   # odd on purpose: ragged shards
+    port = 29600 + os.getpid() % 300
+    mp.spawn(_worker, args=(world, port, n_total, str(tmp_path)), nprocs=world, join=True)
+    r = [np.load(tmp_path / ("r%d.npy" % k)) for k in range(world)]
+    assert r[0].tobytes() == r[1].tobytes()            # identical decisions on both ranks, no broadcast
+    ret, p, info = int(r[0][0]), r[0][1:4], r[0][4:14]
+    c, td, th, x = synth.samples(n_total, seed=123)
+    lib, prefix = (O.ref(), "") if O.ref() is not None else (O.oracle(), "oracle_")
+    wret, wp, winfo = O.brdf_fit(lib, prefix, c, td, th, x, 1, O.REF_GLOBAL)
+    assert ret >= 0 and wret >= 0
+    np.testing.assert_allclose(p, wp, rtol=1e-4)                 # parameters (BASELINE north_star tolerance)
+    np.testing.assert_allclose(info[1], winfo[1], rtol=1e-6)     # final cost
+    assert int(info[6]) == int(winfo[6])
+    assert r[0][14] == info[8] and r[0][15] == info[7]           # one exchange per evaluation, counted as levmar does
