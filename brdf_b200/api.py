@@ -301,10 +301,11 @@ class Context:
 
     def fit_stats(self):
         """dict(jac_passes, cost_passes, cost_points, resident_samples, ctas) of the last global fit"""
-        buf = (C.c_ulonglong * 8)()
-        self._ok(lib().brdfgpu_fit_stats(self.handle, buf, 8))
+        buf = (C.c_ulonglong * 12)()
+        self._ok(lib().brdfgpu_fit_stats(self.handle, buf, 12))
         return dict(jac_passes=int(buf[0]), cost_passes=int(buf[1]), cost_points=int(buf[2]), resident_samples=int(buf[3]),
-                    ctas=int(buf[4]), cyc_sweep=int(buf[5]), cyc_exchange=int(buf[6]), cyc_total=int(buf[7]))
+                    ctas=int(buf[4]), cyc_sweep=int(buf[5]), cyc_exchange=int(buf[6]), cyc_total=int(buf[7]),
+                    cyc_exchange_phases=[int(buf[8 + i]) for i in range(4)])
 
     def synchronize(self):
         self._ok(lib().brdfgpu_synchronize(self.handle))

@@ -112,27 +112,55 @@ BG_HDI CostPoint make_cost_point(const double* p, int model) {
 }
 
 #ifdef __CUDACC__
-// exp(y) for |y| <= 700 (no NaN/Inf handling, no subnormal results by construction)
+// Coefficients of exp_core in constant memory: DFMA takes them as c[bank][offset] operands, so no
+// instruction is spent on materialising 64-bit immediates inside the sample loops.
+// near-minimax degree 10 on |r| <= ln2/2 (Chebyshev interpolation, max rel. error 9e-16)
+static __constant__ double kExpPoly[10] = {
+    0x1.26e46de8d8e82p-22, 0x1.7303e941557e0p-19, 0x1.a01b8fdc8d247p-16, 0x1.a01970086f448p-13, 0x1.6c16c0c5a5d65p-10,
+    0x1.11111130a260cp-7,  0x1.555555558aa3dp-5,  0x1.555555554a290p-3,  0x1.ffffffffffe8fp-2,  0x1.0000000000024p+0};
+static __constant__ double kExpRed[4] = {1.4426950408889634074, 6755399441055744.0 /* 1.5 * 2^52 */,
+                                         -6.93147180369123816490e-01, -1.90821492927058770002e-10};
+
+// exp(y) for |y| <= 700 (no NaN/Inf handling, no subnormal results by construction; any other
+// input gives garbage but never traps -- callers overwrite those lanes on their careful path)
 __device__ __forceinline__ double exp_core(double y) {
-    const double magic = 6755399441055744.0;  // 1.5 * 2^52: round-to-nearest integer in the low word
-    const double t = __fma_rn(y, 1.4426950408889634074, magic);
+    const double magic = kExpRed[1];  // round-to-nearest integer lands in the low word
+    const double t = __fma_rn(y, kExpRed[0], magic);
     const int k = __double2loint(t);
     const double kf = t - magic;
-    double r = __fma_rn(kf, -6.93147180369123816490e-01, y);
-    r = __fma_rn(kf, -1.90821492927058770002e-10, r);
-    // near-minimax degree 10 on |r| <= ln2/2 (Chebyshev interpolation, max rel. error 9e-16)
-    double v = 0x1.26e46de8d8e82p-22;
-    v = __fma_rn(v, r, 0x1.7303e941557e0p-19);
-    v = __fma_rn(v, r, 0x1.a01b8fdc8d247p-16);
-    v = __fma_rn(v, r, 0x1.a01970086f448p-13);
-    v = __fma_rn(v, r, 0x1.6c16c0c5a5d65p-10);
-    v = __fma_rn(v, r, 0x1.11111130a260cp-7);
-    v = __fma_rn(v, r, 0x1.555555558aa3dp-5);
-    v = __fma_rn(v, r, 0x1.555555554a290p-3);
-    v = __fma_rn(v, r, 0x1.ffffffffffe8fp-2);
-    v = __fma_rn(v, r, 0x1.0000000000024p+0);
+    double r = __fma_rn(kf, kExpRed[2], y);
+    r = __fma_rn(kf, kExpRed[3], r);
+    double v = kExpPoly[0];
+#pragma unroll
+    for (int i = 1; i < 10; ++i) v = __fma_rn(v, r, kExpPoly[i]);
     v = __fma_rn(v, r, 1.0);
     return __hiloint2double(__double2hiint(v) + (k << 20), __double2loint(v));
+}
+
+// N independent exponentials, written step-major (every step for all N before the next step) so the
+// instruction stream interleaves N dependency chains: one warp then keeps the FP64 pipe busy by
+// itself instead of relying on other warps to cover the DFMA latency.
+template <int N>
+__device__ __forceinline__ void exp_core_n(const double* y, double* out) {
+    const double magic = kExpRed[1];
+    double t[N], r[N], v[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) t[k] = __fma_rn(y[k], kExpRed[0], magic);
+#pragma unroll
+    for (int k = 0; k < N; ++k) r[k] = __fma_rn(t[k] - magic, kExpRed[2], y[k]);
+#pragma unroll
+    for (int k = 0; k < N; ++k) r[k] = __fma_rn(t[k] - magic, kExpRed[3], r[k]);
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = __fma_rn(kExpPoly[0], r[k], kExpPoly[1]);
+#pragma unroll
+    for (int i = 2; i < 10; ++i) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) v[k] = __fma_rn(v[k], r[k], kExpPoly[i]);
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = __fma_rn(v[k], r[k], 1.0);
+#pragma unroll
+    for (int k = 0; k < N; ++k) out[k] = __hiloint2double(__double2hiint(v[k]) + (__double2loint(t[k]) << 20), __double2loint(v[k]));
 }
 
 // t**n / ln t with libm semantics through the raw cosine.  Deliberately NOT inlined and with
@@ -158,17 +186,15 @@ __device__ __forceinline__ void accumulate_normal(double j0, double j1, double j
     acc[ESQ] = __fma_rn(e, e, acc[ESQ]);
 }
 
-// Prediction hx for one sample given t**n.
-__device__ __forceinline__ double model_eval(const PassParams& q, double c, double pw) {
-    return __fma_rn(q.kd, c, q.cks * pw);
-}
+// Does this sample need libm semantics?  (also catches the NaN flag, t == 0, t == inf)
+template <class Q>
+__device__ __forceinline__ bool needs_care(const Q& q, double L) { return !(fabs(L) <= q.l_lim); }
 
 // careful path of one Jacobian sample: literal levmar differences of full model values
 template <int JAC>
-__device__ __forceinline__ void accumulate_jac_careful(const PassParams& q, double c, double traw, double x, double* acc) {
+__device__ __forceinline__ void jac_terms_careful(const PassParams& q, double c, double traw, double x, double* out4) {
     const double pw = pow_careful(traw, q.n);
     const double hx = q.kd * c + q.cks * pw;
-    const double e = x - hx;
     double j0, j1, j2;
     if (JAC == kJacForward) {  // jac[i][j] = (f(p + d_j e_j) - f(p)) * (1/d_j), misc_core.c:160-170
         const double pw_hi = pow_careful(traw, q.n_hi);
@@ -186,43 +212,93 @@ __device__ __forceinline__ void accumulate_jac_careful(const PassParams& q, doub
         j1 = q.coef * pw;
         j2 = q.ks * pw * (q.dcoef + q.coef * log_careful(traw));
     }
-    accumulate_normal(j0, j1, j2, e, acc);
+    out4[0] = x - hx; out4[1] = j0; out4[2] = j1; out4[3] = j2;
 }
 
-// One sample of a fused residual + Jacobian + normal-equation pass.
+// N samples of a fused residual + Jacobian + normal-equation pass.  The fast path of all N samples
+// is straight-line code (2N..3N independent exp chains the scheduler can interleave); samples that
+// need libm semantics are redone afterwards under one rarely-taken branch.
+// `q` feeds the fast path (callers pass a register copy: only the handful of fields used here stay
+// live), `cold` the careful path (callers pass the original in shared / parameter memory).
+template <int JAC, int N>
+__device__ __forceinline__ void accumulate_jac_n(const PassParams& q, const PassParams& cold, const double* c,
+                                                 const double* L, const double* x, const double* __restrict__ traw,
+                                                 const long* idx, double* acc) {
+    double e[N], j0[N], j1[N], j2[N];
+    bool slow = false;
+    const double g1c = (q.model == 1) ? q.g1 : q.g1 * q.coef;
+    constexpr int NE = (JAC == kJacForward) ? 2 : (JAC == kJacCentral) ? 3 : 1;  // exponentials per sample
+    double y[NE * N], pw[NE * N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        slow |= needs_care(q, L[k]);
+        y[k] = q.n * L[k];
+        if (NE >= 2) y[N + k] = q.n_hi * L[k];
+        if (NE >= 3) y[2 * N + k] = q.n_lo * L[k];
+    }
+    exp_core_n<NE * N>(y, pw);
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        e[k] = x[k] - __fma_rn(q.kd, c[k], q.cks * pw[k]);
+        j0[k] = q.g0 * c[k];
+        j1[k] = g1c * pw[k];
+        if (JAC == kJacForward) j2[k] = __fma_rn(q.a_hi, pw[N + k], -(q.a_lo * pw[k]));
+        else if (JAC == kJacCentral) j2[k] = __fma_rn(q.a_hi, pw[N + k], -(q.a_lo * pw[2 * N + k]));
+        else j2[k] = (q.ks * pw[k]) * __fma_rn(q.coef, L[k], q.dcoef);
+    }
+    if (slow) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            if (needs_care(q, L[k])) {
+                double o[4];
+                jac_terms_careful<JAC>(cold, c[k], traw[idx[k]], x[k], o);
+                e[k] = o[0]; j0[k] = o[1]; j1[k] = o[2]; j2[k] = o[3];
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) accumulate_normal(j0[k], j1[k], j2[k], e[k], acc);
+}
+
+// One sample (tails, the batched kernels' per-lane loops)
 template <int JAC>
 __device__ __forceinline__ void accumulate_jac(const PassParams& q, double c, double L, double x,
                                                const double* __restrict__ traw, long i, double* acc) {
-    if (!(fabs(L) <= q.l_lim)) {  // also catches NaN flags, t == 0, t == inf
-        accumulate_jac_careful<JAC>(q, c, traw[i], x, acc);
-        return;
-    }
-    const double pw = exp_core(q.n * L);
-    const double e = x - __fma_rn(q.kd, c, q.cks * pw);
-    const double j0 = q.g0 * c;
-    const double j1 = (q.model == 1) ? q.g1 * pw : (q.g1 * q.coef) * pw;
-    double j2;
-    if (JAC == kJacForward) {
-        j2 = __fma_rn(q.a_hi, exp_core(q.n_hi * L), -(q.a_lo * pw));
-    } else if (JAC == kJacCentral) {
-        j2 = __fma_rn(q.a_hi, exp_core(q.n_hi * L), -(q.a_lo * exp_core(q.n_lo * L)));
-    } else {
-        j2 = (q.ks * pw) * __fma_rn(q.coef, L, q.dcoef);
-    }
-    accumulate_normal(j0, j1, j2, e, acc);
+    accumulate_jac_n<JAC, 1>(q, q, &c, &L, &x, traw, &i, acc);
 }
 
-// residual e = x - f(p) of one sample (same arithmetic in every pass).  Q is PassParams or CostPoint.
+// residual e = x - f(p) (same arithmetic in every pass).  Q is PassParams or CostPoint.
 template <class Q>
 __device__ __forceinline__ double residual_careful(const Q& q, double c, double traw, double x) {
     return x - (q.kd * c + q.cks * pow_careful(traw, q.n));
 }
 
+template <int N, class Q>
+__device__ __forceinline__ void residuals_n(const Q& q, const double* c, const double* L, const double* x,
+                                            const double* __restrict__ traw, const long* idx, double* e) {
+    bool slow = false;
+    double y[N], pw[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        slow |= needs_care(q, L[k]);
+        y[k] = q.n * L[k];
+    }
+    exp_core_n<N>(y, pw);
+#pragma unroll
+    for (int k = 0; k < N; ++k) e[k] = x[k] - __fma_rn(q.kd, c[k], q.cks * pw[k]);
+    if (slow) {
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+            if (needs_care(q, L[k])) e[k] = residual_careful(q, c[k], traw[idx[k]], x[k]);
+    }
+}
+
 template <class Q>
 __device__ __forceinline__ double residual_of(const Q& q, double c, double L, double x,
                                               const double* __restrict__ traw, long i) {
-    if (!(fabs(L) <= q.l_lim)) return residual_careful(q, c, traw[i], x);
-    return x - __fma_rn(q.kd, c, q.cks * exp_core(q.n * L));
+    double e;
+    residuals_n<1>(q, &c, &L, &x, traw, &i, &e);
+    return e;
 }
 
 // One sample of a trial-point pass: only ||x - f(p)||^2.
@@ -231,6 +307,41 @@ __device__ __forceinline__ void accumulate_cost(const Q& q, double c, double L, 
                                                 const double* __restrict__ traw, long i, double* esq) {
     const double e = residual_of(q, c, L, x, traw, i);
     *esq = __fma_rn(e, e, *esq);
+}
+
+// A PAIR of samples (the 16-byte unit every streaming loop loads)
+template <class Q>
+__device__ __forceinline__ void accumulate_cost_pair(const Q& q, double2 c, double2 L, double2 x,
+                                                     const double* __restrict__ traw, long i0, double* esq) {
+    const double cc[2] = {c.x, c.y}, ll[2] = {L.x, L.y}, xx[2] = {x.x, x.y};
+    const long idx[2] = {i0, i0 + 1};
+    double e[2];
+    residuals_n<2>(q, cc, ll, xx, traw, idx, e);
+    *esq = __fma_rn(e[0], e[0], *esq);
+    *esq = __fma_rn(e[1], e[1], *esq);
+}
+
+// two pairs at once: four independent exp chains
+template <class Q>
+__device__ __forceinline__ void accumulate_cost_2pairs(const Q& q, double2 c, double2 L, double2 x, long i0, double2 d,
+                                                       double2 M, double2 y, long j0, const double* __restrict__ traw,
+                                                       double* esq_a, double* esq_b) {
+    const double cc[4] = {c.x, c.y, d.x, d.y}, ll[4] = {L.x, L.y, M.x, M.y}, xx[4] = {x.x, x.y, y.x, y.y};
+    const long idx[4] = {i0, i0 + 1, j0, j0 + 1};
+    double e[4];
+    residuals_n<4>(q, cc, ll, xx, traw, idx, e);
+    *esq_a = __fma_rn(e[0], e[0], *esq_a);
+    *esq_a = __fma_rn(e[1], e[1], *esq_a);
+    *esq_b = __fma_rn(e[2], e[2], *esq_b);
+    *esq_b = __fma_rn(e[3], e[3], *esq_b);
+}
+
+template <int JAC>
+__device__ __forceinline__ void accumulate_jac_pair(const PassParams& q, const PassParams& cold, double2 c, double2 L,
+                                                    double2 x, const double* __restrict__ traw, long i0, double* acc) {
+    const double cc[2] = {c.x, c.y}, ll[2] = {L.x, L.y}, xx[2] = {x.x, x.y};
+    const long idx[2] = {i0, i0 + 1};
+    accumulate_jac_n<JAC, 2>(q, cold, cc, ll, xx, traw, idx, acc);
 }
 #endif  // __CUDACC__
 

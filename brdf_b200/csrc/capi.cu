@@ -97,7 +97,7 @@ extern "C" unsigned long long brdfgpu_launch_count(brdfgpu_ctx* ctx) {
 extern "C" int brdfgpu_fit_stats(brdfgpu_ctx* ctx, unsigned long long* out, int count) {
     ctx = ctx_or_default(ctx);
     if (!ctx || !out) return BRDFGPU_LM_ERROR;
-    for (int i = 0; i < count && i < 8; ++i) out[i] = ctx->fit_stats[i];
+    for (int i = 0; i < count && i < 12; ++i) out[i] = ctx->fit_stats[i];
     return 0;
 }
 extern "C" void* brdfgpu_stream(brdfgpu_ctx* ctx) {
@@ -464,10 +464,19 @@ struct CallbackEval {
 struct CallbackEvalMany : CallbackEval {
     static constexpr int kCostBatch = 8;
     int max_batch = 0;
-    void cost_many(const double* pts, int cnt, double* esq, bool* bad) {
+    double pts[kCostBatch * kMaxM], es[kCostBatch];
+    bool bads[kCostBatch];
+    double* batch_points() { return pts; }
+    void cost_many(int cnt, const double* dscl, int mm) {
         if (cnt > max_batch) max_batch = cnt;
-        for (int c = 0; c < cnt; ++c) esq[c] = cost(pts + c * m, bad[c]);
+        for (int c = 0; c < cnt; ++c) {
+            double q[kMaxM];
+            for (int i = mm; i-- > 0;) q[i] = dscl ? pts[c * mm + i] * dscl[i] : pts[c * mm + i];
+            es[c] = cost(q, bads[c]);
+        }
     }
+    double batch_cost(int c) const { return es[c]; }
+    bool batch_bad(int c) const { return bads[c]; }
 };
 }  // namespace
 

@@ -56,7 +56,7 @@ struct brdfgpu_ctx {
     // what the last global fit did: sweeps with a Jacobian, cost-only sweeps, trial points evaluated
     // (>= the levmar-counted ones: the projected-gradient walk is evaluated eight points per sweep),
     // samples resident in shared memory, CTAs
-    unsigned long long fit_stats[8] = {0};
+    unsigned long long fit_stats[12] = {0};
 
     // multi-GPU
     void* nccl_comm = nullptr;
@@ -126,6 +126,7 @@ struct GlobalFitOut {
     int aborted;          // an exchange partner never delivered: the fit was abandoned
     unsigned jac_passes, cost_passes, cost_points;
     long long cyc_sweep, cyc_exchange, cyc_total;  // SM cycles of CTA 0 / thread 0
+    long long cyc_x[4];
     double p[kMaxM];
     double info[10];
     double JtJ[kMaxM * kMaxM];

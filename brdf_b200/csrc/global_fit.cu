@@ -55,8 +55,8 @@ __device__ __forceinline__ Pair load_pair(const double2* __restrict__ c2, const 
 }
 
 template <int JAC>
-__device__ __forceinline__ void stream_jac(const SampleView& v, const PassParams& q, long first_pair, long tid,
-                                           long nthreads, double* acc) {
+__device__ __forceinline__ void stream_jac(const SampleView& v, const PassParams& q, const PassParams& cold,
+                                           long first_pair, long tid, long nthreads, double* acc) {
     const double2* __restrict__ c2 = reinterpret_cast<const double2*>(v.c);
     const double2* __restrict__ l2 = reinterpret_cast<const double2*>(v.L);
     const double2* __restrict__ x2 = reinterpret_cast<const double2*>(v.x);
@@ -68,14 +68,13 @@ __device__ __forceinline__ void stream_jac(const SampleView& v, const PassParams
         const long nxt = i + nthreads;
         Pair ahead = cur;
         if (nxt < npair) ahead = load_pair(c2, l2, x2, nxt);
-        accumulate_jac<JAC>(q, cur.c.x, cur.l.x, cur.x.x, v.traw, 2 * i, acc);
-        accumulate_jac<JAC>(q, cur.c.y, cur.l.y, cur.x.y, v.traw, 2 * i + 1, acc);
+        accumulate_jac_pair<JAC>(q, cold, cur.c, cur.l, cur.x, v.traw, 2 * i, acc);
         cur = ahead;
         i = nxt;
     }
     if ((v.n & 1) && tid == 0) {
         const long j = v.n - 1;
-        accumulate_jac<JAC>(q, v.c[j], v.L[j], v.x[j], v.traw, j, acc);
+        accumulate_jac<JAC>(cold, v.c[j], v.L[j], v.x[j], v.traw, j, acc);
     }
 }
 
@@ -93,8 +92,7 @@ __device__ __forceinline__ void stream_cost(const SampleView& v, const Q& q, lon
         const long nxt = i + nthreads;
         Pair ahead = cur;
         if (nxt < npair) ahead = load_pair(c2, l2, x2, nxt);
-        accumulate_cost(q, cur.c.x, cur.l.x, cur.x.x, v.traw, 2 * i, acc2);
-        accumulate_cost(q, cur.c.y, cur.l.y, cur.x.y, v.traw, 2 * i + 1, acc2);
+        accumulate_cost_pair(q, cur.c, cur.l, cur.x, v.traw, 2 * i, acc2);
         cur = ahead;
         i = nxt;
     }
@@ -179,13 +177,13 @@ __device__ __forceinline__ void last_block_finish(double* partials, unsigned* ti
 }
 
 template <int JAC>
-__global__ void __launch_bounds__(kPassThreads, 3) k_normal_eq(SampleView v, PassParams q, double* partials,
+__global__ void __launch_bounds__(kPassThreads, 2) k_normal_eq(SampleView v, PassParams q, double* partials,
                                                              unsigned* ticket, Publish pub) {
     __shared__ double red[(kPassThreads / 32) * NACC];
     double acc[NACC];
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
-    stream_jac<JAC>(v, q, 0, (long)blockIdx.x * blockDim.x + threadIdx.x, (long)gridDim.x * blockDim.x, acc);
+    stream_jac<JAC>(v, q, q, 0, (long)blockIdx.x * blockDim.x + threadIdx.x, (long)gridDim.x * blockDim.x, acc);
     block_reduce_to<NACC>(acc, red, partials + (long)blockIdx.x * NACC);
     last_block_finish<NACC>(partials, ticket, red, pub);
 }
@@ -279,7 +277,7 @@ static int to_jac_kind(int jac_mode, double delta_signed) {
 static int launch_normal_eq(brdfgpu_ctx* ctx, const brdfgpu_samples* s, const double* p, double delta, int jkind,
                             bool publish) {
     const PassParams q = make_pass_params(p, s->model, delta, jkind);
-    const int blocks = pass_blocks(ctx, s->n, 3);
+    const int blocks = pass_blocks(ctx, s->n, 2);
     Publish pub{ctx->d_result, nullptr, nullptr, 0};
     if (publish) pub = Publish{ctx->d_result, ctx->h_result_dev, ctx->h_seq_dev, ++ctx->seq};
     const SampleView v = view_of(s);
@@ -488,22 +486,33 @@ constexpr int kMaxPersistBlocks = 160;  // >= SM count (148 on B200)
 constexpr int kGridCostBatch = 8;       // trial points per cost_many() sweep (<= NACC)
 constexpr long long kSpinCycles = 6000000000LL;  // ~3 s at 2 GHz, then the fit is abandoned
 
+// A cell is two 64-bit words {value.lo | tag << 32, value.hi | tag << 32}; each word is one scalar
+// access, so a reader that finds the current tag in both has the whole double -- the data is its own
+// flag (no fence, no counter).  SYS = cells written by a peer GPU over NVLink, else GPU scope.
+template <bool SYS>
 __device__ __forceinline__ void store_cell(uint4* dst, double v, unsigned tag) {
-    const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
-    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(lo), "r"(tag), "r"(hi), "r"(tag)
-                 : "memory");
+    const unsigned long long t = (unsigned long long)tag << 32;
+    const unsigned long long w0 = t | (unsigned)__double2loint(v), w1 = t | (unsigned)__double2hiint(v);
+    if (SYS) asm volatile("st.relaxed.sys.global.v2.b64 [%0], {%1, %2};" ::"l"(dst), "l"(w0), "l"(w1) : "memory");
+    else asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(dst), "l"(w0), "l"(w1) : "memory");
 }
-__device__ __forceinline__ uint4 load_cell(const uint4* src) {
-    uint4 c;
-    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w) : "l"(src)
-                 : "memory");
+struct Cell {
+    unsigned long long w0, w1;
+    __device__ __forceinline__ bool has(unsigned tag) const { return (unsigned)(w0 >> 32) == tag && (unsigned)(w1 >> 32) == tag; }
+    __device__ __forceinline__ double value() const { return __hiloint2double((int)(unsigned)w1, (int)(unsigned)w0); }
+};
+template <bool SYS>
+__device__ __forceinline__ Cell load_cell(const uint4* src) {
+    Cell c;
+    if (SYS) asm volatile("ld.relaxed.sys.global.v2.b64 {%0, %1}, [%2];" : "=l"(c.w0), "=l"(c.w1) : "l"(src) : "memory");
+    else asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(c.w0), "=l"(c.w1) : "l"(src) : "memory");
     return c;
 }
-// Spin until both halves of the cell carry `tag`.  Every 8-byte half {word, tag} is written
-// atomically, so matching tags mean the whole double is there (no fence, no separate flag).
+// Spin until the cell carries `tag`.
+template <bool SYS>
 __device__ __forceinline__ double wait_cell(const uint4* src, unsigned tag, int* abort_flag) {
-    uint4 c = load_cell(src);
-    if (c.y != tag || c.w != tag) {
+    Cell c = load_cell<SYS>(src);
+    if (!c.has(tag)) {
         const long long t0 = clock64();
         unsigned spins = 0;
         do {
@@ -511,17 +520,18 @@ __device__ __forceinline__ double wait_cell(const uint4* src, unsigned tag, int*
                 *abort_flag = 1;  // somebody (a peer GPU) never delivered: everybody gives up
                 return __longlong_as_double(0x7ff8000000000000LL);  // NaN: the control loop stops with reason 7
             }
-            c = load_cell(src);
-        } while (c.y != tag || c.w != tag);
+            c = load_cell<SYS>(src);
+        } while (!c.has(tag));
     }
-    return __hiloint2double((int)c.z, (int)c.x);
+    return c.value();
 }
 __device__ __forceinline__ unsigned next_tag(unsigned e) { return e + 1u ? e + 1u : 1u; }  // never 0: buffers start zeroed
 
-struct FitStats {
-    unsigned jac_passes, cost_passes, cost_points, pad;
-    long long cyc_sweep, cyc_exchange;  // SM cycles spent streaming samples / in the grid-wide exchange
-};
+__device__ __forceinline__ double2 lds_pair(unsigned base, int i) {
+    double2 v;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(base + 16u * (unsigned)i));
+    return v;
+}
 
 // What the control warp asks the CTA to do next (shared memory).
 enum SweepKind { kQuit = 0, kSweepJacForward, kSweepJacCentral, kSweepJacAnalytic, kSweepCost, kSweepMany, kSweepBad };
@@ -531,299 +541,345 @@ struct SweepRequest {
     CostPoint pts[kGridCostBatch];
 };
 
-// Per-thread view of the persistent fit.  Warp 0 of every CTA runs the levmar control code
-// (lm_engine.cuh) -- its evaluator calls post a SweepRequest and join the sweep; warps 1..15 only
-// serve sweeps.  (All 512 threads running the control code redundantly cost more than the sweeps:
-// its ~1.5 KB of per-thread stack then overflows L1 next to 180 KB of resident samples.)
-struct GridEval {
-    static constexpr int kCostBatch = kGridCostBatch;
+// Everything a sweep needs, written once at kernel start.  Shared memory on purpose: the sweeps are
+// separate (noinline) functions and local memory -- where a context object passed by pointer would
+// live -- costs ~350 cycles per dependent access on B200 (profiles/micro/lat.cu); LDS costs ~30.
+struct FitContext {
     SampleView v;
-    int model, jkind;
-    double delta;
-    // this CTA's resident slice (shared memory), in sample PAIRS
-    const double2 *sc, *sl, *sx;
-    int res_pairs;      // pairs held by this CTA
-    long res_first;     // global index of its first pair
-    long stream_first;  // pairs >= stream_first are streamed from global memory by the whole grid
-    // grid-wide exchange
-    uint4* cells;       // [2 parities][gridDim.x][NACC]
-    unsigned epoch;
-    double *red, *res, *stage;  // shared: [(threads/32)*NACC], [NACC], [kMaxPersistBlocks*NACC]
-    SweepRequest* req;          // shared
-    // cross-GPU exchange (nranks == 1: none)
-    PeerView peer;
-    double* pstage;             // shared [kMaxRanks*NACC]
-    int* abort_flag;            // global
-    FitStats stats;
-    long long t_mark;  // clock at the start of the current sweep
+    int model;
+    unsigned sc, sl, sx;  // resident slice (shared-window addresses), in sample PAIRS
+    int res_pairs;        // pairs held by this CTA
+    long res_first;       // global index of its first pair
+    long stream_first;    // pairs >= stream_first are streamed from global memory by the whole grid
+    uint4* cells;         // [2 parities][gridDim.x][NACC]
+    PeerView peer;        // nranks == 1: no cross-GPU step
+    int* abort_flag;      // global
+};
 
-    // ---- the sums of all CTAs (and all ranks) in res[0..NV), identical bits everywhere ----
-    template <int NV>
-    __device__ __forceinline__ void all_reduce(const double* acc) {
-        const long long t_in = clock64();
-        stats.cyc_sweep += t_in - t_mark;
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+__shared__ FitContext s_ctx;
+__shared__ SweepRequest s_req;
+__shared__ unsigned s_epoch, s_peer_epoch;  // tags of the last grid / peer exchange (uniform in the CTA)
+__shared__ double s_red[(kPersistThreads / 32) * NACC];
+__shared__ double s_res[NACC];
+__shared__ double s_stage[kMaxPersistBlocks * NACC];
+__shared__ double s_pstage[kMaxRanks * NACC];
+__shared__ double s_cand[kGridCostBatch * 3];  // candidate points of the projected-gradient walk
+__shared__ double s_cand_cost[kGridCostBatch];
+__shared__ int s_cand_bad[kGridCostBatch];
+__shared__ long long s_cyc[6];  // thread 0: cycles in sweeps, exchanges, and the 4 exchange phases
+
+// Cross-GPU step, fused into the same kernel: CTA 0 of every rank stores its rank's sums as flagged
+// cells into slot [parity][rank] of EVERY rank's exchange buffer (peer stores over NVLink /
+// NVSwitch); every CTA polls its own rank's buffer until all slots carry the tag and adds them in
+// rank order -- identical bits on all ranks, so all ranks take identical LM decisions.  Two
+// parities: a rank can be at most one exchange ahead of any CTA of any peer.
+template <int NV>
+__device__ __forceinline__ void peer_exchange() {
+    const unsigned tag = next_tag(s_peer_epoch);
+    const int par = (int)(tag & 1u);
+    const int nranks = s_ctx.peer.nranks;
+    const int r = threadIdx.x / NV, k = threadIdx.x - r * NV;
+    if (threadIdx.x < NV * nranks) {
+        if (blockIdx.x == 0)
+            store_cell<true>(s_ctx.peer.remote[r] + ((long)(par * kMaxRanks + s_ctx.peer.rank) * kPeerCellsPerRank + k), s_res[k], tag);
+        s_pstage[r * NV + k] =
+            wait_cell<true>(s_ctx.peer.local + ((long)(par * kMaxRanks + r) * kPeerCellsPerRank + k), tag, s_ctx.abort_flag);
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double sum = 0.0;
+        for (int q = 0; q < nranks; ++q) sum += s_pstage[q * NV + threadIdx.x];
+        s_res[threadIdx.x] = sum;
+    }
+    if (threadIdx.x == 0) s_peer_epoch = tag;
+    __syncthreads();
+}
+
+// The sums of all CTAs (and all ranks) in s_res[0..NV), identical bits everywhere.  Latency is
+// everything here (one exchange per evaluation): every step is written so that the NV quantities
+// advance together instead of one after the other.
+template <int NV>
+__device__ __forceinline__ void all_reduce(const double* acc, long long t_sweep_start) {
+    const long long t_in = clock64();
+    constexpr int kWarps = kPersistThreads / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grid = gridDim.x;
+    // 1. warp butterflies, step-major
+    double s[NV];
 #pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            double s = acc[k];
+    for (int k = 0; k < NV; ++k) s[k] = acc[k];
 #pragma unroll
-            for (int off = 16; off; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
-            if (lane == 0) red[warp * NV + k] = s;
-        }
-        __syncthreads();
-        epoch = next_tag(epoch);
-        const unsigned tag = epoch;
-        uint4* base = cells + (long)(tag & 1u) * gridDim.x * NACC;
-        if (threadIdx.x < NV) {
-            double s = 0.0;
-            for (int w = 0; w < nwarps; ++w) s += red[w * NV + threadIdx.x];
-            store_cell(base + (long)blockIdx.x * NACC + threadIdx.x, s, tag);
-        }
-        // every thread collects up to 4 cells: all loads go out together, late ones are re-polled
-        constexpr int kPerThread = (kMaxPersistBlocks * NACC + kPersistThreads - 1) / kPersistThreads;
-        const int total = gridDim.x * NV;
-        uint4 c[kPerThread];
-        const uint4* src[kPerThread];
+    for (int off = 16; off; off >>= 1) {
 #pragma unroll
-        for (int j = 0; j < kPerThread; ++j) {
-            const int idx = threadIdx.x + j * kPersistThreads;
+        for (int k = 0; k < NV; ++k) s[k] += __shfl_down_sync(0xffffffffu, s[k], off);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) s_red[warp * NV + k] = s[k];
+    }
+    __syncthreads();
+    const long long t_a = clock64();
+    // 2. across the 16 warps: 16 lanes per quantity, 4 butterfly steps; publish
+    const unsigned tag = next_tag(s_epoch);
+    uint4* base = s_ctx.cells + (long)(tag & 1u) * grid * NACC;
+    if (threadIdx.x < ((NV * kWarps + 31) & ~31)) {
+        const int k = threadIdx.x / kWarps, w = threadIdx.x % kWarps;
+        double t = (k < NV) ? s_red[w * NV + k] : 0.0;
+#pragma unroll
+        for (int off = kWarps / 2; off; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off, kWarps);
+        if (k < NV && w == 0) store_cell<false>(base + (long)blockIdx.x * NACC + k, t, tag);
+    }
+    const long long t_b = clock64();
+    // 3. every thread collects up to 4 cells: all loads go out together, late ones are re-polled
+    constexpr int kPerThread = (kMaxPersistBlocks * NACC + kPersistThreads - 1) / kPersistThreads;
+    const int total = grid * NV;
+    Cell c[kPerThread];
+#pragma unroll
+    for (int j = 0; j < kPerThread; ++j) {
+        const int idx = threadIdx.x + j * kPersistThreads;
+        const int b = idx / NV, k = idx - b * NV;
+        if (idx < total) c[j] = load_cell<false>(base + (long)b * NACC + k);
+    }
+#pragma unroll
+    for (int j = 0; j < kPerThread; ++j) {
+        const int idx = threadIdx.x + j * kPersistThreads;
+        if (idx < total) {
             const int b = idx / NV, k = idx - b * NV;
-            src[j] = base + (long)b * NACC + k;
-            if (idx < total) c[j] = load_cell(src[j]);
+            s_stage[idx] = c[j].has(tag) ? c[j].value() : wait_cell<false>(base + (long)b * NACC + k, tag, s_ctx.abort_flag);
         }
-#pragma unroll
-        for (int j = 0; j < kPerThread; ++j) {
-            const int idx = threadIdx.x + j * kPersistThreads;
-            if (idx < total) {
-                double val;
-                if (c[j].y == tag && c[j].w == tag) val = __hiloint2double((int)c[j].z, (int)c[j].x);
-                else val = wait_cell(src[j], tag, abort_flag);
-                stage[idx] = val;
-            }
-        }
-        __syncthreads();
-        for (int k = warp; k < NV; k += nwarps) {  // fixed order: lanes stride the CTAs, butterfly
-            double s = 0.0;
-            for (int b = lane; b < gridDim.x; b += 32) s += stage[b * NV + k];
-#pragma unroll
-            for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-            if (lane == 0) res[k] = s;
-        }
-        __syncthreads();
-        if (peer.nranks > 1) peer_exchange<NV>();
-        stats.cyc_exchange += clock64() - t_in;
     }
-
-    // Cross-GPU step, fused into the same kernel: CTA 0 of every rank stores its rank's sums as
-    // flagged cells into slot [parity][rank] of EVERY rank's exchange buffer (peer stores over
-    // NVLink / NVSwitch); every CTA polls its own rank's buffer until all slots carry the tag and
-    // adds them in rank order -- identical bits on all ranks, so all ranks take identical LM
-    // decisions.  Two parities: a rank can be at most one exchange ahead of any CTA of any peer.
-    template <int NV>
-    __device__ __forceinline__ void peer_exchange() {
-        peer.epoch = next_tag(peer.epoch);
-        const unsigned tag = peer.epoch;
-        const int par = (int)(tag & 1u);
-        const int r = threadIdx.x / NV, k = threadIdx.x - r * NV;
-        if (threadIdx.x < NV * peer.nranks) {
-            if (blockIdx.x == 0)
-                store_cell(peer.remote[r] + ((long)(par * kMaxRanks + peer.rank) * kPeerCellsPerRank + k), res[k], tag);
-            pstage[r * NV + k] = wait_cell(peer.local + ((long)(par * kMaxRanks + r) * kPeerCellsPerRank + k), tag, abort_flag);
-        }
-        __syncthreads();
-        if (threadIdx.x < NV) {
-            double sum = 0.0;
-            for (int q = 0; q < peer.nranks; ++q) sum += pstage[q * NV + threadIdx.x];
-            res[threadIdx.x] = sum;
-        }
-        __syncthreads();
-    }
-
-    // ---- sweeps (all threads of the CTA) ----
-    template <int JAC>
-    __device__ __noinline__ void jac_sweep() {
-        t_mark = clock64();
-        const PassParams q = req->q;
-        double acc[NACC];
+    __syncthreads();
+    const long long t_c = clock64();
+    // 4. fixed order: one warp per quantity, lanes stride the CTAs, butterfly
+    for (int k = warp; k < NV; k += kWarps) {
+        double t = 0.0;
+        for (int b = lane; b < grid; b += 32) t += s_stage[b * NV + k];
 #pragma unroll
-        for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
-        for (int i = threadIdx.x; i < res_pairs; i += blockDim.x) {
-            const double2 c = sc[i], l = sl[i], x = sx[i];
-            const long g = 2 * (res_first + i);
-            accumulate_jac<JAC>(q, c.x, l.x, x.x, v.traw, g, acc);
-            accumulate_jac<JAC>(q, c.y, l.y, x.y, v.traw, g + 1, acc);
-        }
-        stream_jac<JAC>(v, q, stream_first, (long)blockIdx.x * blockDim.x + threadIdx.x, (long)gridDim.x * blockDim.x, acc);
-        all_reduce<NACC>(acc);
+        for (int off = 16; off; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+        if (lane == 0) s_res[k] = t;
     }
-
-    // sum of squared residuals at one point over this thread's share of the samples
-    __device__ __forceinline__ double resident_cost(const CostPoint& q) const {
-        double a0 = 0.0, a1 = 0.0;  // two pairs in flight: four independent exp chains per thread
-        int i = threadIdx.x;
-        for (; i + (int)blockDim.x < res_pairs; i += 2 * blockDim.x) {
-            const int i2 = i + blockDim.x;
-            const double2 c = sc[i], l = sl[i], x = sx[i];
-            const double2 d = sc[i2], m = sl[i2], y = sx[i2];
-            const long g = 2 * (res_first + i), h = 2 * (res_first + i2);
-            accumulate_cost(q, c.x, l.x, x.x, v.traw, g, &a0);
-            accumulate_cost(q, d.x, m.x, y.x, v.traw, h, &a1);
-            accumulate_cost(q, c.y, l.y, x.y, v.traw, g + 1, &a0);
-            accumulate_cost(q, d.y, m.y, y.y, v.traw, h + 1, &a1);
-        }
-        if (i < res_pairs) {
-            const double2 c = sc[i], l = sl[i], x = sx[i];
-            const long g = 2 * (res_first + i);
-            accumulate_cost(q, c.x, l.x, x.x, v.traw, g, &a0);
-            accumulate_cost(q, c.y, l.y, x.y, v.traw, g + 1, &a1);
-        }
-        return a0 + a1;
+    if (threadIdx.x == 0) s_epoch = tag;  // everybody read the old value before the barrier above
+    __syncthreads();
+    if (s_ctx.peer.nranks > 1) peer_exchange<NV>();
+    if (threadIdx.x == 0) {
+        const long long t_d = clock64();
+        s_cyc[0] += t_in - t_sweep_start; s_cyc[1] += t_d - t_in;
+        s_cyc[2] += t_a - t_in; s_cyc[3] += t_b - t_a; s_cyc[4] += t_c - t_b; s_cyc[5] += t_d - t_c;
     }
+}
 
-    __device__ __noinline__ void cost_sweep() {
-        t_mark = clock64();
-        const CostPoint q = req->pts[0];
-        double acc[1];
-        acc[0] = resident_cost(q);
-        stream_cost(v, q, stream_first, (long)blockIdx.x * blockDim.x + threadIdx.x, (long)gridDim.x * blockDim.x, acc);
-        all_reduce<1>(acc);
-    }
-
-    // number of non-finite residuals at point req->pts[req->cnt] (rare second sweep)
-    __device__ __noinline__ void bad_sweep() {
-        t_mark = clock64();
-        const CostPoint q = req->pts[req->cnt];
-        double cnt[1] = {0.0};
-        for (int i = threadIdx.x; i < res_pairs; i += blockDim.x) {
-            const double2 c = sc[i], l = sl[i], x = sx[i];
-            const long g = 2 * (res_first + i);
-            cnt[0] += lm_finite(residual_of(q, c.x, l.x, x.x, v.traw, g)) ? 0.0 : 1.0;
-            cnt[0] += lm_finite(residual_of(q, c.y, l.y, x.y, v.traw, g + 1)) ? 0.0 : 1.0;
-        }
-        const long nth = (long)gridDim.x * blockDim.x;
-        for (long i = 2 * stream_first + (long)blockIdx.x * blockDim.x + threadIdx.x; i < v.n; i += nth)
-            cnt[0] += lm_finite(residual_of(q, v.c[i], v.L[i], v.x[i], v.traw, i)) ? 0.0 : 1.0;
-        all_reduce<1>(cnt);
-    }
-
-    // up to kGridCostBatch trial points in ONE sweep + ONE exchange
-    __device__ __noinline__ void many_sweep() {
-        t_mark = clock64();
-        const int cnt = req->cnt;
-        double acc[kGridCostBatch];
+// ---- sweeps (all threads of the CTA) ----
+template <int JAC>
+__device__ __noinline__ void jac_sweep() {
+    const long long t0 = clock64();
+    const PassParams q = s_req.q;
+    const unsigned sc = s_ctx.sc, sl = s_ctx.sl, sx = s_ctx.sx;
+    const int res_pairs = s_ctx.res_pairs;
+    const long res_first = s_ctx.res_first;
+    const double* traw = s_ctx.v.traw;
+    double acc[NACC];
 #pragma unroll
-        for (int k = 0; k < kGridCostBatch; ++k) acc[k] = 0.0;
-        // resident slice: candidate-outer, parameters in registers, samples re-read from shared memory
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+    for (int i = threadIdx.x; i < res_pairs; i += kPersistThreads) {
+        const double2 c = lds_pair(sc, i), l = lds_pair(sl, i), x = lds_pair(sx, i);
+        accumulate_jac_pair<JAC>(q, s_req.q, c, l, x, traw, 2 * (res_first + i), acc);
+    }
+    if (s_ctx.stream_first < (s_ctx.v.n >> 1) || (s_ctx.v.n & 1))
+        stream_jac<JAC>(s_ctx.v, q, s_req.q, s_ctx.stream_first, (long)blockIdx.x * kPersistThreads + threadIdx.x,
+                        (long)gridDim.x * kPersistThreads, acc);
+    all_reduce<NACC>(acc, t0);
+}
+
+// sum of squared residuals at one point over this thread's share of the resident samples
+__device__ __forceinline__ double resident_cost(const CostPoint& q, unsigned sc, unsigned sl, unsigned sx, int res_pairs,
+                                                long res_first, const double* traw) {
+    double a0 = 0.0, a1 = 0.0;  // two pairs in flight: four independent exp chains per thread
+    int i = threadIdx.x;
+    for (; i + kPersistThreads < res_pairs; i += 2 * kPersistThreads) {
+        const int i2 = i + kPersistThreads;
+        const double2 c = lds_pair(sc, i), l = lds_pair(sl, i), x = lds_pair(sx, i);
+        const double2 d = lds_pair(sc, i2), m = lds_pair(sl, i2), y = lds_pair(sx, i2);
+        accumulate_cost_2pairs(q, c, l, x, 2 * (res_first + i), d, m, y, 2 * (res_first + i2), traw, &a0, &a1);
+    }
+    if (i < res_pairs) {
+        const double2 c = lds_pair(sc, i), l = lds_pair(sl, i), x = lds_pair(sx, i);
+        accumulate_cost_pair(q, c, l, x, traw, 2 * (res_first + i), &a0);
+    }
+    return a0 + a1;
+}
+
+__device__ __noinline__ void cost_sweep() {
+    const long long t0 = clock64();
+    const CostPoint q = s_req.pts[0];
+    double acc[1];
+    acc[0] = resident_cost(q, s_ctx.sc, s_ctx.sl, s_ctx.sx, s_ctx.res_pairs, s_ctx.res_first, s_ctx.v.traw);
+    if (s_ctx.stream_first < (s_ctx.v.n >> 1) || (s_ctx.v.n & 1))
+        stream_cost(s_ctx.v, q, s_ctx.stream_first, (long)blockIdx.x * kPersistThreads + threadIdx.x,
+                    (long)gridDim.x * kPersistThreads, acc);
+    all_reduce<1>(acc, t0);
+}
+
+// number of non-finite residuals at point s_req.pts[s_req.cnt] (rare second sweep)
+__device__ __noinline__ void bad_sweep() {
+    const long long t0 = clock64();
+    const CostPoint q = s_req.pts[s_req.cnt];
+    const SampleView v = s_ctx.v;
+    double cnt[1] = {0.0};
+    for (int i = threadIdx.x; i < s_ctx.res_pairs; i += kPersistThreads) {
+        const double2 c = lds_pair(s_ctx.sc, i), l = lds_pair(s_ctx.sl, i), x = lds_pair(s_ctx.sx, i);
+        const long g = 2 * (s_ctx.res_first + i);
+        cnt[0] += lm_finite(residual_of(q, c.x, l.x, x.x, v.traw, g)) ? 0.0 : 1.0;
+        cnt[0] += lm_finite(residual_of(q, c.y, l.y, x.y, v.traw, g + 1)) ? 0.0 : 1.0;
+    }
+    const long nth = (long)gridDim.x * kPersistThreads;
+    for (long i = 2 * s_ctx.stream_first + (long)blockIdx.x * kPersistThreads + threadIdx.x; i < v.n; i += nth)
+        cnt[0] += lm_finite(residual_of(q, v.c[i], v.L[i], v.x[i], v.traw, i)) ? 0.0 : 1.0;
+    all_reduce<1>(cnt, t0);
+}
+
+// up to kGridCostBatch trial points in ONE sweep + ONE exchange
+__device__ __noinline__ void many_sweep() {
+    const long long t0 = clock64();
+    const int cnt = s_req.cnt;
+    const unsigned sc = s_ctx.sc, sl = s_ctx.sl, sx = s_ctx.sx;
+    const int res_pairs = s_ctx.res_pairs;
+    const long res_first = s_ctx.res_first;
+    const double* traw = s_ctx.v.traw;
+    double acc[kGridCostBatch];
 #pragma unroll
-        for (int k = 0; k < kGridCostBatch; ++k)
-            if (k < cnt) acc[k] = resident_cost(req->pts[k]);
-        // streamed remainder: sample-outer (one read of the sample for all candidates)
-        {
-            const double2* __restrict__ c2 = reinterpret_cast<const double2*>(v.c);
-            const double2* __restrict__ l2 = reinterpret_cast<const double2*>(v.L);
-            const double2* __restrict__ x2 = reinterpret_cast<const double2*>(v.x);
-            const long npair = v.n >> 1, nth = (long)gridDim.x * blockDim.x;
-            for (long i = stream_first + (long)blockIdx.x * blockDim.x + threadIdx.x; i < npair; i += nth) {
-                const Pair s = load_pair(c2, l2, x2, i);
+    for (int k = 0; k < kGridCostBatch; ++k) acc[k] = 0.0;
+    // resident slice: candidate-outer, parameters in registers, samples re-read from shared memory
 #pragma unroll
-                for (int k = 0; k < kGridCostBatch; ++k) {
-                    if (k < cnt) {
-                        const CostPoint q = req->pts[k];
-                        accumulate_cost(q, s.c.x, s.l.x, s.x.x, v.traw, 2 * i, &acc[k]);
-                        accumulate_cost(q, s.c.y, s.l.y, s.x.y, v.traw, 2 * i + 1, &acc[k]);
-                    }
+    for (int k = 0; k < kGridCostBatch; ++k)
+        if (k < cnt) acc[k] = resident_cost(s_req.pts[k], sc, sl, sx, res_pairs, res_first, traw);
+    // streamed remainder: sample-outer (one read of the sample for all candidates)
+    const SampleView v = s_ctx.v;
+    if (s_ctx.stream_first < (v.n >> 1) || (v.n & 1)) {
+        const double2* __restrict__ c2 = reinterpret_cast<const double2*>(v.c);
+        const double2* __restrict__ l2 = reinterpret_cast<const double2*>(v.L);
+        const double2* __restrict__ x2 = reinterpret_cast<const double2*>(v.x);
+        const long npair = v.n >> 1, nth = (long)gridDim.x * kPersistThreads;
+        for (long i = s_ctx.stream_first + (long)blockIdx.x * kPersistThreads + threadIdx.x; i < npair; i += nth) {
+            const Pair sp = load_pair(c2, l2, x2, i);
+#pragma unroll
+            for (int k = 0; k < kGridCostBatch; ++k) {
+                if (k < cnt) {
+                    const CostPoint q = s_req.pts[k];
+                    accumulate_cost_pair(q, sp.c, sp.l, sp.x, v.traw, 2 * i, &acc[k]);
                 }
             }
-            if ((v.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-                const long j = v.n - 1;
+        }
+        if ((v.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+            const long j = v.n - 1;
 #pragma unroll
-                for (int k = 0; k < kGridCostBatch; ++k)
-                    if (k < cnt) accumulate_cost(req->pts[k], v.c[j], v.L[j], v.x[j], v.traw, j, &acc[k]);
-            }
-        }
-        all_reduce<kGridCostBatch>(acc);
-    }
-
-    __device__ __forceinline__ void run_sweep(int kind) {
-        switch (kind) {
-            case kSweepJacForward: jac_sweep<kJacForward>(); break;
-            case kSweepJacCentral: jac_sweep<kJacCentral>(); break;
-            case kSweepJacAnalytic: jac_sweep<kJacAnalytic>(); break;
-            case kSweepCost: cost_sweep(); break;
-            case kSweepMany: many_sweep(); break;
-            default: bad_sweep(); break;
+            for (int k = 0; k < kGridCostBatch; ++k)
+                if (k < cnt) accumulate_cost(s_req.pts[k], v.c[j], v.L[j], v.x[j], v.traw, j, &acc[k]);
         }
     }
+    all_reduce<kGridCostBatch>(acc, t0);
+}
 
-    // warps 1..15: serve sweeps until the control warp quits
-    __device__ __forceinline__ void serve() {
-        for (;;) {
-            __syncthreads();  // the request is posted
-            const int kind = req->kind;
-            if (kind == kQuit) return;
-            run_sweep(kind);
-        }
+__device__ __forceinline__ void run_sweep(int kind) {
+    switch (kind) {
+        case kSweepJacForward: jac_sweep<kJacForward>(); break;
+        case kSweepJacCentral: jac_sweep<kJacCentral>(); break;
+        case kSweepJacAnalytic: jac_sweep<kJacAnalytic>(); break;
+        case kSweepCost: cost_sweep(); break;
+        case kSweepMany: many_sweep(); break;
+        default: bad_sweep(); break;
     }
+}
 
-    // ---- control warp only: the Evaluator of lm_engine.cuh ----
+// warps 1..15: serve sweeps until the control warp quits
+__device__ __forceinline__ void serve_sweeps() {
+    for (;;) {
+        __syncthreads();  // the request is posted
+        const int kind = s_req.kind;
+        if (kind == kQuit) return;
+        run_sweep(kind);
+    }
+}
+
+// The Evaluator of lm_engine.cuh as seen by the control warp (warp 0 of every CTA): each call posts
+// a SweepRequest, joins the sweep and reads the reduced sums.  All 512 threads running the control
+// code redundantly cost more than the sweeps themselves.
+struct GridEval {
+    static constexpr int kCostBatch = kGridCostBatch;
+    int model, jkind;
+    double delta;
+    unsigned jac_passes, cost_passes, cost_points;
+
     __device__ __forceinline__ void post(int kind) {
-        if (threadIdx.x == 0) req->kind = kind;
+        if (threadIdx.x == 0) s_req.kind = kind;
         __syncthreads();
         if (kind != kQuit) run_sweep(kind);
     }
 
     __device__ __forceinline__ void jac(const double* p, double* JtJ, double* Jte) {
-        if (threadIdx.x == 0) req->q = make_pass_params(p, model, delta, jkind);
+        const PassParams q = make_pass_params(p, model, delta, jkind);
+        if (threadIdx.x == 0) s_req.q = q;
         post(jkind == kJacForward ? kSweepJacForward : jkind == kJacCentral ? kSweepJacCentral : kSweepJacAnalytic);
-        ++stats.jac_passes;
-        JtJ[0] = res[A00]; JtJ[1] = res[A01]; JtJ[2] = res[A02];
-        JtJ[3] = res[A01]; JtJ[4] = res[A11]; JtJ[5] = res[A12];
-        JtJ[6] = res[A02]; JtJ[7] = res[A12]; JtJ[8] = res[A22];
-        Jte[0] = res[G0]; Jte[1] = res[G1]; Jte[2] = res[G2];
+        ++jac_passes;
+        JtJ[0] = s_res[A00]; JtJ[1] = s_res[A01]; JtJ[2] = s_res[A02];
+        JtJ[3] = s_res[A01]; JtJ[4] = s_res[A11]; JtJ[5] = s_res[A12];
+        JtJ[6] = s_res[A02]; JtJ[7] = s_res[A12]; JtJ[8] = s_res[A22];
+        Jte[0] = s_res[G0]; Jte[1] = s_res[G1]; Jte[2] = s_res[G2];
     }
 
     __device__ __forceinline__ double count_bad(int k) {
-        if (threadIdx.x == 0) req->cnt = k;
+        if (threadIdx.x == 0) s_req.cnt = k;
         post(kSweepBad);
-        ++stats.cost_passes;
-        return res[0];
+        ++cost_passes;
+        return s_res[0];
     }
 
     __device__ __forceinline__ double cost(const double* p, bool& bad) {
-        if (threadIdx.x == 0) req->pts[0] = make_cost_point(p, model);
+        const CostPoint q = make_cost_point(p, model);
+        if (threadIdx.x == 0) s_req.pts[0] = q;
         post(kSweepCost);
-        ++stats.cost_passes;
-        ++stats.cost_points;
-        const double esq = res[0];
+        ++cost_passes;
+        ++cost_points;
+        const double esq = s_res[0];
         bad = false;
         if (!lm_finite(esq)) bad = count_bad(0) != 0.0;  // uniform across the grid: same sums everywhere
         return esq;
     }
 
-    __device__ __forceinline__ void cost_many(const double* pts, int cnt, double* esq, bool* bad) {
-        if (threadIdx.x < cnt) req->pts[threadIdx.x] = make_cost_point(pts + 3 * threadIdx.x, model);
-        if (threadIdx.x == 0) req->cnt = cnt;
+    // projected-gradient candidates (lm_engine.cuh PgBatch): the engine writes the points into
+    // shared memory, lanes 0..cnt-1 turn them into CostPoints in parallel
+    __device__ __forceinline__ double* batch_points() { return s_cand; }
+    __device__ __forceinline__ void cost_many(int cnt, const double* dscl, int) {
+        __syncwarp();
+        if (threadIdx.x < cnt) {
+            double q[3];
+            for (int i = 0; i < 3; ++i) q[i] = dscl ? s_cand[3 * threadIdx.x + i] * dscl[i] : s_cand[3 * threadIdx.x + i];
+            s_req.pts[threadIdx.x] = make_cost_point(q, model);
+        }
+        if (threadIdx.x == 0) s_req.cnt = cnt;
         post(kSweepMany);
-        ++stats.cost_passes;
-        stats.cost_points += cnt;
-        for (int k = 0; k < cnt; ++k) esq[k] = res[k];
+        ++cost_passes;
+        cost_points += cnt;
+        if (threadIdx.x < cnt) {
+            s_cand_cost[threadIdx.x] = s_res[threadIdx.x];
+            s_cand_bad[threadIdx.x] = 0;
+        }
+        __syncwarp();
         for (int k = 0; k < cnt; ++k) {
-            bad[k] = false;
-            if (!lm_finite(esq[k])) bad[k] = count_bad(k) != 0.0;
+            if (!lm_finite(s_cand_cost[k])) {  // uniform: every lane reads the same value
+                const double nbad = count_bad(k);
+                if (threadIdx.x == 0) s_cand_bad[k] = nbad != 0.0;
+                __syncwarp();
+            }
         }
     }
+    __device__ __forceinline__ double batch_cost(int c) const { return s_cand_cost[c]; }
+    __device__ __forceinline__ bool batch_bad(int c) const { return s_cand_bad[c] != 0; }
 };
 
 __global__ void __launch_bounds__(kPersistThreads, 1) k_persistent_fit(SampleView v, int model, GlobalFitSpec spec,
                                                                         uint4* cells, long resident_pairs,
                                                                         PeerView peer, GlobalFitOut* out) {
     extern __shared__ double2 smem_dyn[];
-    __shared__ double red[(kPersistThreads / 32) * NACC];
-    __shared__ double res[NACC];
-    __shared__ double stage[kMaxPersistBlocks * NACC];
-    __shared__ double pstage[kMaxRanks * NACC];
-    __shared__ SweepRequest req;
-
     // this CTA's resident slice: pairs [first, last) of the first `resident_pairs` pairs, balanced
     const long first = resident_pairs * blockIdx.x / gridDim.x, last = resident_pairs * (blockIdx.x + 1) / gridDim.x;
     const int cap = (int)((resident_pairs + gridDim.x - 1) / gridDim.x);
@@ -833,27 +889,31 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_persistent_fit(SampleVie
         const double2* __restrict__ c2 = reinterpret_cast<const double2*>(v.c);
         const double2* __restrict__ l2 = reinterpret_cast<const double2*>(v.L);
         const double2* __restrict__ x2 = reinterpret_cast<const double2*>(v.x);
-        for (int i = threadIdx.x; i < mine; i += blockDim.x) {
+        for (int i = threadIdx.x; i < mine; i += kPersistThreads) {
             sc[i] = __ldg(c2 + first + i);
             sl[i] = __ldg(l2 + first + i);
             sx[i] = __ldg(x2 + first + i);
         }
     }
+    if (threadIdx.x == 0) {
+        s_ctx.v = v; s_ctx.model = model;
+        s_ctx.sc = (unsigned)__cvta_generic_to_shared(sc); s_ctx.sl = (unsigned)__cvta_generic_to_shared(sl);
+        s_ctx.sx = (unsigned)__cvta_generic_to_shared(sx);
+        s_ctx.res_pairs = mine; s_ctx.res_first = first; s_ctx.stream_first = resident_pairs;
+        s_ctx.cells = cells; s_ctx.peer = peer; s_ctx.abort_flag = &out->aborted;
+        s_epoch = 0u; s_peer_epoch = peer.epoch;
+        for (int i = 0; i < 6; ++i) s_cyc[i] = 0;
+    }
     __syncthreads();
 
-    GridEval ev;
-    ev.v = v; ev.model = model; ev.jkind = spec.jac_mode; ev.delta = spec.delta;
-    ev.sc = sc; ev.sl = sl; ev.sx = sx; ev.res_pairs = mine; ev.res_first = first; ev.stream_first = resident_pairs;
-    ev.cells = cells; ev.epoch = 0u; ev.red = red; ev.res = res; ev.stage = stage; ev.req = &req;
-    ev.peer = peer; ev.pstage = pstage; ev.abort_flag = &out->aborted;
-    ev.stats = FitStats{0u, 0u, 0u, 0u, 0, 0};
-    ev.t_mark = 0;
-
     if (threadIdx.x >= 32) {
-        ev.serve();
+        serve_sweeps();
         return;
     }
     const long long t_start = clock64();
+    GridEval ev;
+    ev.model = model; ev.jkind = spec.jac_mode; ev.delta = spec.delta;
+    ev.jac_passes = ev.cost_passes = ev.cost_points = 0u;
     double p[3], info[10], JtJ[9];
     for (int i = 0; i < 3; ++i) p[i] = spec.p[i];
     int ret;
@@ -865,13 +925,14 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_persistent_fit(SampleVie
     ev.post(kQuit);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         out->ret = ret;
-        out->peer_epoch = ev.peer.epoch;
-        out->jac_passes = ev.stats.jac_passes;
-        out->cost_passes = ev.stats.cost_passes;
-        out->cost_points = ev.stats.cost_points;
-        out->cyc_sweep = ev.stats.cyc_sweep;
-        out->cyc_exchange = ev.stats.cyc_exchange;
+        out->peer_epoch = s_peer_epoch;
+        out->jac_passes = ev.jac_passes;
+        out->cost_passes = ev.cost_passes;
+        out->cost_points = ev.cost_points;
+        out->cyc_sweep = s_cyc[0];
+        out->cyc_exchange = s_cyc[1];
         out->cyc_total = clock64() - t_start;
+        for (int i = 0; i < 4; ++i) out->cyc_x[i] = s_cyc[2 + i];
         for (int i = 0; i < 3; ++i) out->p[i] = p[i];
         for (int i = 0; i < 10; ++i) out->info[i] = info[i];
         for (int i = 0; i < 9; ++i) out->JtJ[i] = JtJ[i];
@@ -1030,6 +1091,7 @@ int global_fit(brdfgpu_ctx* ctx, const brdfgpu_samples* s, double* p, int m, con
         ctx->fit_stats[3] = (unsigned long long)plan.resident_pairs * 2; ctx->fit_stats[4] = (unsigned long long)plan.grid;
         ctx->fit_stats[5] = (unsigned long long)h->cyc_sweep; ctx->fit_stats[6] = (unsigned long long)h->cyc_exchange;
         ctx->fit_stats[7] = (unsigned long long)h->cyc_total;
+        for (int i = 0; i < 4; ++i) ctx->fit_stats[8 + i] = (unsigned long long)h->cyc_x[i];
         ret = h->ret;
         for (int i = 0; i < 3; ++i) p[i] = h->p[i];
         for (int i = 0; i < 10; ++i) fit_info[i] = h->info[i];

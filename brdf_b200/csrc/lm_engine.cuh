@@ -62,84 +62,110 @@ BG_HDI LmOptions lm_options(const double* opts, int itmax) {
     return o;
 }
 
+// Loops over the m parameters are written against the compile-time bound MM with an `i < m` guard
+// and unrolled, and nothing below indexes a local array with a run-time value: on the device every
+// local array then lives in registers.  (Local memory costs ~350 cycles per dependent access on
+// B200 -- profiles/micro/lat.cu -- and this code sits on the critical path of every evaluation.)
+#define LM_FOR(i) _Pragma("unroll") for (int i = 0; i < MM; ++i) if (i < m)
+#define LM_FOR_REV(i) _Pragma("unroll") for (int i = MM; i-- > 0;) if (i < m)
+#define LM_FOR2(i, lo, hi) _Pragma("unroll") for (int i = 0; i < MM; ++i) if (i >= (lo) && i < (hi))
+
 // ---------------------------------------------------------------------------------------------
 // m x m solve: Crout LU, implicit row scaling, partial pivoting (Axb_core.c:1196-1270).
 // Returns 0 when a row of A is all zero; a zero pivot is replaced by DBL_EPSILON.
 // ---------------------------------------------------------------------------------------------
 template <int MM>
-BG_HDI int lu_factor(double* a, int* perm, int m) {
+BG_HDI int lu_factor(double (&a)[MM * MM], int (&perm)[MM], int m) {
     double rowscale[MM];
     int piv = -1;
-    for (int i = 0; i < m; ++i) {
+    bool zero_row = false;
+    LM_FOR(i) {
         double big = 0.0;
-        for (int j = 0; j < m; ++j) {
-            const double t = lm_abs(a[i * m + j]);
+        LM_FOR(j) {
+            const double t = lm_abs(a[i * MM + j]);
             if (t > big) big = t;
         }
-        if (big == 0.0) return 0;
+        if (big == 0.0) zero_row = true;
         rowscale[i] = 1.0 / big;
     }
-    for (int j = 0; j < m; ++j) {
-        for (int i = 0; i < j; ++i) {
-            double s = a[i * m + j];
-            for (int k = 0; k < i; ++k) s -= a[i * m + k] * a[k * m + j];
-            a[i * m + j] = s;
+    if (zero_row) return 0;
+    LM_FOR(j) {
+        LM_FOR2(i, 0, j) {
+            double s = a[i * MM + j];
+            LM_FOR2(k, 0, i) s -= a[i * MM + k] * a[k * MM + j];
+            a[i * MM + j] = s;
         }
         double big = 0.0;
-        for (int i = j; i < m; ++i) {
-            double s = a[i * m + j];
-            for (int k = 0; k < j; ++k) s -= a[i * m + k] * a[k * m + j];
-            a[i * m + j] = s;
+        LM_FOR2(i, j, m) {
+            double s = a[i * MM + j];
+            LM_FOR2(k, 0, j) s -= a[i * MM + k] * a[k * MM + j];
+            a[i * MM + j] = s;
             const double t = rowscale[i] * lm_abs(s);
             if (t >= big) { big = t; piv = i; }
         }
-        if (j != piv) {
-            for (int k = 0; k < m; ++k) {
-                const double t = a[piv * m + k];
-                a[piv * m + k] = a[j * m + k];
-                a[j * m + k] = t;
+        // row interchange j <-> piv, written per candidate row so every index is static.  (piv < j
+        // only happens when NaNs froze the pivot search at an earlier column: kept as levmar does)
+        LM_FOR(r) {
+            if (r != j && piv == r) {
+                LM_FOR(k) {
+                    const double t = a[r * MM + k];
+                    a[r * MM + k] = a[j * MM + k];
+                    a[j * MM + k] = t;
+                }
+                rowscale[r] = rowscale[j];
             }
-            rowscale[piv] = rowscale[j];
         }
         perm[j] = piv;
-        if (a[j * m + j] == 0.0) a[j * m + j] = DBL_EPSILON;
+        if (a[j * MM + j] == 0.0) a[j * MM + j] = DBL_EPSILON;
         if (j != m - 1) {
-            const double t = 1.0 / a[j * m + j];
-            for (int i = j + 1; i < m; ++i) a[i * m + j] *= t;
+            const double t = 1.0 / a[j * MM + j];
+            LM_FOR2(i, j + 1, m) a[i * MM + j] *= t;
         }
     }
     return 1;
 }
 
 template <int MM>
-BG_HDI void lu_substitute(const double* a, const int* perm, double* x, int m) {
+BG_HDI void lu_substitute(const double (&a)[MM * MM], const int (&perm)[MM], double (&x)[MM], int m) {
     int first = 0;
-    for (int i = 0; i < m; ++i) {
-        const int j = perm[i];
-        double s = x[j];
-        x[j] = x[i];
+    LM_FOR(i) {
+        // s = x[perm[i]]; x[perm[i]] = x[i]
+        double s = x[i];
+        LM_FOR(r) {
+            if (r != i && perm[i] == r) {
+                s = x[r];
+                x[r] = x[i];
+            }
+        }
         if (first != 0) {
-            for (int k = first - 1; k < i; ++k) s -= a[i * m + k] * x[k];
+            LM_FOR2(k, 0, i) if (k >= first - 1) s -= a[i * MM + k] * x[k];
         } else if (s != 0.0) {
             first = i + 1;
         }
         x[i] = s;
     }
-    for (int i = m - 1; i >= 0; --i) {
+    LM_FOR_REV(i) {
         double s = x[i];
-        for (int j = i + 1; j < m; ++j) s -= a[i * m + j] * x[j];
-        x[i] = s / a[i * m + i];
+        LM_FOR2(j, i + 1, m) s -= a[i * MM + j] * x[j];
+        x[i] = s / a[i * MM + i];
     }
 }
 
+// A, B, x: m x m row-major / m (caller layout, stride m)
 template <int MM>
 BG_HDI int solve_lu(const double* A, const double* B, double* x, int m) {
-    double a[MM * MM];
+    double a[MM * MM], xx[MM];
     int perm[MM];
-    for (int i = 0; i < m * m; ++i) a[i] = A[i];
-    for (int i = 0; i < m; ++i) x[i] = B[i];
-    if (!lu_factor<MM>(a, perm, m)) return 0;
-    lu_substitute<MM>(a, perm, x, m);
+    LM_FOR(i) {
+        LM_FOR(j) a[i * MM + j] = A[i * m + j];
+        xx[i] = B[i];
+    }
+    if (!lu_factor<MM>(a, perm, m)) {
+        LM_FOR(i) x[i] = xx[i];  // levmar leaves B's copy in x on failure (never read by the callers)
+        return 0;
+    }
+    lu_substitute<MM>(a, perm, xx, m);
+    LM_FOR(i) x[i] = xx[i];
     return 1;
 }
 
@@ -148,13 +174,12 @@ template <int MM>
 BG_HDI int lm_covar(const double* JtJ, double* C, double sumsq, int m, long n) {
     double a[MM * MM], x[MM];
     int perm[MM];
-    for (int i = 0; i < m * m; ++i) a[i] = JtJ[i];
+    LM_FOR(i) LM_FOR(j) a[i * MM + j] = JtJ[i * m + j];
     if (!lu_factor<MM>(a, perm, m)) return 0;
     for (int l = 0; l < m; ++l) {
-        for (int i = 0; i < m; ++i) x[i] = 0.0;
-        x[l] = 1.0;
+        LM_FOR(i) x[i] = (i == l) ? 1.0 : 0.0;
         lu_substitute<MM>(a, perm, x, m);
-        for (int i = 0; i < m; ++i) C[i * m + l] = x[i];
+        LM_FOR(i) C[i * m + l] = x[i];
     }
     const double fact = sumsq / (double)(n - m);
     for (int i = 0; i < m * m; ++i) C[i] *= fact;
@@ -178,9 +203,10 @@ struct Box {
     const double* ub;  // may be nullptr
 };
 
+template <int MM = 8>
 BG_HDI void box_project(double* p, const Box& b, int m) {
     if (!b.lb && !b.ub) return;
-    for (int i = m; i-- > 0;) {
+    LM_FOR_REV(i) {
         if (b.lb && b.ub) p[i] = lm_median3(b.lb[i], p[i], b.ub[i]);
         else if (b.ub) { if (p[i] > b.ub[i]) p[i] = b.ub[i]; }
         else { if (p[i] < b.lb[i]) p[i] = b.lb[i]; }
@@ -202,11 +228,11 @@ BG_HDI void eval_jac_scaled(Eval& ev, const double* q, const double* dscl, int m
         return;
     }
     double ps[MM];
-    for (int i = m; i-- > 0;) ps[i] = q[i] * dscl[i];
+    LM_FOR_REV(i) ps[i] = q[i] * dscl[i];
     ev.jac(ps, JtJ, Jte);
-    for (int i = 0; i < m; ++i) {
+    LM_FOR(i) {
         Jte[i] *= dscl[i];
-        for (int j = 0; j < m; ++j) JtJ[i * m + j] *= dscl[i] * dscl[j];
+        LM_FOR(j) JtJ[i * m + j] *= dscl[i] * dscl[j];
     }
 }
 
@@ -214,36 +240,40 @@ template <int MM, class Eval>
 BG_HDI double eval_cost_scaled(Eval& ev, const double* q, const double* dscl, int m, bool& bad) {
     if (!dscl) return ev.cost(q, bad);
     double ps[MM];
-    for (int i = m; i-- > 0;) ps[i] = q[i] * dscl[i];
+    LM_FOR_REV(i) ps[i] = q[i] * dscl[i];
     return ev.cost(ps, bad);
 }
 
-// several trial points at once (projected-gradient walk): evaluators with kCostBatch > 1 provide
-//     void cost_many(const double* pts /*cnt x m*/, int cnt, double* esq /*cnt*/, bool* bad /*cnt*/);
+// Candidate points of the projected-gradient walk.  Evaluators with kCostBatch > 1 own the storage
+// (shared memory in the persistent kernel) and evaluate up to kCostBatch points per call:
+//     double* batch_points();                       // kCostBatch x m, filled by the engine (unscaled)
+//     void    cost_many(int cnt, const double* dscl, int m);
+//     double  batch_cost(int c);  bool batch_bad(int c);
+// Everybody else evaluates one point per call through cost().
+template <int MM, class Eval, bool MANY = (Eval::kCostBatch > 1)>
+struct PgBatch {
+    double pts[MM], e;
+    bool b;
+    BG_HDI double* points(Eval&) { return pts; }
+    BG_HDI void run(Eval& ev, int, const double* dscl, int m) { e = eval_cost_scaled<MM>(ev, pts, dscl, m, b); }
+    BG_HDI double cost(Eval&, int) const { return e; }
+    BG_HDI bool bad(Eval&, int) const { return b; }
+};
 template <int MM, class Eval>
-BG_HDI void eval_cost_many_scaled(Eval& ev, const double* pts, int cnt, const double* dscl, int m, double* esq,
-                                  bool* bad) {
-    if constexpr (Eval::kCostBatch > 1) {
-        if (!dscl) {
-            ev.cost_many(pts, cnt, esq, bad);
-        } else {
-            double ps[Eval::kCostBatch * MM];
-            for (int c = 0; c < cnt; ++c)
-                for (int i = m; i-- > 0;) ps[c * m + i] = pts[c * m + i] * dscl[i];
-            ev.cost_many(ps, cnt, esq, bad);
-        }
-    } else {
-        for (int c = 0; c < cnt; ++c) esq[c] = eval_cost_scaled<MM>(ev, pts + c * m, dscl, m, bad[c]);
-    }
-}
+struct PgBatch<MM, Eval, true> {
+    BG_HDI double* points(Eval& ev) { return ev.batch_points(); }
+    BG_HDI void run(Eval& ev, int cnt, const double* dscl, int m) { ev.cost_many(cnt, dscl, m); }
+    BG_HDI double cost(Eval& ev, int c) const { return ev.batch_cost(c); }
+    BG_HDI bool bad(Eval& ev, int c) const { return ev.batch_bad(c); }
+};
 
 // info[] of lmbc_core.c:978-991 / lm_core.c:405-418
+template <int MM>
 BG_HDI void lm_fill_info(double* info, const double* JtJ, int m, double e0, double e, double ginf,
                          double dp2, double mu, int k, int stop, const LmCounters& c) {
     if (!info) return;
     double big = -DBL_MAX;
-    for (int i = 0; i < m; ++i)
-        if (big < JtJ[i * m + i]) big = JtJ[i * m + i];
+    LM_FOR(i) if (big < JtJ[i * m + i]) big = JtJ[i * m + i];
     info[0] = e0; info[1] = e; info[2] = ginf; info[3] = dp2; info[4] = mu / big;
     info[5] = (double)k; info[6] = (double)stop; info[7] = (double)c.nfev;
     info[8] = (double)c.njev; info[9] = (double)c.nlss;
@@ -262,15 +292,15 @@ BG_HDI int lm_line_search(Eval& ev, int m, const double* xc, double fc, const do
 
     fc *= 0.5;
     t = 0.0;
-    for (int i = m; i-- > 0;) t += step[i] * step[i];
+    LM_FOR_REV(i) t += step[i] * step[i];
     sln = sqrt(t);
     if (sln > stepmx) {
         const double scl = stepmx / sln;
-        for (int i = m; i-- > 0;) step[i] *= scl;
+        LM_FOR_REV(i) step[i] *= scl;
         sln = stepmx;
     }
     slp = rln = 0.0;
-    for (int i = m; i-- > 0;) {
+    LM_FOR_REV(i) {
         slp += g[i] * step[i];
         const double a = (lm_abs(xc[i]) >= 1.0) ? lm_abs(xc[i]) : 1.0;
         const double b = lm_abs(step[i]) / a;
@@ -280,15 +310,15 @@ BG_HDI int lm_line_search(Eval& ev, int m, const double* xc, double fc, const do
     lambda = 1.0;
 
     for (int it = kLsItMax; it-- > 0;) {
-        for (int i = m; i-- > 0;) xnew[i] = xc[i] + lambda * step[i];
-        box_project(xnew, box, m);
+        LM_FOR_REV(i) xnew[i] = xc[i] + lambda * step[i];
+        box_project<MM>(xnew, box, m);
 
         if (!dscl) {
             t = ev.cost(xnew, bad);
         } else {  // :262-266 scales the point in place and back (not an exact round trip)
-            for (int i = m; i-- > 0;) xnew[i] *= dscl[i];
+            LM_FOR_REV(i) xnew[i] *= dscl[i];
             t = ev.cost(xnew, bad);
-            for (int i = m; i-- > 0;) xnew[i] /= dscl[i];
+            LM_FOR_REV(i) xnew[i] /= dscl[i];
         }
         ++cnt.nfev;
         fpls = 0.5 * t;
@@ -346,8 +376,10 @@ BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double*
     LmCounters cnt = {0, 0, 0};
     const Box box = {lb, ub};
 
-    for (int i = 0; i < m * m; ++i) JtJ[i] = 0.0;
-    for (int i = 0; i < m; ++i) diag[i] = 0.0;
+    LM_FOR(i) {
+        LM_FOR(jj) JtJ[i * m + jj] = 0.0;
+        diag[i] = 0.0;
+    }
 
     // e = x - f(p) at the (projected) start, :522-534.  p is still in caller coordinates here.
     e_cur = ev.cost(p, bad);
@@ -355,8 +387,7 @@ BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double*
     e_init = e_cur;
     if (!lm_finite(e_cur)) stop = 7;
 
-    if (dscl)
-        for (int i = m; i-- > 0;) p[i] /= dscl[i];
+    if (dscl) LM_FOR_REV(i) p[i] /= dscl[i];
 
     for (k = 0; k < o.itmax && !stop; ++k) {
         if (e_cur <= o.eps3) { stop = 6; break; }
@@ -367,7 +398,7 @@ BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double*
         // ||J^T e||_inf over free variables, ||p||^2 (:639-646)
         j = numactive = 0;
         p_L2 = ginf = 0.0;
-        for (int i = 0; i < m; ++i) {
+        LM_FOR(i) {
             if (ub && p[i] == ub[i]) { ++numactive; if (Jte[i] > 0.0) ++j; }
             else if (lb && p[i] == lb[i]) { ++numactive; if (Jte[i] < 0.0) ++j; }
             else if (ginf < (tmp = lm_abs(Jte[i]))) ginf = tmp;
@@ -379,8 +410,7 @@ BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double*
         if (k == 0) {  // :666-674
             if (!lb && !ub) {
                 tmp = -DBL_MAX;
-                for (int i = 0; i < m; ++i)
-                    if (diag[i] > tmp) tmp = diag[i];
+                LM_FOR(i) if (diag[i] > tmp) tmp = diag[i];
                 mu = o.tau * tmp;
             } else {
                 mu = 0.5 * o.tau * e_cur;  // Kanzow's starting mu
@@ -390,7 +420,7 @@ BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double*
         for (;;) {
             bool use_pg = false;
 
-            for (int i = 0; i < m; ++i) JtJ[i * m + i] += mu;
+            LM_FOR(i) JtJ[i * m + i] += mu;
             const int solved = solve_lu<MM>(JtJ, Jte, Dp, m);
             ++cnt.nlss;
 
@@ -399,14 +429,14 @@ BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double*
                 const int nu2 = (int)((unsigned)nu << 1);
                 if (nu2 <= nu) { stop = 5; break; }
                 nu = nu2;
-                for (int i = 0; i < m; ++i) JtJ[i * m + i] = diag[i];
+                LM_FOR(i) JtJ[i * m + i] = diag[i];
                 continue;
             }
 
-            for (int i = 0; i < m; ++i) pDp[i] = p[i] + Dp[i];
-            box_project(pDp, box, m);
+            LM_FOR(i) pDp[i] = p[i] + Dp[i];
+            box_project<MM>(pDp, box, m);
             Dp_L2 = 0.0;
-            for (int i = 0; i < m; ++i) {
+            LM_FOR(i) {
                 Dp[i] = tmp = pDp[i] - p[i];
                 Dp_L2 += tmp * tmp;
             }
@@ -420,7 +450,7 @@ BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double*
 
             if (e_new <= gamma * e_cur) {  // LM step accepted, :753-785
                 dL = 0.0;
-                for (int i = 0; i < m; ++i) dL += Dp[i] * (mu * Dp[i] + Jte[i]);
+                LM_FOR(i) dL += Dp[i] * (mu * Dp[i] + Jte[i]);
                 if (dL > 0.0) {
                     dF = e_cur - e_new;
                     tmp = (2.0 * dF / dL - 1.0);
@@ -431,7 +461,7 @@ BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double*
                     mu = (mu >= tmp) ? tmp : mu;
                 }
                 nu = 2;
-                for (int i = 0; i < m; ++i) p[i] = pDp[i];
+                LM_FOR(i) p[i] = pDp[i];
                 e_cur = e_new;
                 gprevtaken = 0;
                 break;
@@ -439,7 +469,7 @@ BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double*
 
             // rejected: descent direction? (:810-816)
             gTd = 0.0;
-            for (int i = 0; i < m; ++i) {
+            LM_FOR(i) {
                 Jte[i] = -Jte[i];
                 gTd += Jte[i] * Dp[i];
             }
@@ -458,7 +488,7 @@ BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double*
             if (use_pg) {  // projected gradient search, :871-946
                 bool found = false, fatal = false;
                 tmp = 0.0;
-                for (int i = 0; i < m; ++i) tmp += Jte[i] * Jte[i];
+                LM_FOR(i) tmp += Jte[i] * Jte[i];
                 tmp = sqrt(tmp);
                 tmp = 100.0 / (1.0 + tmp);
                 t0 = (tmp <= tini) ? tmp : tini;
@@ -469,35 +499,38 @@ BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double*
                 // reduction); they are consumed strictly in levmar's order with levmar's tests, and
                 // candidates past the stopping one are discarded and not counted in nfev.
                 constexpr int KB = Eval::kCostBatch;
-                double ts[KB], pts[KB * MM], es[KB];
-                bool bads[KB], pg_done = false;
+                PgBatch<MM, Eval> batch;
+                double* pts = batch.points(ev);
+                bool pg_done = false;
                 t = gprevtaken ? t : t0;
                 while (t > tming && !pg_done) {
                     int nc = 0;
                     double tt = t;
                     while (nc < KB && tt > tming) {
-                        ts[nc] = tt;
-                        for (int i = 0; i < m; ++i) pts[nc * m + i] = p[i] - tt * Jte[i];
-                        box_project(pts + nc * m, box, m);
+                        double cand[MM];
+                        LM_FOR(i) cand[i] = p[i] - tt * Jte[i];
+                        box_project<MM>(cand, box, m);
+                        LM_FOR(i) pts[nc * m + i] = cand[i];
                         ++nc;
                         tt *= beta;
                     }
-                    eval_cost_many_scaled<MM>(ev, pts, nc, dscl, m, es, bads);
+                    batch.run(ev, nc, dscl, m);
                     bool restarted = false;
-                    for (int c = 0; c < nc; ++c) {
-                        t = ts[c];
+                    double tc = t;  // the same recurrence reproduces every candidate's t
+                    for (int c = 0; c < nc; ++c, tc *= beta) {
+                        t = tc;
                         Dp_L2 = 0.0;
-                        for (int i = 0; i < m; ++i) {
+                        LM_FOR(i) {
                             pDp[i] = pts[c * m + i];
                             Dp[i] = tmp = pDp[i] - p[i];
                             Dp_L2 += tmp * tmp;
                         }
-                        e_new = es[c];
+                        e_new = batch.cost(ev, c);
                         ++cnt.nfev;
-                        if (!lm_finite(e_new) && bads[c]) { stop = 7; fatal = true; pg_done = true; break; }
+                        if (!lm_finite(e_new) && batch.bad(ev, c)) { stop = 7; fatal = true; pg_done = true; break; }
 
                         gTd = 0.0;
-                        for (int i = 0; i < m; ++i) gTd += Jte[i] * Dp[i];
+                        LM_FOR(i) gTd += Jte[i] * Dp[i];
 
                         if (gprevtaken && e_new <= e_cur + 2.0 * 0.99999 * gTd) {  // starting t too small
                             t = t0 * beta;  // t = t0, then the loop increment of :885 still applies (:926-930)
@@ -516,12 +549,12 @@ BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double*
 
             // take the line-search / projected-gradient point (:948-967)
             Dp_L2 = 0.0;
-            for (int i = 0; i < m; ++i) {
+            LM_FOR(i) {
                 tmp = pDp[i] - p[i];
                 Dp_L2 += tmp * tmp;
             }
             if (Dp_L2 <= o.eps2_sq * p_L2) { stop = 2; break; }
-            for (int i = 0; i < m; ++i) p[i] = pDp[i];
+            LM_FOR(i) p[i] = pDp[i];
             e_cur = e_new;
             break;
         }
@@ -529,12 +562,10 @@ BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double*
 
 done:
     if (k >= o.itmax) stop = 3;
-    for (int i = 0; i < m; ++i) JtJ[i * m + i] = diag[i];
-    lm_fill_info(info, JtJ, m, e_init, e_cur, ginf, Dp_L2, mu, k, stop, cnt);
-    if (JtJ_out)
-        for (int i = 0; i < m * m; ++i) JtJ_out[i] = JtJ[i];
-    if (dscl)
-        for (int i = 0; i < m; ++i) p[i] *= dscl[i];
+    LM_FOR(i) JtJ[i * m + i] = diag[i];
+    lm_fill_info<MM>(info, JtJ, m, e_init, e_cur, ginf, Dp_L2, mu, k, stop, cnt);
+    if (JtJ_out) LM_FOR(i) LM_FOR(jj) JtJ_out[i * m + jj] = JtJ[i * m + jj];
+    if (dscl) LM_FOR(i) p[i] *= dscl[i];
     return (stop != 4 && stop != 7) ? k : kLmError;
 }
 
@@ -549,8 +580,10 @@ BG_HDI int lm_der(Eval& ev, int m, double* p, const LmOptions& o, double* info, 
     bool bad = false;
     LmCounters cnt = {0, 0, 0};
 
-    for (int i = 0; i < m * m; ++i) JtJ[i] = 0.0;
-    for (int i = 0; i < m; ++i) diag[i] = 0.0;
+    LM_FOR(i) {
+        LM_FOR(jj) JtJ[i * m + jj] = 0.0;
+        diag[i] = 0.0;
+    }
 
     e_cur = ev.cost(p, bad);
     cnt.nfev = 1;
@@ -564,7 +597,7 @@ BG_HDI int lm_der(Eval& ev, int m, double* p, const LmOptions& o, double* info, 
         ++cnt.njev;
 
         p_L2 = ginf = 0.0;
-        for (int i = 0; i < m; ++i) {
+        LM_FOR(i) {
             if (ginf < (tmp = lm_abs(Jte[i]))) ginf = tmp;
             diag[i] = JtJ[i * m + i];
             p_L2 += p[i] * p[i];
@@ -573,17 +606,16 @@ BG_HDI int lm_der(Eval& ev, int m, double* p, const LmOptions& o, double* info, 
 
         if (k == 0) {
             tmp = -DBL_MAX;
-            for (int i = 0; i < m; ++i)
-                if (diag[i] > tmp) tmp = diag[i];
+            LM_FOR(i) if (diag[i] > tmp) tmp = diag[i];
             mu = o.tau * tmp;
         }
 
         for (;;) {
-            for (int i = 0; i < m; ++i) JtJ[i * m + i] += mu;
+            LM_FOR(i) JtJ[i * m + i] += mu;
             ++cnt.nlss;
             if (solve_lu<MM>(JtJ, Jte, Dp, m)) {
                 Dp_L2 = 0.0;
-                for (int i = 0; i < m; ++i) {
+                LM_FOR(i) {
                     pDp[i] = p[i] + (tmp = Dp[i]);
                     Dp_L2 += tmp * tmp;
                 }
@@ -595,14 +627,14 @@ BG_HDI int lm_der(Eval& ev, int m, double* p, const LmOptions& o, double* info, 
                 if (!lm_finite(e_new)) { stop = 7; break; }
 
                 dL = 0.0;
-                for (int i = 0; i < m; ++i) dL += Dp[i] * (mu * Dp[i] + Jte[i]);
+                LM_FOR(i) dL += Dp[i] * (mu * Dp[i] + Jte[i]);
                 dF = e_cur - e_new;
                 if (dL > 0.0 && dF > 0.0) {
                     tmp = (2.0 * dF / dL - 1.0);
                     tmp = 1.0 - tmp * tmp * tmp;
                     mu = mu * ((tmp >= kOneThird) ? tmp : kOneThird);
                     nu = 2;
-                    for (int i = 0; i < m; ++i) p[i] = pDp[i];
+                    LM_FOR(i) p[i] = pDp[i];
                     e_cur = e_new;
                     break;
                 }
@@ -611,14 +643,13 @@ BG_HDI int lm_der(Eval& ev, int m, double* p, const LmOptions& o, double* info, 
             const int nu2 = (int)((unsigned)nu << 1);
             if (nu2 <= nu) { stop = 5; break; }
             nu = nu2;
-            for (int i = 0; i < m; ++i) JtJ[i * m + i] = diag[i];
+            LM_FOR(i) JtJ[i * m + i] = diag[i];
         }
     }
     if (k >= o.itmax) stop = 3;
-    for (int i = 0; i < m; ++i) JtJ[i * m + i] = diag[i];
-    lm_fill_info(info, JtJ, m, e_init, e_cur, ginf, Dp_L2, mu, k, stop, cnt);
-    if (JtJ_out)
-        for (int i = 0; i < m * m; ++i) JtJ_out[i] = JtJ[i];
+    LM_FOR(i) JtJ[i * m + i] = diag[i];
+    lm_fill_info<MM>(info, JtJ, m, e_init, e_cur, ginf, Dp_L2, mu, k, stop, cnt);
+    if (JtJ_out) LM_FOR(i) LM_FOR(jj) JtJ_out[i * m + jj] = JtJ[i * m + jj];
     return (stop != 4 && stop != 7) ? k : kLmError;
 }
 

@@ -62,6 +62,7 @@ elif what == "micro":
                 if st["cyc_total"]:
                     line += " [kernel Mcyc: sweep %.2f exchange %.2f total %.2f, points %d]" % (
                         st["cyc_sweep"] / 1e6, st["cyc_exchange"] / 1e6, st["cyc_total"] / 1e6, st["cost_points"])
+                    line += " x-phases/pass %s" % [int(v / passes) for v in st["cyc_exchange_phases"]]
         print(line, flush=True)
         del s
 elif what == "gather":
