@@ -80,6 +80,11 @@ extern "C" void brdfgpu_destroy(brdfgpu_ctx* ctx) {
     if (!ctx) return;
     brdfgpu_comm_destroy(ctx);
     cudaSetDevice(ctx->device);
+    if (ctx->pooled) {
+        ctx->pooled->pooled = false;
+        brdfgpu_samples_free(ctx, ctx->pooled);
+        ctx->pooled = nullptr;
+    }
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_partials); cudaFree(ctx->d_sync); cudaFree(ctx->d_result); cudaFree(ctx->d_fitio); cudaFree(ctx->d_cells);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
@@ -123,7 +128,39 @@ static int samples_fill(brdfgpu_ctx* ctx, brdfgpu_samples* s, const double* c, c
     if (x) BG_CUDA_OK(ctx, cudaMemcpyAsync(s->x, x, nb, kind, ctx->stream));
     else BG_CUDA_OK(ctx, cudaMemsetAsync(s->x, 0, nb, ctx->stream));  // x == NULL: zeros, lmbc_core.c:373
     if (samples_prepare(ctx, s) != 0) return BRDFGPU_LM_ERROR;
-    BG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    // host buffers may be reused by the caller as soon as we return: wait for the copies (the log
+    // pass behind them is a few microseconds)
+    if (kind == cudaMemcpyHostToDevice) BG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// Sample set backed by the context's reusable buffers (one user at a time; falls back to a fresh
+// allocation when busy).
+static int samples_upload_pooled(brdfgpu_ctx* ctx, long n, const double* cosphi, const double* t, const double* x,
+                                 int model, brdfgpu_samples** out) {
+    if (ctx->pooled_busy || n <= 0) return brdfgpu_samples_upload(ctx, n, cosphi, t, x, model, out);
+    BG_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->pooled || ctx->pooled_capacity < n) {
+        if (ctx->pooled) {
+            ctx->pooled->pooled = false;
+            brdfgpu_samples_free(ctx, ctx->pooled);
+            ctx->pooled = nullptr;
+            ctx->pooled_capacity = 0;
+        }
+        const long cap = n + n / 4 + 1024;
+        if (samples_alloc(ctx, cap, model, &ctx->pooled) != 0) return BRDFGPU_LM_ERROR;
+        ctx->pooled_capacity = cap;
+        ctx->pooled->pooled = true;
+    }
+    brdfgpu_samples* s = ctx->pooled;
+    s->n = n;
+    s->model = model;
+    ctx->pooled_busy = true;
+    if (samples_fill(ctx, s, cosphi, t, x, cudaMemcpyHostToDevice) != 0) {
+        ctx->pooled_busy = false;
+        return BRDFGPU_LM_ERROR;
+    }
+    *out = s;
     return 0;
 }
 
@@ -186,8 +223,12 @@ extern "C" int brdfgpu_samples_download(brdfgpu_ctx* ctx, const brdfgpu_samples*
 }
 
 extern "C" void brdfgpu_samples_free(brdfgpu_ctx* ctx, brdfgpu_samples* s) {
-    (void)ctx;
     if (!s) return;
+    if (s->pooled) {  // back to its context
+        ctx = ctx_or_default(ctx);
+        if (ctx && ctx->pooled == s) ctx->pooled_busy = false;
+        return;
+    }
     cudaFree(s->c); cudaFree(s->L); cudaFree(s->x); cudaFree(s->traw); cudaFree(s->jac);
     delete s;
 }
@@ -288,7 +329,7 @@ static int levmar_entry(const char* name, brdfgpu_func_t func, brdfgpu_jacf_t ja
     if (!ctx) return BRDFGPU_LM_ERROR;
     brdfgpu_samples* s = nullptr;
     const double* t = d->angles + (d->modelInfo == 1 ? (size_t)n : 2 * (size_t)n);
-    if (brdfgpu_samples_upload(ctx, n, d->angles, t, x, d->modelInfo, &s) != 0) return BRDFGPU_LM_ERROR;
+    if (samples_upload_pooled(ctx, n, d->angles, t, x, d->modelInfo, &s) != 0) return BRDFGPU_LM_ERROR;
     int ret;
     const int jm = need_jacf ? BRDFGPU_JAC_ANALYTIC : BRDFGPU_JAC_FD;
     if (constrained) ret = brdfgpu_fit_global(ctx, s, p, m, lb, ub, dscl, itmax, opts, info, covar, BRDFGPU_DRIVE_PERSISTENT, jm);
@@ -344,7 +385,7 @@ extern "C" int brdfgpu_solve_equation_single(const double* phi, const double* th
     static const double lb[3] = {0, 0, 0}, ub[3] = {100, 100, 100};
     static const double opts[5] = {1E-03, 1E-15, 1E-10, 1E-50, 1.0};  // brdfdata.cpp:1055-1056
     brdfgpu_samples* s = nullptr;
-    if (brdfgpu_samples_upload(ctx, nsamples, phi, t, I, model, &s) != 0) return BRDFGPU_LM_ERROR;
+    if (samples_upload_pooled(ctx, nsamples, phi, t, I, model, &s) != 0) return BRDFGPU_LM_ERROR;
     p[0] = p[1] = p[2] = 0.0;  // brdfdata.cpp:1002
     const int ret = brdfgpu_fit_global(ctx, s, p, 3, lb, ub, nullptr, 2000, opts, info, nullptr, BRDFGPU_DRIVE_PERSISTENT,
                                        BRDFGPU_JAC_FD);

@@ -58,6 +58,12 @@ struct brdfgpu_ctx {
     // samples resident in shared memory, CTAs
     unsigned long long fit_stats[12] = {0};
 
+    // device buffers of the levmar-signature entry points, kept between calls (cudaMalloc/cudaFree
+    // per call cost more than the fit itself at 10^6 samples)
+    struct brdfgpu_samples* pooled = nullptr;
+    long pooled_capacity = 0;
+    bool pooled_busy = false;
+
     // multi-GPU
     void* nccl_comm = nullptr;
     int rank = 0, nranks = 1;
@@ -77,6 +83,7 @@ struct brdfgpu_samples {
     double* traw = nullptr;  // raw model cosine (read only on the pow() path)
     // secant (dlevmar_dif) state: stored Jacobian, 3 columns SoA, allocated on first use
     double* jac = nullptr;
+    bool pooled = false;  // owned by the context (brdfgpu_ctx::pooled): free only returns it
 };
 
 struct brdfgpu_batch {

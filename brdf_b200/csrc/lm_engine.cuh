@@ -502,11 +502,12 @@ BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double*
                 PgBatch<MM, Eval> batch;
                 double* pts = batch.points(ev);
                 bool pg_done = false;
+                int width = 1;  // most walks stop at their first candidates: speculate 1, 2, 4, ... KB points
                 t = gprevtaken ? t : t0;
                 while (t > tming && !pg_done) {
                     int nc = 0;
                     double tt = t;
-                    while (nc < KB && tt > tming) {
+                    while (nc < width && tt > tming) {
                         double cand[MM];
                         LM_FOR(i) cand[i] = p[i] - tt * Jte[i];
                         box_project<MM>(cand, box, m);
@@ -541,6 +542,7 @@ BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double*
                         if (e_new <= e_cur + 2.0 * alpha * gTd) { found = true; pg_done = true; break; }
                     }
                     if (!pg_done && !restarted) t = tt;
+                    width = (2 * width < KB) ? 2 * width : KB;
                 }
                 if (fatal) goto done;
                 if (!found) { gprevtaken = 0; break; }
