@@ -42,7 +42,8 @@ class ExtraData(C.Structure):
 
 
 def lib_path():
-    return os.path.join(HERE, "libbrdfgpu.so")
+    # BRDFGPU_LIB: a tuning variant built with `make VARIANT=... EXTRA=...` (experiments only)
+    return os.environ.get("BRDFGPU_LIB") or os.path.join(HERE, "libbrdfgpu.so")
 
 
 def build(force=False):

@@ -14,6 +14,12 @@
 namespace brdfgpu {
 
 constexpr int kBatchThreads = 128;
+// resident CTAs per SM the register allocation is held to: 8 (64 registers) for half-warp fits,
+// 6 (80 registers) for warp fits -- measured best on B200 (profiles/r01_summary.md); the kernel is
+// latency-bound (divergent control flow between fits), so occupancy beats a spill-free allocation
+#ifndef BG_BATCH_MIN_BLOCKS
+#define BG_BATCH_MIN_BLOCKS(G) ((G) == 16 ? 8 : 6)
+#endif
 
 struct BatchSpec {
     int itmax, jkind, has_lb, has_ub, dif_accounting;
@@ -96,7 +102,7 @@ struct GroupEval {
 };
 
 template <int G, int S>
-__global__ void __launch_bounds__(kBatchThreads) k_batched_fit(const double* __restrict__ c, const double* __restrict__ L,
+__global__ void __launch_bounds__(kBatchThreads, BG_BATCH_MIN_BLOCKS(G)) k_batched_fit(const double* __restrict__ c, const double* __restrict__ L,
                                                                 const double* __restrict__ x,
                                                                 const double* __restrict__ traw, long nfit, int nper,
                                                                 int model, BatchSpec spec, double* __restrict__ p_out,

@@ -7,7 +7,7 @@
  * call it: the product path is CUDA only and fails loudly without its extension.
  *
  * Pinning: the solver half is checked bit-for-bit against the reference's own levmar compiled
- * unmodified into oracle/_ref/liblevmar_ref.so (tests/test_oracle_vs_ref.py), against the known
+ * unmodified into oracle/_ref/liblevmar_ref.so (tests/test_oracle_kat.py, tests/test_oracle_golden.py), against the known
  * answers of levmar/lmdemo.c (tests/test_oracle_kat.py) and against committed golden vectors that
  * oracle/_ref produced (tests/golden/, tests/golden/make_golden.py).  The gather half restates
  * brdfdata.cpp with the Tsai .cal projection; no reference test pins results
