@@ -83,6 +83,7 @@ struct brdfgpu_samples {
     double* traw = nullptr;  // raw model cosine (read only on the pow() path)
     // secant (dlevmar_dif) state: stored Jacobian, 3 columns SoA, allocated on first use
     double* jac = nullptr;
+    long jac_capacity = 0;  // samples the secant state was allocated for
     bool pooled = false;  // owned by the context (brdfgpu_ctx::pooled): free only returns it
 };
 
