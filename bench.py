@@ -198,12 +198,15 @@ def run_gpu_arm(args):
     launches0 = ctx.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
-    evals = passes = 0.0
+    evals = passes = ref_passes = 0.0
     for _ in range(args.steps):
         ret, p, info = fit()
         evals += info[7]
         st = ctx.fit_stats()
         passes += st["jac_passes"] + st["cost_passes"]   # sweeps over the samples (a batched PG sweep counts once)
+        # passes over the samples the REFERENCE algorithm makes for the same trajectory: one per Jacobian (fused
+        # here; levmar makes m+1) and one per counted cost evaluation (speculative trial points are not counted)
+        ref_passes += info[8] + (info[7] - 4.0 * info[8])
     ev1.record(stream)
     barrier()
     launches = ctx.launches - launches0
@@ -221,7 +224,7 @@ def run_gpu_arm(args):
         # the step IS one persistent kernel launch per rank (+ an 800-byte result copy); at N>1 the
         # cross-GPU exchange of the sums happens inside it (peer stores over NVLink)
         kernel, launches_per_step, kern_ms = "k_persistent_fit", 1, ms / args.steps
-        algo_bytes = 24.0 * n * passes / args.steps
+        algo_bytes = 24.0 * n * ref_passes / args.steps
     else:
         kernel = "k_normal_eq<forward>"
         reps = 50
@@ -237,9 +240,14 @@ def run_gpu_arm(args):
     roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
                 "launch_ms": kern_ms,
-                "note": "24 B/sample/sweep x the sweeps the kernel made; at 10^6 samples/GPU the whole shard is held in "
-                        "shared memory for the fit, so this 'achieved' is on-chip traffic and may exceed the HBM peak -- "
-                        "see roofline_hbm for the HBM-resident regime (10^8 samples)"}
+                "sweeps_per_launch": passes / args.steps, "evaluations_per_launch": ref_passes / args.steps,
+                "swept_bytes_per_launch": 24.0 * n * passes / args.steps,
+                "note": "algorithmic bytes = 24 B/sample x the evaluations levmar counts for this trajectory (1 per fused "
+                        "Jacobian, 1 per cost evaluation; SURVEY.md 8d).  At 10^6 samples/GPU the shard is held in shared "
+                        "memory for the whole fit and the projected-gradient walk evaluates up to 8 trial points per sweep, "
+                        "so almost none of these bytes move through HBM (ncu: 45 MB of DRAM traffic per launch) and "
+                        "'achieved' is an algorithmic rate, not HBM utilisation; the kernel is bound by the FP64 pipe and "
+                        "the per-evaluation exchange latency.  roofline_hbm is the HBM-resident regime (10^8 samples)."}
 
     extra = {}
     if rank == 0 and world == 1 and not args.quick:

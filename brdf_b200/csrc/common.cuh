@@ -52,6 +52,7 @@ struct brdfgpu_ctx {
     void* d_fitio = nullptr;
     void* h_fitio = nullptr;  // pinned
     uint4* d_cells = nullptr;     // flagged exchange cells of the persistent fit: 2 x kMaxPersistBlocks x 16
+    int tma_mode = 0;             // 0: not probed, 1: automatic, 2: never, 3: always (BRDFGPU_TMA)
     long persist_smem_max = 0;    // dynamic shared memory one CTA of the persistent fit may use (0: not probed, <0: unusable)
     // what the last global fit did: sweeps with a Jacobian, cost-only sweeps, trial points evaluated
     // (>= the levmar-counted ones: the projected-gradient walk is evaluated eight points per sweep),

@@ -20,6 +20,7 @@
 //                code on the same grid-reduced sums, a grid barrier per evaluation.
 #include <cooperative_groups.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -87,6 +88,149 @@ __device__ __forceinline__ void stream_count_bad(const SampleView& v, const Pass
         const double e = residual_of(q, v.c[i], v.L[i], v.x[i], v.traw, i);
         *cnt += lm_finite(e) ? 0.0 : 1.0;
     }
+}
+
+__device__ __forceinline__ double2 lds_pair(unsigned base, int i) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(base + 16u * (unsigned)i) : "memory");
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA-staged streaming (large sample sets, HBM regime).  The loads of a register-prefetch loop are
+// limited by registers: ~48 B per thread in flight, 24-36 KB per SM, while HBM3e needs ~40 KB per SM
+// just to cover its latency.  Here one elected thread per CTA moves whole tiles (512 sample pairs of
+// each of the three arrays = 24 KB) from global to shared memory with 1-D bulk async copies
+// (cp.async.bulk, the TMA engine) into a 4-deep ring guarded by mbarriers: ~72 KB per CTA in flight,
+// no registers spent on it, and the compute warps read their pairs back with LDS.128.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTileThreads = 256;
+constexpr int kTilePairs = 2 * kTileThreads;  // two pairs (four samples) per thread and tile
+constexpr int kTileStages = 4;
+constexpr size_t kTileRingBytes = (size_t)kTileStages * 3 * kTilePairs * sizeof(double2);  // 96 KB
+
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+// Calls body(c0, l0, x0, i0, c1, l1, x1, i1, n_valid) for every group of two sample pairs this CTA
+// owns (tiles blockIdx.x, blockIdx.x + gridDim.x, ...); n_valid in {0, 1, 2} pairs, i* = index of the
+// pair's first sample.
+template <class Body>
+__device__ __forceinline__ void stream_tiles(const SampleView& v, Body&& body) {
+    extern __shared__ __align__(128) unsigned char tile_ring[];
+    __shared__ __align__(8) unsigned long long bars[2 * kTileStages];  // full[stage], empty[stage]
+    const long npair = v.n >> 1;
+    const long ntiles = (npair + kTilePairs - 1) / kTilePairs;
+    const long mine = (long)blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const unsigned ring = smem_addr(tile_ring), bar0 = smem_addr(bars);
+    constexpr unsigned kArrayBytes = kTilePairs * sizeof(double2), kStageBytes = 3 * kArrayBytes;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kTileStages; ++s) {
+            mbar_init(bar0 + 8 * s, 1);                                    // the producer's expect_tx arrive
+            mbar_init(bar0 + 8 * (kTileStages + s), kTileThreads / 32);    // one arrive per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](long j) {  // tile number j of this CTA into stage j % kTileStages
+        const int s = (int)(j % kTileStages);
+        const long first = ((long)blockIdx.x + j * gridDim.x) * kTilePairs;
+        const long left = npair - first;
+        const unsigned bytes = (unsigned)((left < kTilePairs ? left : kTilePairs) * sizeof(double2));
+        const unsigned full = bar0 + 8 * s, dst = ring + s * kStageBytes;
+        mbar_expect_tx(full, 3 * bytes);
+        bulk_g2s(dst, v.c + 2 * first, bytes, full);
+        bulk_g2s(dst + kArrayBytes, v.L + 2 * first, bytes, full);
+        bulk_g2s(dst + 2 * kArrayBytes, v.x + 2 * first, bytes, full);
+    };
+    if (threadIdx.x == 0)
+        for (long j = 0; j < mine && j < kTileStages; ++j) issue(j);
+    for (long j = 0; j < mine; ++j) {
+        const int s = (int)(j % kTileStages);
+        if (threadIdx.x == 0 && j >= 1 && j - 1 + kTileStages < mine) {  // refill the stage drained one tile ago
+            mbar_wait(bar0 + 8 * (kTileStages + (int)((j - 1) % kTileStages)), (unsigned)(((j - 1) / kTileStages) & 1));
+            issue(j - 1 + kTileStages);
+        }
+        mbar_wait(bar0 + 8 * s, (unsigned)((j / kTileStages) & 1));
+        const long first = ((long)blockIdx.x + j * gridDim.x) * kTilePairs;
+        const long left = npair - first;
+        const int here = (int)(left < kTilePairs ? left : kTilePairs);
+        const unsigned base = ring + s * kStageBytes;
+        const int a = threadIdx.x, b = threadIdx.x + kTileThreads;
+        const int valid = (a < here) + (b < here);
+        double2 c0 = make_double2(0, 0), l0 = c0, x0 = c0, c1 = c0, l1 = c0, x1 = c0;
+        if (valid >= 1) { c0 = lds_pair(base, a); l0 = lds_pair(base + kArrayBytes, a); x0 = lds_pair(base + 2 * kArrayBytes, a); }
+        if (valid >= 2) { c1 = lds_pair(base, b); l1 = lds_pair(base + kArrayBytes, b); x1 = lds_pair(base + 2 * kArrayBytes, b); }
+        body(c0, l0, x0, 2 * (first + a), c1, l1, x1, 2 * (first + b), valid);
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(bar0 + 8 * (kTileStages + s));
+    }
+}
+
+template <int JAC>
+__global__ void __launch_bounds__(kTileThreads, 2) k_normal_eq_tma(SampleView v, PassParams q, double* partials,
+                                                                   unsigned* ticket, Publish pub) {
+    __shared__ double red[(kTileThreads / 32) * NACC];
+    double acc[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+    stream_tiles(v, [&](double2 c0, double2 l0, double2 x0, long i0, double2 c1, double2 l1, double2 x1, long i1, int valid) {
+        if (valid == 2) {
+            const double cc[4] = {c0.x, c0.y, c1.x, c1.y}, ll[4] = {l0.x, l0.y, l1.x, l1.y}, xx[4] = {x0.x, x0.y, x1.x, x1.y};
+            const long idx[4] = {i0, i0 + 1, i1, i1 + 1};
+            accumulate_jac_n<JAC, 4>(q, q, cc, ll, xx, v.traw, idx, acc);
+        } else if (valid == 1) {
+            accumulate_jac_pair<JAC>(q, q, c0, l0, x0, v.traw, i0, acc);
+        }
+    });
+    if ((v.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const long j = v.n - 1;
+        accumulate_jac<JAC>(q, v.c[j], v.L[j], v.x[j], v.traw, j, acc);
+    }
+    block_reduce_to<NACC>(acc, red, partials + (long)blockIdx.x * NACC);
+    last_block_finish<NACC>(partials, ticket, red, pub);
+}
+
+__global__ void __launch_bounds__(kTileThreads, 2) k_cost_tma(SampleView v, PassParams q, double* partials, unsigned* ticket,
+                                                              Publish pub) {
+    __shared__ double red[(kTileThreads / 32)];
+    double a0 = 0.0, a1 = 0.0;
+    stream_tiles(v, [&](double2 c0, double2 l0, double2 x0, long i0, double2 c1, double2 l1, double2 x1, long i1, int valid) {
+        if (valid == 2) accumulate_cost_2pairs(q, c0, l0, x0, i0, c1, l1, x1, i1, v.traw, &a0, &a1);
+        else if (valid == 1) accumulate_cost_pair(q, c0, l0, x0, v.traw, i0, &a0);
+    });
+    if ((v.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const long j = v.n - 1;
+        accumulate_cost(q, v.c[j], v.L[j], v.x[j], v.traw, j, &a0);
+    }
+    double acc[1] = {a0 + a1};
+    block_reduce_to<1>(acc, red, partials + (long)blockIdx.x);
+    last_block_finish<1>(partials, ticket, red, pub);
 }
 
 template <int JAC>
@@ -187,13 +331,55 @@ static int to_jac_kind(int jac_mode, double delta_signed) {
     return delta_signed < 0.0 ? kJacCentral : kJacForward;
 }
 
+// The TMA-staged kernel pays off for the Jacobian pass (FP64-heavy, register-hungry) once the sample
+// set outgrows on-chip residency.  BRDFGPU_TMA=0/1 in the environment forces never/always (tests).
+static bool use_tma(brdfgpu_ctx* ctx, long n, bool cost_pass = false) {
+    if (ctx->tma_mode == 0) {
+        const char* e = getenv("BRDFGPU_TMA");
+        int mode = 1;  // 1 = automatic
+        if (e && *e) mode = (*e == '0') ? 2 : 3;  // 2 = never, 3 = always
+        bool ok = cudaFuncSetAttribute(k_cost_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileRingBytes) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(k_normal_eq_tma<kJacForward>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileRingBytes) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(k_normal_eq_tma<kJacCentral>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileRingBytes) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(k_normal_eq_tma<kJacAnalytic>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileRingBytes) == cudaSuccess;
+        ctx->tma_mode = ok ? mode : 2;
+    }
+    if (ctx->tma_mode == 2) return false;
+    if (ctx->tma_mode == 3) return n >= 2 * kTilePairs;
+    // measured on B200 (profiles/r01_summary.md): K2 5.2 -> 6.0 TB/s at 10^8 samples, break-even near
+    // 10^6; the cost pass is purely HBM-bound and already at 6.9 TB/s with register prefetch
+    return !cost_pass && n >= 2000000;
+}
+static int tma_blocks(const brdfgpu_ctx* ctx, long n) {
+    const long ntiles = ((n >> 1) + kTilePairs - 1) / kTilePairs;
+    const long cap = (long)ctx->sm_count * 2;
+    return (int)(ntiles < cap ? (ntiles < 1 ? 1 : ntiles) : cap);
+}
+
 static int launch_normal_eq(brdfgpu_ctx* ctx, const brdfgpu_samples* s, const double* p, double delta, int jkind,
                             bool publish) {
     const PassParams q = make_pass_params(p, s->model, delta, jkind);
-    const int blocks = pass_blocks(ctx, s->n, 2);
     Publish pub{ctx->d_result, nullptr, nullptr, 0};
     if (publish) pub = Publish{ctx->d_result, ctx->h_result_dev, ctx->h_seq_dev, ++ctx->seq};
     const SampleView v = view_of(s);
+    if (use_tma(ctx, s->n)) {
+        const int blocks = tma_blocks(ctx, s->n);
+        switch (jkind) {
+            case kJacForward:
+                k_normal_eq_tma<kJacForward><<<blocks, kTileThreads, kTileRingBytes, ctx->stream>>>(v, q, ctx->d_partials, ctx->d_sync, pub);
+                break;
+            case kJacCentral:
+                k_normal_eq_tma<kJacCentral><<<blocks, kTileThreads, kTileRingBytes, ctx->stream>>>(v, q, ctx->d_partials, ctx->d_sync, pub);
+                break;
+            default:
+                k_normal_eq_tma<kJacAnalytic><<<blocks, kTileThreads, kTileRingBytes, ctx->stream>>>(v, q, ctx->d_partials, ctx->d_sync, pub);
+                break;
+        }
+        ++ctx->launches;
+        BG_CUDA_OK(ctx, cudaGetLastError());
+        return 0;
+    }
+    const int blocks = pass_blocks(ctx, s->n, 2);
     switch (jkind) {
         case kJacForward:
             k_normal_eq<kJacForward><<<blocks, kPassThreads, 0, ctx->stream>>>(v, q, ctx->d_partials, ctx->d_sync, pub);
@@ -215,6 +401,12 @@ int launch_cost(brdfgpu_ctx* ctx, const brdfgpu_samples* s, const double* p, boo
     const int blocks = pass_blocks(ctx, s->n, 4);
     Publish pub{ctx->d_result, nullptr, nullptr, 0};
     if (publish) pub = Publish{ctx->d_result, ctx->h_result_dev, ctx->h_seq_dev, ++ctx->seq};
+    if (!count_bad && use_tma(ctx, s->n, true)) {
+        k_cost_tma<<<tma_blocks(ctx, s->n), kTileThreads, kTileRingBytes, ctx->stream>>>(view_of(s), q, ctx->d_partials, ctx->d_sync, pub);
+        ++ctx->launches;
+        BG_CUDA_OK(ctx, cudaGetLastError());
+        return 0;
+    }
     if (count_bad) k_cost<true><<<blocks, kPassThreads, 0, ctx->stream>>>(view_of(s), q, ctx->d_partials, ctx->d_sync, pub);
     else k_cost<false><<<blocks, kPassThreads, 0, ctx->stream>>>(view_of(s), q, ctx->d_partials, ctx->d_sync, pub);
     ++ctx->launches;
@@ -394,7 +586,10 @@ struct HostEval {
 //   * the projected-gradient walk hands its candidate points to cost_many() eight at a time: one
 //     sweep over the samples and one exchange for eight levmar function evaluations.
 // ------------------------------------------------------------------------------------------------
-constexpr int kPersistThreads = 512;    // 16 warps, <= 128 registers per thread
+#ifndef BG_PERSIST_THREADS
+#define BG_PERSIST_THREADS 512
+#endif
+constexpr int kPersistThreads = BG_PERSIST_THREADS;  // 512: 16 warps, <= 128 registers per thread
 constexpr int kMaxPersistBlocks = 160;  // >= SM count (148 on B200)
 constexpr int kGridCostBatch = 8;       // trial points per cost_many() sweep (<= NACC)
 constexpr long long kSpinCycles = 6000000000LL;  // ~3 s at 2 GHz, then the fit is abandoned
@@ -439,12 +634,6 @@ __device__ __forceinline__ double wait_cell(const uint4* src, unsigned tag, int*
     return c.value();
 }
 __device__ __forceinline__ unsigned next_tag(unsigned e) { return e + 1u ? e + 1u : 1u; }  // never 0: buffers start zeroed
-
-__device__ __forceinline__ double2 lds_pair(unsigned base, int i) {
-    double2 v;
-    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(base + 16u * (unsigned)i));
-    return v;
-}
 
 // What the control warp asks the CTA to do next (shared memory).
 enum SweepKind { kQuit = 0, kSweepJacForward, kSweepJacCentral, kSweepJacAnalytic, kSweepCost, kSweepMany, kSweepBad };
