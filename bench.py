@@ -238,8 +238,9 @@ def run_gpu_arm(args):
         kern_ms, launches_per_step, algo_bytes = e0.elapsed_time(e1) / reps, None, 24.0 * n
     achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
-                "launch_ms": kern_ms,
+                "traffic": 45.6e6 if drive == A.DRIVE_PERSISTENT else None,
+                "traffic_source": "ncu --set full, profiles/r01_ncu_tables.md (dram read + write of one k_persistent_fit launch)",
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": kern_ms,
                 "sweeps_per_launch": passes / args.steps, "evaluations_per_launch": ref_passes / args.steps,
                 "swept_bytes_per_launch": 24.0 * n * passes / args.steps,
                 "note": "algorithmic bytes = 24 B/sample x the evaluations levmar counts for this trajectory (1 per fused "
@@ -292,20 +293,25 @@ def run_gpu_arm(args):
         barrier()
         t0 = time.perf_counter()
         ev = 0.0
+        h = C.c_void_p()
+        ctx._ok(A.lib().brdfgpu_samples_upload(ctx.handle, n, C.cast(pin[0].data_ptr(), A.dptr), C.cast(pin[1].data_ptr(), A.dptr),
+                                               C.cast(pin[2].data_ptr(), A.dptr), 1, C.byref(h)))
+        ss = A.Samples(ctx, h)
+        barrier()
+        t0 = time.perf_counter()
         for _ in range(args.steps):
-            h = C.c_void_p()
-            ctx._ok(A.lib().brdfgpu_samples_upload(ctx.handle, n, C.cast(pin[0].data_ptr(), A.dptr), C.cast(pin[1].data_ptr(), A.dptr),
-                                                   C.cast(pin[2].data_ptr(), A.dptr), 1, C.byref(h)))
-            ss = A.Samples(ctx, h)
+            # every step: this rank's shard host -> device, the fit over all ranks' shards, results back
+            ctx._ok(A.lib().brdfgpu_samples_reload(ctx.handle, ss.handle, C.cast(pin[0].data_ptr(), A.dptr),
+                                                   C.cast(pin[1].data_ptr(), A.dptr), C.cast(pin[2].data_ptr(), A.dptr)))
             r, pp, inf = ctx.fit_global(ss, A.REF_GLOBAL, drive=drive)
             ev += inf[7]
-            ss.free()
+        ss.free()
         barrier()
         dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         dt = float(dt.item())
         e2e = {"value": ev * n_total / dt, "unit": UNIT, "h2d_bytes_per_step": 3 * 8 * n, "d2h_bytes_per_step": 8 * 13 + 4,
-               "ms_per_step": 1e3 * dt / args.steps, "call": "brdfgpu_samples_upload + brdfgpu_fit_global per rank"}
+               "ms_per_step": 1e3 * dt / args.steps, "call": "brdfgpu_samples_reload (pinned host shard -> device) + brdfgpu_fit_global per rank"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -313,6 +319,9 @@ def run_gpu_arm(args):
         cpu = {"value": nfev * n / dt, "unit": UNIT, "cores": 1, "kind": kind,
                "sample": "the full step once: n=%d, REF_GLOBAL, %d iterations, %.1f s" % (n, int(info_cpu[5]), dt),
                "host_cores_available": os.cpu_count(), "seconds_per_fit": dt,
+               "time_to_solution_ratio": {"resident": dt / (ms / args.steps * 1e-3), "e2e": dt / (e2e["ms_per_step"] * 1e-3),
+                                          "note": "same problem, same answer; the two trajectories differ in evaluation count "
+                                                  "(summation order, SURVEY.md Q13), so seconds per fit is the like-for-like ratio"},
                "parity": {"p_rel_err_max": float(np.max(np.abs(p - p_cpu) / np.abs(p_cpu))),
                           "cost_rel_err": float(abs(info[1] - info_cpu[1]) / info_cpu[1]),
                           "p_gpu": [float(v) for v in p], "p_cpu": [float(v) for v in p_cpu]}}
@@ -362,7 +371,8 @@ def side_measurements(ctx, torch, stream, A, peak):
         res[name] = {"launch_ms": ms, "achieved": gbs, "frac": gbs / peak, "sample_visits_per_s": n / (ms * 1e-3)}
     k2 = res["k_normal_eq<forward>"]
     out["roofline_hbm"] = {"bound": "hbm", "kernel": "k_normal_eq<forward>", "samples": n, "achieved": k2["achieved"], "peak": peak,
-                           "unit": "GB/s", "frac": k2["frac"], "traffic": None, "algorithmic_bytes_per_launch": 24.0 * n,
+                           "unit": "GB/s", "frac": k2["frac"], "traffic": 2.4048e9,
+                           "traffic_source": "ncu --set full, profiles/r01_ncu_tables.md", "algorithmic_bytes_per_launch": 24.0 * n,
                            "launch_ms": k2["launch_ms"], "k_cost": res["k_cost"],
                            "note": "inputs 2.4 GB >> 126 MB L2, 10 back-to-back launches after 3 warm-ups"}
     del s

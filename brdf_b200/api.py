@@ -72,6 +72,7 @@ SIGNATURES = {
     "brdfgpu_stream": (_V, [_V]),
     "brdfgpu_synchronize": (C.c_int, [_V]),
     "brdfgpu_samples_upload": (C.c_int, [_V, C.c_long, dptr, dptr, dptr, C.c_int, C.POINTER(_V)]),
+    "brdfgpu_samples_reload": (C.c_int, [_V, _V, dptr, dptr, dptr]),
     "brdfgpu_samples_from_device": (C.c_int, [_V, C.c_long, _V, _V, _V, C.c_int, C.POINTER(_V)]),
     "brdfgpu_samples_synth": (C.c_int, [_V, C.c_long, C.c_ulonglong, C.c_long, dptr, C.c_int, C.POINTER(_V)]),
     "brdfgpu_samples_count": (C.c_long, [_V]),

@@ -179,6 +179,14 @@ extern "C" int brdfgpu_samples_upload(brdfgpu_ctx* ctx, long n, const double* co
     return 0;
 }
 
+extern "C" int brdfgpu_samples_reload(brdfgpu_ctx* ctx, brdfgpu_samples* s, const double* cosphi, const double* t,
+                                      const double* x) {
+    ctx = ctx_or_default(ctx);
+    if (!ctx || !s || (s->n > 0 && (!cosphi || !t))) return BRDFGPU_LM_ERROR;
+    BG_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    return samples_fill(ctx, s, cosphi, t, x, cudaMemcpyHostToDevice);
+}
+
 extern "C" int brdfgpu_samples_from_device(brdfgpu_ctx* ctx, long n, const double* d_cosphi, const double* d_t,
                                            const double* d_x, int model, brdfgpu_samples** out) {
     ctx = ctx_or_default(ctx);

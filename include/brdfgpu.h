@@ -110,6 +110,9 @@ int brdfgpu_synchronize(brdfgpu_ctx *ctx);
  * lmbc_core.c:373).  Device layout: three fp64 arrays, 24 B per sample per pass. */
 int brdfgpu_samples_upload(brdfgpu_ctx *ctx, long n, const double *cosphi, const double *t,
                            const double *x, int model, brdfgpu_samples **out);
+/* New values for an existing set of the same size (device buffers are reused: no allocation). */
+int brdfgpu_samples_reload(brdfgpu_ctx *ctx, brdfgpu_samples *s, const double *cosphi, const double *t,
+                           const double *x);
 /* Same from DEVICE pointers (e.g. another library's tensors); data is copied device-to-device. */
 int brdfgpu_samples_from_device(brdfgpu_ctx *ctx, long n, const double *d_cosphi, const double *d_t,
                                 const double *d_x, int model, brdfgpu_samples **out);
