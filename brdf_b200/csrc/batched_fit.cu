@@ -58,7 +58,7 @@ struct GroupEval {
         }
     }
 
-    __device__ __noinline__ void jac(const double* p, double* JtJ, double* Jte) const {
+    __device__ __forceinline__ void jac(const double* p, double* JtJ, double* Jte) const {
         const PassParams q = make_pass_params(p, model, delta, jkind);
         double acc[NACC];
 #pragma unroll
@@ -74,8 +74,8 @@ struct GroupEval {
         Jte[0] = acc[G0]; Jte[1] = acc[G1]; Jte[2] = acc[G2];
     }
 
-    __device__ __noinline__ double cost(const double* p, bool& bad) const {
-        const PassParams q = make_pass_params(p, model, 1.0, kJacAnalytic);
+    __device__ __forceinline__ double cost(const double* p, bool& bad) const {
+        const CostPoint q = make_cost_point(p, model);
         double esq = 0.0, nbad = 0.0;
         if (S > 0) {
 #pragma unroll
