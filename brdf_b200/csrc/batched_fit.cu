@@ -8,6 +8,8 @@
 // code (lm_engine.cuh) on the same sums, so there is no divergence inside a group and no
 // communication between groups.  Fits diverge freely from each other (different iteration counts,
 // line searches, projected-gradient probes).
+#include <cstdlib>
+
 #include "brdf_model.cuh"
 #include "common.cuh"
 
@@ -18,7 +20,7 @@ constexpr int kBatchThreads = 128;
 // 6 (80 registers) for warp fits -- measured best on B200 (profiles/r01_summary.md); the kernel is
 // latency-bound (divergent control flow between fits), so occupancy beats a spill-free allocation
 #ifndef BG_BATCH_MIN_BLOCKS
-#define BG_BATCH_MIN_BLOCKS(G) ((G) == 16 ? 8 : 6)
+#define BG_BATCH_MIN_BLOCKS(G) ((G) == 32 ? 6 : 8)
 #endif
 
 struct BatchSpec {
@@ -216,12 +218,35 @@ int batch_fit(brdfgpu_ctx* ctx, brdfgpu_batch* b, const double* p0, const double
     }
     spec.opt = lm_options(opts, itmax);
 
+    // Lanes per fit G and samples per lane S (S * G >= nper).  Several fits share a warp when G < 32:
+    // their control flow runs in the same instruction stream wherever it coincides (loops reconverge
+    // at their exits), which matters because the control code, not the model, dominates the
+    // instruction count of a small fit.  BRDFGPU_BATCH_G overrides the choice (experiments).
     const int n = b->nper;
-    if (n <= 16) launch_batch<16, 1>(ctx, b, spec);
-    else if (n <= 32) launch_batch<32, 1>(ctx, b, spec);
-    else if (n <= 64) launch_batch<32, 2>(ctx, b, spec);
-    else if (n <= 128) launch_batch<32, 4>(ctx, b, spec);
-    else launch_batch<32, 0>(ctx, b, spec);
+    int G = n <= 16 ? 16 : 32;
+    if (const char* e = getenv("BRDFGPU_BATCH_G")) G = atoi(e);
+    const int S = (n + G - 1) / G;
+    bool ok = true;
+    if (G == 8) {
+        if (S <= 1) launch_batch<8, 1>(ctx, b, spec);
+        else if (S <= 2) launch_batch<8, 2>(ctx, b, spec);
+        else if (S <= 4) launch_batch<8, 4>(ctx, b, spec);
+        else if (S <= 8) launch_batch<8, 8>(ctx, b, spec);
+        else ok = false;
+    } else if (G == 16) {
+        if (S <= 1) launch_batch<16, 1>(ctx, b, spec);
+        else if (S <= 2) launch_batch<16, 2>(ctx, b, spec);
+        else if (S <= 4) launch_batch<16, 4>(ctx, b, spec);
+        else ok = false;
+    } else {
+        ok = false;
+    }
+    if (!ok) {
+        if (n <= 32) launch_batch<32, 1>(ctx, b, spec);
+        else if (n <= 64) launch_batch<32, 2>(ctx, b, spec);
+        else if (n <= 128) launch_batch<32, 4>(ctx, b, spec);
+        else launch_batch<32, 0>(ctx, b, spec);
+    }
     ++ctx->launches;
     BG_CUDA_OK(ctx, cudaGetLastError());
     return 0;

@@ -286,7 +286,8 @@ BG_HDI void lm_fill_info(double* info, const double* JtJ, int m, double e0, doub
 template <int MM, class Eval>
 BG_HDI int lm_line_search(Eval& ev, int m, const double* xc, double fc, const double* g, double* step,
                           double alpha, double* xnew, double& fnew_sumsq, const Box& box,
-                          const double* dscl, double stepmx, double steptl, LmCounters& cnt) {
+                          const double* dscl, double stepmx, double steptl, LmCounters& cnt,
+                          const double* known_pt, double known_f) {
     bool firstback = true, bad;
     double sln, slp, rln, rmnlmb, lambda, tlmbda = 0.0, plmbda = 0.0, pfpls = 0.0, fpls, t;
 
@@ -313,7 +314,16 @@ BG_HDI int lm_line_search(Eval& ev, int m, const double* xc, double fc, const do
         LM_FOR_REV(i) xnew[i] = xc[i] + lambda * step[i];
         box_project<MM>(xnew, box, m);
 
-        if (!dscl) {
+        // levmar's first probe (lambda = 1) is usually the very point whose rejection started this
+        // search -- p + (pDp - p) == pDp exactly for ordinary steps -- and it evaluates it again
+        // (:260).  Evaluations are deterministic here, so the known value is reused: one sweep over
+        // the samples less, same numbers, and the evaluation is still counted in nfev.
+        bool reuse = known_pt != nullptr && !dscl;
+        if (reuse) LM_FOR(i) reuse = reuse && xnew[i] == known_pt[i];
+        if (reuse) {
+            t = known_f;
+            known_pt = nullptr;
+        } else if (!dscl) {
             t = ev.cost(xnew, bad);
         } else {  // :262-266 scales the point in place and back (not an exact round trip)
             LM_FOR_REV(i) xnew[i] *= dscl[i];
@@ -477,8 +487,11 @@ BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double*
                 const double steptl = 1e3 * sqrt(DBL_EPSILON);
                 tmp = sqrt(p_L2);
                 const double stepmx = 1e3 * ((tmp >= 1.0) ? tmp : 1.0);
+                // the rejected trial point and its (finite or overflowed-sum) cost, for the probe at lambda = 1
+                double trial_pt[MM];
+                LM_FOR(i) trial_pt[i] = pDp[i];
                 const int rc = lm_line_search<MM>(ev, m, p, e_cur, Jte, Dp, alpha, pDp, e_new, box, dscl,
-                                                  stepmx, steptl, cnt);
+                                                  stepmx, steptl, cnt, trial_pt, e_new);
                 if (rc != 0 || !lm_finite(e_new)) use_pg = true;
                 else gprevtaken = 0;
             } else {

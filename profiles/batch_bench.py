@@ -14,5 +14,5 @@ for nfit,nper in ((65536,64),(65536,16),(262144,64)):
     e1.record(stream); ctx.synchronize()
     ms=e0.elapsed_time(e1)/3
     pp,info,ret=b.results()
-    print(os.environ.get("BRDFGPU_LIB","base"), nfit,nper,"%.2f ms  %.3g fits/s  mean iters %.1f nfev %.1f conv %.3f"%(ms,nfit/ms*1e3,info[:,5].mean(),info[:,7].mean(),np.isin(info[:,6].astype(int),(1,2,6)).mean()),flush=True)
+    print(os.environ.get("BRDFGPU_LIB","base"), "G=%s" % os.environ.get("BRDFGPU_BATCH_G","auto"), nfit,nper,"%.2f ms  %.3g fits/s  mean iters %.1f nfev %.1f conv %.3f"%(ms,nfit/ms*1e3,info[:,5].mean(),info[:,7].mean(),np.isin(info[:,6].astype(int),(1,2,6)).mean()),flush=True)
     b.free()

@@ -102,4 +102,7 @@ def test_sharded_global_fit_two_ranks_gloo(tmp_path):
     np.testing.assert_allclose(p, wp, rtol=1e-4)                 # parameters (BASELINE north_star tolerance)
     np.testing.assert_allclose(info[1], winfo[1], rtol=1e-6)     # final cost
     assert int(info[6]) == int(winfo[6])
-    assert r[0][14] == info[8] and r[0][15] == info[7]           # one exchange per evaluation, counted as levmar does
+    # one exchange per Jacobian; one per counted cost evaluation, except that the line search's first
+    # probe reuses the rejected trial point's value (at most once per iteration)
+    assert r[0][14] == info[8]
+    assert info[7] - info[5] <= r[0][15] <= info[7]
