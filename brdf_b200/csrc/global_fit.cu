@@ -1145,7 +1145,11 @@ int global_fit(brdfgpu_ctx* ctx, const brdfgpu_samples* s, double* p, int m, con
     int ret;
     const bool can_persist = ctx->coop && (ctx->nranks == 1 || ctx->peer_attached);
     PersistPlan plan{0, 0, 0};
-    const bool persist = drive == BRDFGPU_DRIVE_PERSISTENT && can_persist && persistent_plan(ctx, s->n, &plan);
+    // Far beyond on-chip residency (> 4e7 samples per GPU, ~1 GB) the kernel-per-evaluation driver is
+    // the faster one: its streaming kernels run at 6-7 TB/s, the launch + ticket round trip (~10 us) no
+    // longer matters next to a 350 us pass (measured crossover between 1e7 and 1e8, profiles/r01_summary.md).
+    const bool host_is_better = s->n > 40000000 && (ctx->nranks == 1 || ctx->nccl_comm != nullptr);
+    const bool persist = drive == BRDFGPU_DRIVE_PERSISTENT && can_persist && !host_is_better && persistent_plan(ctx, s->n, &plan);
     if (persist) {
         GlobalFitSpec spec;
         memset(&spec, 0, sizeof(spec));

@@ -51,7 +51,7 @@ elif what == "micro":
             us = 1e3 * timed(lambda r: ctx.repeat(s, p, 1.0, kind, r), 50 if n < 10**8 else 10)
             out.append("%s %.2f us %.0f GB/s" % ("K2" if kind == 0 else "K3", us, 24.0 * n / us / 1e3))
         line = "n=%d  %s" % (n, "  ".join(out))
-        if n <= 10**7:
+        if n <= 10**8:
             for drive, name in ((A.DRIVE_HOST, "host"), (A.DRIVE_PERSISTENT, "persistent")):
                 ctx.fit_global(s, A.REF_GLOBAL, drive=drive)
                 import time
