@@ -383,6 +383,21 @@ def side_measurements(ctx, torch, stream, A, peak):
                            "traffic_source": "ncu --set full, profiles/r01_ncu_tables.md", "algorithmic_bytes_per_launch": 24.0 * n,
                            "launch_ms": k2["launch_ms"], "k_cost": res["k_cost"],
                            "note": "inputs 2.4 GB >> 126 MB L2, 10 back-to-back launches after 3 warm-ups"}
+    # a COMPLETE fit at 10^8 samples (every Jacobian and trial evaluation streams 2.4 GB from HBM)
+    ctx.fit_global(s, A.REF_GLOBAL)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    ret8, p8, info8 = ctx.fit_global(s, A.REF_GLOBAL)
+    e1.record(stream)
+    ctx.synchronize()
+    st8 = ctx.fit_stats()
+    ms8 = e0.elapsed_time(e1)
+    sweeps8 = st8["jac_passes"] + st8["cost_passes"]
+    out["roofline_hbm"]["complete_fit"] = {
+        "samples": n, "ms": ms8, "iterations": float(info8[5]), "nfev": float(info8[7]), "sweeps": sweeps8,
+        "driver": "persistent kernel" if st8["ctas"] else "one kernel per evaluation (K2 TMA-staged, K3)",
+        "achieved": 24.0 * n * sweeps8 / (ms8 * 1e-3) / 1e9, "unit": "GB/s", "frac": 24.0 * n * sweeps8 / (ms8 * 1e-3) / 1e9 / peak,
+        "sample_evals_per_s": float(info8[7]) * n / (ms8 * 1e-3), "p": [float(v) for v in p8]}
     del s
     # batched mode, BASELINE configs[3]: 65,536 fits x 64 samples
     nfit, nper = 65536, 64
