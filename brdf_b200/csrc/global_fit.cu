@@ -137,59 +137,82 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
                  : "memory");
 }
 
-// Calls body(c0, l0, x0, i0, c1, l1, x1, i1, n_valid) for every group of two sample pairs this CTA
-// owns (tiles blockIdx.x, blockIdx.x + gridDim.x, ...); n_valid in {0, 1, 2} pairs, i* = index of the
-// pair's first sample.
+// The ring: STAGES x {c, L, x} x (2 * THREADS) pairs in shared memory + full/empty mbarriers.
+// `seq` counts the tiles that went through the ring since init (stage = seq % STAGES, mbarrier phase
+// parity = (seq / STAGES) & 1), so a persistent kernel can keep using one ring sweep after sweep.
+template <int THREADS, int STAGES>
+struct TileRing {
+    static constexpr int kPairs = 2 * THREADS;
+    static constexpr unsigned kArrayBytes = kPairs * sizeof(double2), kStageBytes = 3 * kArrayBytes;
+    static constexpr size_t kBytes = (size_t)STAGES * kStageBytes;
+    unsigned ring, bars;  // shared-window addresses
+
+    __device__ __forceinline__ void init(void* ring_smem, unsigned long long* bar_smem /*[2 * STAGES]*/) {
+        ring = smem_addr(ring_smem);
+        bars = smem_addr(bar_smem);
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < STAGES; ++s) {
+                mbar_init(bars + 8 * s, 1);                      // the producer's expect_tx arrive
+                mbar_init(bars + 8 * (STAGES + s), THREADS / 32);  // one arrive per consumer warp
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
+
+    // Calls body(c0, l0, x0, i0, c1, l1, x1, i1, n_valid) for every group of two sample pairs of the
+    // tiles blockIdx.x, blockIdx.x + gridDim.x, ... of the pair range [first_pair, v.n / 2);
+    // n_valid in {0, 1, 2} pairs, i* = index of the pair's first sample.  Returns the new seq.
+    template <class Body>
+    __device__ __forceinline__ long stream(const SampleView& v, long first_pair, long seq, Body&& body) const {
+        const long npair = (v.n >> 1) - first_pair;
+        const long ntiles = (npair + kPairs - 1) / kPairs;
+        const long mine = (long)blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        auto issue = [&](long j) {  // tile number j of this CTA
+            const int s = (int)((seq + j) % STAGES);
+            const long first = ((long)blockIdx.x + j * gridDim.x) * kPairs;
+            const long left = npair - first;
+            const unsigned bytes = (unsigned)((left < kPairs ? left : kPairs) * sizeof(double2));
+            const unsigned full = bars + 8 * s, dst = ring + s * kStageBytes;
+            mbar_expect_tx(full, 3 * bytes);
+            bulk_g2s(dst, v.c + 2 * (first_pair + first), bytes, full);
+            bulk_g2s(dst + kArrayBytes, v.L + 2 * (first_pair + first), bytes, full);
+            bulk_g2s(dst + 2 * kArrayBytes, v.x + 2 * (first_pair + first), bytes, full);
+        };
+        if (threadIdx.x == 0)
+            for (long j = 0; j < mine && j < STAGES; ++j) issue(j);
+        for (long j = 0; j < mine; ++j) {
+            const int s = (int)((seq + j) % STAGES);
+            if (threadIdx.x == 0 && j >= 1 && j - 1 + STAGES < mine) {  // refill the stage drained one tile ago
+                mbar_wait(bars + 8 * (STAGES + (int)((seq + j - 1) % STAGES)), (unsigned)(((seq + j - 1) / STAGES) & 1));
+                issue(j - 1 + STAGES);
+            }
+            mbar_wait(bars + 8 * s, (unsigned)(((seq + j) / STAGES) & 1));
+            const long first = ((long)blockIdx.x + j * gridDim.x) * kPairs;
+            const long left = npair - first;
+            const int here = (int)(left < kPairs ? left : kPairs);
+            const unsigned base = ring + s * kStageBytes;
+            const int a = threadIdx.x, b = threadIdx.x + THREADS;
+            const int valid = (a < here) + (b < here);
+            double2 c0 = make_double2(0, 0), l0 = c0, x0 = c0, c1 = c0, l1 = c0, x1 = c0;
+            if (valid >= 1) { c0 = lds_pair(base, a); l0 = lds_pair(base + kArrayBytes, a); x0 = lds_pair(base + 2 * kArrayBytes, a); }
+            if (valid >= 2) { c1 = lds_pair(base, b); l1 = lds_pair(base + kArrayBytes, b); x1 = lds_pair(base + 2 * kArrayBytes, b); }
+            body(c0, l0, x0, 2 * (first_pair + first + a), c1, l1, x1, 2 * (first_pair + first + b), valid);
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) mbar_arrive(bars + 8 * (STAGES + s));
+        }
+        return seq + mine;
+    }
+};
+
+// one-shot form for the streaming kernels: ring in dynamic shared memory
 template <class Body>
 __device__ __forceinline__ void stream_tiles(const SampleView& v, Body&& body) {
     extern __shared__ __align__(128) unsigned char tile_ring[];
-    __shared__ __align__(8) unsigned long long bars[2 * kTileStages];  // full[stage], empty[stage]
-    const long npair = v.n >> 1;
-    const long ntiles = (npair + kTilePairs - 1) / kTilePairs;
-    const long mine = (long)blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const unsigned ring = smem_addr(tile_ring), bar0 = smem_addr(bars);
-    constexpr unsigned kArrayBytes = kTilePairs * sizeof(double2), kStageBytes = 3 * kArrayBytes;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kTileStages; ++s) {
-            mbar_init(bar0 + 8 * s, 1);                                    // the producer's expect_tx arrive
-            mbar_init(bar0 + 8 * (kTileStages + s), kTileThreads / 32);    // one arrive per consumer warp
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    auto issue = [&](long j) {  // tile number j of this CTA into stage j % kTileStages
-        const int s = (int)(j % kTileStages);
-        const long first = ((long)blockIdx.x + j * gridDim.x) * kTilePairs;
-        const long left = npair - first;
-        const unsigned bytes = (unsigned)((left < kTilePairs ? left : kTilePairs) * sizeof(double2));
-        const unsigned full = bar0 + 8 * s, dst = ring + s * kStageBytes;
-        mbar_expect_tx(full, 3 * bytes);
-        bulk_g2s(dst, v.c + 2 * first, bytes, full);
-        bulk_g2s(dst + kArrayBytes, v.L + 2 * first, bytes, full);
-        bulk_g2s(dst + 2 * kArrayBytes, v.x + 2 * first, bytes, full);
-    };
-    if (threadIdx.x == 0)
-        for (long j = 0; j < mine && j < kTileStages; ++j) issue(j);
-    for (long j = 0; j < mine; ++j) {
-        const int s = (int)(j % kTileStages);
-        if (threadIdx.x == 0 && j >= 1 && j - 1 + kTileStages < mine) {  // refill the stage drained one tile ago
-            mbar_wait(bar0 + 8 * (kTileStages + (int)((j - 1) % kTileStages)), (unsigned)(((j - 1) / kTileStages) & 1));
-            issue(j - 1 + kTileStages);
-        }
-        mbar_wait(bar0 + 8 * s, (unsigned)((j / kTileStages) & 1));
-        const long first = ((long)blockIdx.x + j * gridDim.x) * kTilePairs;
-        const long left = npair - first;
-        const int here = (int)(left < kTilePairs ? left : kTilePairs);
-        const unsigned base = ring + s * kStageBytes;
-        const int a = threadIdx.x, b = threadIdx.x + kTileThreads;
-        const int valid = (a < here) + (b < here);
-        double2 c0 = make_double2(0, 0), l0 = c0, x0 = c0, c1 = c0, l1 = c0, x1 = c0;
-        if (valid >= 1) { c0 = lds_pair(base, a); l0 = lds_pair(base + kArrayBytes, a); x0 = lds_pair(base + 2 * kArrayBytes, a); }
-        if (valid >= 2) { c1 = lds_pair(base, b); l1 = lds_pair(base + kArrayBytes, b); x1 = lds_pair(base + 2 * kArrayBytes, b); }
-        body(c0, l0, x0, 2 * (first + a), c1, l1, x1, 2 * (first + b), valid);
-        __syncwarp();
-        if ((threadIdx.x & 31) == 0) mbar_arrive(bar0 + 8 * (kTileStages + s));
-    }
+    __shared__ __align__(8) unsigned long long bars[2 * kTileStages];
+    TileRing<kTileThreads, kTileStages> ring;
+    ring.init(tile_ring, bars);
+    ring.stream(v, 0, 0, body);
 }
 
 template <int JAC>
@@ -669,6 +692,11 @@ __shared__ double s_cand[kGridCostBatch * 3];  // candidate points of the projec
 __shared__ double s_cand_cost[kGridCostBatch];
 __shared__ int s_cand_bad[kGridCostBatch];
 __shared__ long long s_cyc[6];  // thread 0: cycles in sweeps, exchanges, and the 4 exchange phases
+// TMA ring of the streamed part (sample sets beyond on-chip residency): 3 stages x 48 KB
+using PersistRing = TileRing<kPersistThreads, 3>;
+__shared__ PersistRing s_ring;
+__shared__ __align__(8) unsigned long long s_ring_bars[2 * 3];
+__shared__ long s_ring_seq;  // tiles that went through the ring so far (uniform in the CTA)
 
 // Cross-GPU step, fused into the same kernel: CTA 0 of every rank stores its rank's sums as flagged
 // cells into slot [parity][rank] of EVERY rank's exchange buffer (peer stores over NVLink /
@@ -786,9 +814,20 @@ __device__ __noinline__ void jac_sweep() {
         const double2 c = lds_pair(sc, i), l = lds_pair(sl, i), x = lds_pair(sx, i);
         accumulate_jac_pair<JAC>(q, s_req.q, c, l, x, traw, 2 * (res_first + i), acc);
     }
-    if (s_ctx.stream_first < (s_ctx.v.n >> 1) || (s_ctx.v.n & 1))
-        stream_jac<JAC>(s_ctx.v, q, s_req.q, s_ctx.stream_first, (long)blockIdx.x * kPersistThreads + threadIdx.x,
-                        (long)gridDim.x * kPersistThreads, acc);
+    if (s_ctx.stream_first < (s_ctx.v.n >> 1)) {
+        const SampleView v = s_ctx.v;
+        const long seq = s_ring.stream(v, s_ctx.stream_first, s_ring_seq,
+            [&](double2 c0, double2 l0, double2 x0, long i0, double2 c1, double2 l1, double2 x1, long i1, int valid) {
+                if (valid >= 1) accumulate_jac_pair<JAC>(q, s_req.q, c0, l0, x0, v.traw, i0, acc);
+                if (valid >= 2) accumulate_jac_pair<JAC>(q, s_req.q, c1, l1, x1, v.traw, i1, acc);
+            });
+        __syncthreads();  // everybody has read s_ring_seq
+        if (threadIdx.x == 0) s_ring_seq = seq;
+    }
+    if ((s_ctx.v.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const long j = s_ctx.v.n - 1;
+        accumulate_jac<JAC>(s_req.q, s_ctx.v.c[j], s_ctx.v.L[j], s_ctx.v.x[j], traw, j, acc);
+    }
     all_reduce<NACC>(acc, t0);
 }
 
@@ -815,9 +854,22 @@ __device__ __noinline__ void cost_sweep() {
     const CostPoint q = s_req.pts[0];
     double acc[1];
     acc[0] = resident_cost(q, s_ctx.sc, s_ctx.sl, s_ctx.sx, s_ctx.res_pairs, s_ctx.res_first, s_ctx.v.traw);
-    if (s_ctx.stream_first < (s_ctx.v.n >> 1) || (s_ctx.v.n & 1))
-        stream_cost(s_ctx.v, q, s_ctx.stream_first, (long)blockIdx.x * kPersistThreads + threadIdx.x,
-                    (long)gridDim.x * kPersistThreads, acc);
+    if (s_ctx.stream_first < (s_ctx.v.n >> 1)) {
+        const SampleView v = s_ctx.v;
+        double a0 = 0.0, a1 = 0.0;
+        const long seq = s_ring.stream(v, s_ctx.stream_first, s_ring_seq,
+            [&](double2 c0, double2 l0, double2 x0, long i0, double2 c1, double2 l1, double2 x1, long i1, int valid) {
+                if (valid == 2) accumulate_cost_2pairs(q, c0, l0, x0, i0, c1, l1, x1, i1, v.traw, &a0, &a1);
+                else if (valid == 1) accumulate_cost_pair(q, c0, l0, x0, v.traw, i0, &a0);
+            });
+        acc[0] += a0 + a1;
+        __syncthreads();
+        if (threadIdx.x == 0) s_ring_seq = seq;
+    }
+    if ((s_ctx.v.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const long j = s_ctx.v.n - 1;
+        accumulate_cost(q, s_ctx.v.c[j], s_ctx.v.L[j], s_ctx.v.x[j], s_ctx.v.traw, j, acc);
+    }
     all_reduce<1>(acc, t0);
 }
 
@@ -854,29 +906,30 @@ __device__ __noinline__ void many_sweep() {
 #pragma unroll
     for (int k = 0; k < kGridCostBatch; ++k)
         if (k < cnt) acc[k] = resident_cost(s_req.pts[k], sc, sl, sx, res_pairs, res_first, traw);
-    // streamed remainder: sample-outer (one read of the sample for all candidates)
+    // streamed remainder: sample-outer (one trip through the ring for all candidates)
     const SampleView v = s_ctx.v;
-    if (s_ctx.stream_first < (v.n >> 1) || (v.n & 1)) {
-        const double2* __restrict__ c2 = reinterpret_cast<const double2*>(v.c);
-        const double2* __restrict__ l2 = reinterpret_cast<const double2*>(v.L);
-        const double2* __restrict__ x2 = reinterpret_cast<const double2*>(v.x);
-        const long npair = v.n >> 1, nth = (long)gridDim.x * kPersistThreads;
-        for (long i = s_ctx.stream_first + (long)blockIdx.x * kPersistThreads + threadIdx.x; i < npair; i += nth) {
-            const Pair sp = load_pair(c2, l2, x2, i);
+    if (s_ctx.stream_first < (v.n >> 1)) {
+        const long seq = s_ring.stream(v, s_ctx.stream_first, s_ring_seq,
+            [&](double2 c0, double2 l0, double2 x0, long i0, double2 c1, double2 l1, double2 x1, long i1, int valid) {
 #pragma unroll
-            for (int k = 0; k < kGridCostBatch; ++k) {
-                if (k < cnt) {
-                    const CostPoint q = s_req.pts[k];
-                    accumulate_cost_pair(q, sp.c, sp.l, sp.x, v.traw, 2 * i, &acc[k]);
+                for (int k = 0; k < kGridCostBatch; ++k) {
+                    if (k < cnt) {
+                        const CostPoint q = s_req.pts[k];
+                        double a0 = 0.0, a1 = 0.0;
+                        if (valid == 2) accumulate_cost_2pairs(q, c0, l0, x0, i0, c1, l1, x1, i1, v.traw, &a0, &a1);
+                        else if (valid == 1) accumulate_cost_pair(q, c0, l0, x0, v.traw, i0, &a0);
+                        acc[k] += a0 + a1;
+                    }
                 }
-            }
-        }
-        if ((v.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-            const long j = v.n - 1;
+            });
+        __syncthreads();
+        if (threadIdx.x == 0) s_ring_seq = seq;
+    }
+    if ((v.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const long j = v.n - 1;
 #pragma unroll
-            for (int k = 0; k < kGridCostBatch; ++k)
-                if (k < cnt) accumulate_cost(s_req.pts[k], v.c[j], v.L[j], v.x[j], v.traw, j, &acc[k]);
-        }
+        for (int k = 0; k < kGridCostBatch; ++k)
+            if (k < cnt) accumulate_cost(s_req.pts[k], v.c[j], v.L[j], v.x[j], v.traw, j, &acc[k]);
     }
     all_reduce<kGridCostBatch>(acc, t0);
 }
@@ -987,6 +1040,9 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_persistent_fit(SampleVie
     const int cap = (int)((resident_pairs + gridDim.x - 1) / gridDim.x);
     const int mine = (int)(last - first);
     double2 *sc = smem_dyn, *sl = smem_dyn + cap, *sx = smem_dyn + 2 * cap;
+    // the TMA ring of the streamed part sits behind the resident slice (128-byte aligned)
+    const size_t ring_off = (((size_t)3 * cap * sizeof(double2)) + 127) & ~(size_t)127;
+    if (resident_pairs < (v.n >> 1)) s_ring.init(reinterpret_cast<unsigned char*>(smem_dyn) + ring_off, s_ring_bars);
     {
         const double2* __restrict__ c2 = reinterpret_cast<const double2*>(v.c);
         const double2* __restrict__ l2 = reinterpret_cast<const double2*>(v.L);
@@ -1003,7 +1059,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_persistent_fit(SampleVie
         s_ctx.sx = (unsigned)__cvta_generic_to_shared(sx);
         s_ctx.res_pairs = mine; s_ctx.res_first = first; s_ctx.stream_first = resident_pairs;
         s_ctx.cells = cells; s_ctx.peer = peer; s_ctx.abort_flag = &out->aborted;
-        s_epoch = 0u; s_peer_epoch = peer.epoch;
+        s_epoch = 0u; s_peer_epoch = peer.epoch; s_ring_seq = 0;
         for (int i = 0; i < 6; ++i) s_cyc[i] = 0;
     }
     __syncthreads();
@@ -1071,13 +1127,20 @@ static bool persistent_plan(brdfgpu_ctx* ctx, long n, PersistPlan* plan) {
     long cap = ctx->sm_count < kMaxPersistBlocks ? ctx->sm_count : kMaxPersistBlocks;
     if (grid < 1) grid = 1;
     if (grid > cap) grid = cap;
-    const long cap_pairs = ctx->persist_smem_max / (3 * (long)sizeof(double2));
-    long resident = npair < grid * cap_pairs ? npair : grid * cap_pairs;
+    long cap_pairs = ctx->persist_smem_max / (3 * (long)sizeof(double2));
+    long resident = npair;
+    size_t ring_bytes = 0;
+    if (npair > grid * cap_pairs) {  // not everything fits on chip: part of the shared memory becomes the TMA ring
+        ring_bytes = PersistRing::kBytes + 128;
+        cap_pairs = ((long)ctx->persist_smem_max - (long)ring_bytes) / (3 * (long)sizeof(double2));
+        if (cap_pairs < 0) return false;
+        resident = grid * cap_pairs;
+    }
     // a slice is ceil(resident / grid) pairs at most
     while (resident > 0 && (resident + grid - 1) / grid > cap_pairs) --resident;
     plan->grid = (int)grid;
     plan->resident_pairs = resident;
-    plan->smem = (size_t)((resident + grid - 1) / grid) * 3 * sizeof(double2);
+    plan->smem = (size_t)((resident + grid - 1) / grid) * 3 * sizeof(double2) + ring_bytes;
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persistent_fit, kPersistThreads, plan->smem) != cudaSuccess ||
         per_sm < 1)
