@@ -49,6 +49,11 @@ extern "C" int brdfgpu_create(int device, brdfgpu_ctx** out) {
     }
     brdfgpu_ctx* ctx = new brdfgpu_ctx;
     ctx->device = device;
+    // The fit kernels keep ~1 KB of per-thread stack; without this flag the driver shrinks the
+    // local-memory pool again after every such launch and re-grows it for the next one (a
+    // synchronising reallocation of tens of milliseconds).  Only takes effect if the primary
+    // context is not active yet; harmless otherwise.
+    if (cudaSetDeviceFlags(cudaDeviceLmemResizeToMax) != cudaSuccess) cudaGetLastError();
     e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->coop, cudaDevAttrCooperativeLaunch, device);

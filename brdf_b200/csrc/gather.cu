@@ -531,7 +531,33 @@ extern "C" int brdfgpu_gather_resident(brdfgpu_ctx* ctx, const brdfgpu_scene* sc
     return rc;
 }
 
-// CBRDFdata::CalcBRDFEquation (brdfdata.cpp:1188-1227)
+// resident global-fit sample set of one colour channel from a finished gather
+static int samples_from_gather(brdfgpu_ctx* ctx, const brdfgpu_scene* sc, const GatherDev& g, int model, int channel,
+                               brdfgpu_samples** out) {
+    const long ns = g.nfit * sc->nimg;
+    const size_t nb = sizeof(double) * (size_t)ns;
+    const double* t = model == 1 ? g.thetaDash : g.theta;
+    brdfgpu_samples* s = nullptr;
+    if (samples_alloc(ctx, ns, model, &s) != 0) return BRDFGPU_LM_ERROR;
+    cudaError_t e = cudaSuccess;
+    if (ns > 0) {
+        e = cudaMemcpyAsync(s->c, g.phi, nb, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(s->traw, t, nb, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(s->x, g.I + (size_t)channel * ns, nb, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e == cudaSuccess && samples_prepare(ctx, s) != 0) e = cudaErrorUnknown;
+    }
+    if (e != cudaSuccess) {
+        brdfgpu_samples_free(ctx, s);
+        set_error(ctx, std::string("gather -> samples: ") + cudaGetErrorString(e));
+        return BRDFGPU_LM_ERROR;
+    }
+    *out = s;
+    return 0;
+}
+
+// CBRDFdata::CalcBRDFEquation (brdfdata.cpp:1188-1227): ONE gather, then the fits of all three colour
+// channels as one batch of 3 x nfit problems (fit ch * nfit + f = face f, channel ch: the B, G, R
+// intensity blocks of the gather are already laid out that way) in a single launch.
 extern "C" long brdfgpu_calc_brdf_equation(brdfgpu_ctx* ctx, const brdfgpu_scene* sc, const double* cam, int model,
                                            double* brdf_surfaces) {
     ctx = ctx_or_default(ctx);
@@ -539,44 +565,66 @@ extern "C" long brdfgpu_calc_brdf_equation(brdfgpu_ctx* ctx, const brdfgpu_scene
     static const double p0[3] = {0.5, 1.0, 1.0}, lb[3] = {0, 0, 0}, ub[3] = {100, 100, 100};
     static const double opts[5] = {1E-03, 1E-15, 1E-15, 1E-20, 1E-06};
     GatherDev g;
-    if (gather_device(ctx, sc, cam, 1, false, &g) != 0) {
+    if (gather_device(ctx, sc, cam, 1, true, &g) != 0) {
         g.release();
         return BRDFGPU_LM_ERROR;
     }
     const long nfit = g.nfit;
-    std::vector<int> faces(nfit);
-    cudaMemcpyAsync(faces.data(), g.fit_face, sizeof(int) * nfit, cudaMemcpyDeviceToHost, ctx->stream);
-    cudaStreamSynchronize(ctx->stream);
-    g.release();
-    std::vector<double> p(3 * (size_t)nfit);
-    for (int ch = 0; ch < 3; ++ch) {  // brdfdata.cpp:1205: B, G, R
-        brdfgpu_batch* b = nullptr;
-        long n2 = 0;
-        if (brdfgpu_gather_resident(ctx, sc, cam, 1, model, ch, nullptr, &b, &n2) != 0 || n2 != nfit) return BRDFGPU_LM_ERROR;
-        int rc = 0;
-        if (nfit > 0) {
-            rc = brdfgpu_batch_fit(ctx, b, p0, lb, ub, 100, opts, BRDFGPU_JAC_FD);
-            if (rc == 0) rc = brdfgpu_batch_results(ctx, b, p.data(), nullptr, nullptr);
-        }
-        brdfgpu_batch_free(ctx, b);
-        if (rc != 0) return BRDFGPU_LM_ERROR;
-        for (long f = 0; f < nfit; ++f)  // SaveValuesToSurface, brdfdata.cpp:368-377
-            for (int j = 0; j < 3; ++j) brdf_surfaces[((size_t)faces[f] * 3 + ch) * 3 + j] = p[3 * f + j];
+    if (nfit == 0) {
+        g.release();
+        return 0;
     }
+    const long ns = nfit * sc->nimg;
+    const size_t nb = sizeof(double) * (size_t)ns;
+    const double* t = model == 1 ? g.thetaDash : g.theta;
+    std::vector<int> faces(nfit);
+    std::vector<double> p(9 * (size_t)nfit);
+    brdfgpu_batch* b = nullptr;
+    int rc = batch_alloc(ctx, 3 * nfit, sc->nimg, model, &b);
+    cudaError_t e = cudaSuccess;
+    if (rc == 0) {
+        e = cudaMemcpyAsync(faces.data(), g.fit_face, sizeof(int) * nfit, cudaMemcpyDeviceToHost, ctx->stream);
+        for (int ch = 0; ch < 3 && e == cudaSuccess; ++ch) {
+            e = cudaMemcpyAsync(b->c + (size_t)ch * ns, g.phi, nb, cudaMemcpyDeviceToDevice, ctx->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(b->traw + (size_t)ch * ns, t, nb, cudaMemcpyDeviceToDevice, ctx->stream);
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(b->x, g.I, 3 * nb, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e != cudaSuccess) rc = BRDFGPU_LM_ERROR;
+        if (rc == 0) rc = batch_prepare(ctx, b);
+        if (rc == 0) rc = brdfgpu_batch_fit(ctx, b, p0, lb, ub, 100, opts, BRDFGPU_JAC_FD);
+        if (rc == 0) rc = brdfgpu_batch_results(ctx, b, p.data(), nullptr, nullptr);
+    }
+    if (b) brdfgpu_batch_free(ctx, b);
+    g.release();
+    if (rc != 0) {
+        if (e != cudaSuccess) set_error(ctx, std::string("calc_brdf_equation: ") + cudaGetErrorString(e));
+        return BRDFGPU_LM_ERROR;
+    }
+    for (int ch = 0; ch < 3; ++ch)          // brdfdata.cpp:1205: B, G, R
+        for (long f = 0; f < nfit; ++f)     // SaveValuesToSurface, brdfdata.cpp:368-377
+            for (int j = 0; j < 3; ++j) brdf_surfaces[((size_t)faces[f] * 3 + ch) * 3 + j] = p[3 * ((size_t)ch * nfit + f) + j];
     return nfit;
 }
 
-// CBRDFdata::CalcBRDFEquation_SingleBRDF (brdfdata.cpp:1138-1186)
+// CBRDFdata::CalcBRDFEquation_SingleBRDF (brdfdata.cpp:1138-1186): one gather, one global fit per channel
 extern "C" long brdfgpu_calc_brdf_equation_single(brdfgpu_ctx* ctx, const brdfgpu_scene* sc, const double* cam, int model,
                                                   double* single_brdf, double* info, int* ret) {
     ctx = ctx_or_default(ctx);
     if (!ctx || !sc || !cam || !single_brdf) return BRDFGPU_LM_ERROR;
     static const double lb[3] = {0, 0, 0}, ub[3] = {100, 100, 100};
     static const double opts[5] = {1E-03, 1E-15, 1E-10, 1E-50, 1.0};
-    long nfit = 0;
+    GatherDev g;
+    if (gather_device(ctx, sc, cam, 1, true, &g) != 0) {
+        g.release();
+        return BRDFGPU_LM_ERROR;
+    }
+    const long nfit = g.nfit;
     for (int ch = 0; ch < 3; ++ch) {
         brdfgpu_samples* s = nullptr;
-        if (brdfgpu_gather_resident(ctx, sc, cam, 1, model, ch, &s, nullptr, &nfit) != 0) return BRDFGPU_LM_ERROR;
+        if (samples_from_gather(ctx, sc, g, model, ch, &s) != 0) {
+            g.release();
+            return BRDFGPU_LM_ERROR;
+        }
         double p[3] = {0.0, 0.0, 0.0}, inf[10] = {0};
         const int r = brdfgpu_fit_global(ctx, s, p, 3, lb, ub, nullptr, 2000, opts, inf, nullptr, BRDFGPU_DRIVE_PERSISTENT,
                                          BRDFGPU_JAC_FD);
@@ -586,5 +634,6 @@ extern "C" long brdfgpu_calc_brdf_equation_single(brdfgpu_ctx* ctx, const brdfgp
             for (int j = 0; j < 10; ++j) info[ch * 10 + j] = inf[j];
         if (ret) ret[ch] = r;
     }
+    g.release();
     return nfit;
 }
