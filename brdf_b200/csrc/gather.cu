@@ -18,6 +18,24 @@
 
 #include "common.cuh"
 
+// BRDFGPU_TRACE=1: wall-clock milestones of the scene drivers on stderr (host-side diagnosis)
+#include <chrono>
+#include <cstdlib>
+namespace {
+struct Trace {
+    const char* what;
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    explicit Trace(const char* w) : what(w), on(getenv("BRDFGPU_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* step) {
+        if (!on) return;
+        const auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[brdfgpu trace] %s: %s +%.2f ms\n", what, step, std::chrono::duration<double, std::milli>(t - t0).count());
+        t0 = t;
+    }
+};
+}  // namespace
+
 struct brdfgpu_scene {
     int nV = 0, nF = 0, nimg = 0, W = 0, H = 0;
     double* V = nullptr;           // nV x 3
@@ -277,6 +295,7 @@ static int gather_device(brdfgpu_ctx* ctx, const brdfgpu_scene* sc, const double
     }
     const long total = (long)ncam * sc->nF, npix = (long)ncam * sc->W * sc->H;
     const int nblocks = (int)((total + kScanThreads - 1) / kScanThreads);
+    Trace tr("gather_device");
     g->ncam = ncam;
     BG_CUDA_OK(ctx, cudaMalloc(&g->cams, sizeof(double) * 16 * ncam));
     BG_CUDA_OK(ctx, cudaMalloc(&g->pix, sizeof(int) * total));
@@ -287,6 +306,7 @@ static int gather_device(brdfgpu_ctx* ctx, const brdfgpu_scene* sc, const double
     BG_CUDA_OK(ctx, cudaMalloc(&g->cam_first, sizeof(int) * (ncam + 1)));
     BG_CUDA_OK(ctx, cudaMalloc(&g->block_sums, sizeof(int) * (nblocks + 1)));
     BG_CUDA_OK(ctx, cudaMemcpyAsync(g->cams, cams_host, sizeof(double) * 16 * ncam, cudaMemcpyHostToDevice, ctx->stream));
+    tr.mark("8 cudaMalloc + H2D of the cameras");
 
     k_fill_int<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(g->maps, npix, -1);
     k_project<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(sc->V, sc->F, sc->nF, g->cams, ncam, sc->W, sc->H,
@@ -301,6 +321,7 @@ static int gather_device(brdfgpu_ctx* ctx, const brdfgpu_scene* sc, const double
     BG_CUDA_OK(ctx, cudaMemcpyAsync(g->h_cam_first.data(), g->cam_first, sizeof(int) * (ncam + 1), cudaMemcpyDeviceToHost,
                                      ctx->stream));
     BG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    tr.mark("project + compaction kernels, sync");
     g->nfit = g->h_cam_first[ncam];
     if (!want_samples || g->nfit == 0) return 0;
 
@@ -314,6 +335,7 @@ static int gather_device(brdfgpu_ctx* ctx, const brdfgpu_scene* sc, const double
         sc->H, ns, g->phi, g->thetaDash, g->theta, g->I);
     ++ctx->launches;
     BG_CUDA_OK(ctx, cudaGetLastError());
+    tr.mark("4 cudaMalloc + sample kernel launch");
     return 0;
 }
 
@@ -619,21 +641,26 @@ extern "C" long brdfgpu_calc_brdf_equation_single(brdfgpu_ctx* ctx, const brdfgp
         return BRDFGPU_LM_ERROR;
     }
     const long nfit = g.nfit;
+    Trace tr("calc_brdf_equation_single");
     for (int ch = 0; ch < 3; ++ch) {
         brdfgpu_samples* s = nullptr;
         if (samples_from_gather(ctx, sc, g, model, ch, &s) != 0) {
             g.release();
             return BRDFGPU_LM_ERROR;
         }
+        tr.mark("samples from gather (4 cudaMalloc, 3 D2D, log pass)");
         double p[3] = {0.0, 0.0, 0.0}, inf[10] = {0};
         const int r = brdfgpu_fit_global(ctx, s, p, 3, lb, ub, nullptr, 2000, opts, inf, nullptr, BRDFGPU_DRIVE_PERSISTENT,
                                          BRDFGPU_JAC_FD);
+        tr.mark("global fit");
         brdfgpu_samples_free(ctx, s);
+        tr.mark("samples free");
         for (int j = 0; j < 3; ++j) single_brdf[ch * 3 + j] = p[j];
         if (info)
             for (int j = 0; j < 10; ++j) info[ch * 10 + j] = inf[j];
         if (ret) ret[ch] = r;
     }
     g.release();
+    tr.mark("gather release (12 cudaFree)");
     return nfit;
 }
