@@ -42,7 +42,6 @@ struct PassParams {
     double g0, g1;           // ((kd+d0)-kd)/d0 [central: ((kd+d0)-(kd-d0))*0.5/d0], same for ks; analytic: 1
     double a_hi, a_lo;       // coef(n_hi)*ks/d2 and coef(n)*ks/d2 [central: coef(n_lo)*ks*0.5/d2]
     double dcoef;            // d coef / d n (analytic, Phong: pi/2)
-    double l_lim;            // fast path iff |L| <= l_lim  (700 / max |exponent| of the pass)
     // literal difference data for the careful path: p_j + d_j, p_j - d_j, 1/d_j (0.5/d_j central)
     double kd_hi, ks_hi, kd_lo, ks_lo, coef_hi, coef_lo, inv[3];
     int model;
@@ -70,36 +69,27 @@ BG_HDI PassParams make_pass_params(const double* p, int model, double delta, int
     q.kd_lo = p[0] - d[0]; q.ks_lo = p[1] - d[1]; q.n_lo = p[2] - d[2];
     q.coef_hi = model_coef(model, q.n_hi);
     q.coef_lo = model_coef(model, q.n_lo);
-    double emax = lm_abs(q.n);
-    bool plain = lm_finite(q.n) && q.n != 0.0;
     if (jac_mode == kJacForward) {
         q.g0 = (q.kd_hi - q.kd) * q.inv[0];
         q.g1 = (q.ks_hi - q.ks) * q.inv[1];
         q.a_hi = (q.coef_hi * q.ks) * q.inv[2];
         q.a_lo = q.cks * q.inv[2];
-        plain = plain && lm_finite(q.n_hi) && q.n_hi != 0.0;
-        if (lm_abs(q.n_hi) > emax) emax = lm_abs(q.n_hi);
         q.n_lo = q.n;
     } else if (jac_mode == kJacCentral) {
         q.g0 = (q.kd_hi - q.kd_lo) * q.inv[0];
         q.g1 = (q.ks_hi - q.ks_lo) * q.inv[1];
         q.a_hi = (q.coef_hi * q.ks) * q.inv[2];
         q.a_lo = (q.coef_lo * q.ks) * q.inv[2];
-        plain = plain && lm_finite(q.n_hi) && q.n_hi != 0.0 && lm_finite(q.n_lo) && q.n_lo != 0.0;
-        if (lm_abs(q.n_hi) > emax) emax = lm_abs(q.n_hi);
-        if (lm_abs(q.n_lo) > emax) emax = lm_abs(q.n_lo);
     } else {
         q.g0 = 1.0; q.g1 = 1.0; q.a_hi = 0.0; q.a_lo = 0.0;
         q.n_hi = q.n_lo = q.n;
     }
-    // zero or non-finite exponents send every sample down the careful path (l_lim < 0 never passes)
-    q.l_lim = plain ? kFastExpLimit / emax : -1.0;
     return q;
 }
 
-// The four numbers a trial-point (cost-only) evaluation needs.
+// The three numbers a trial-point (cost-only) evaluation needs.
 struct CostPoint {
-    double kd, cks, n, l_lim;
+    double kd, cks, n;
 };
 
 BG_HDI CostPoint make_cost_point(const double* p, int model) {
@@ -107,7 +97,6 @@ BG_HDI CostPoint make_cost_point(const double* p, int model) {
     q.kd = p[0];
     q.n = p[2];
     q.cks = model_coef(model, p[2]) * p[1];
-    q.l_lim = (lm_finite(q.n) && q.n != 0.0) ? kFastExpLimit / lm_abs(q.n) : -1.0;
     return q;
 }
 
@@ -186,9 +175,11 @@ __device__ __forceinline__ void accumulate_normal(double j0, double j1, double j
     acc[ESQ] = __fma_rn(e, e, acc[ESQ]);
 }
 
-// Does this sample need libm semantics?  (also catches the NaN flag, t == 0, t == inf)
-template <class Q>
-__device__ __forceinline__ bool needs_care(const Q& q, double L) { return !(fabs(L) <= q.l_lim); }
+// Does an exponential with argument y = exponent * log(t) need libm semantics?  exp_core is valid for
+// |y| <= 700; everything else -- results that under/overflow, the NaN flag of t < 0, t == 0 or inf
+// (y = +-inf, or NaN against a zero exponent), non-finite exponents -- goes through pow().
+// A zero exponent with an ordinary t gives y = 0 and exp_core(0) == 1 == pow(t, 0) exactly.
+__device__ __forceinline__ bool needs_care(double y) { return !(fabs(y) <= kFastExpLimit); }
 
 // careful path of one Jacobian sample: literal levmar differences of full model values
 template <int JAC>
@@ -231,11 +222,12 @@ __device__ __forceinline__ void accumulate_jac_n(const PassParams& q, const Pass
     double y[NE * N], pw[NE * N];
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-        slow |= needs_care(q, L[k]);
         y[k] = q.n * L[k];
         if (NE >= 2) y[N + k] = q.n_hi * L[k];
         if (NE >= 3) y[2 * N + k] = q.n_lo * L[k];
     }
+#pragma unroll
+    for (int k = 0; k < NE * N; ++k) slow |= needs_care(y[k]);
     exp_core_n<NE * N>(y, pw);
 #pragma unroll
     for (int k = 0; k < N; ++k) {
@@ -249,7 +241,10 @@ __device__ __forceinline__ void accumulate_jac_n(const PassParams& q, const Pass
     if (slow) {
 #pragma unroll
         for (int k = 0; k < N; ++k) {
-            if (needs_care(q, L[k])) {
+            bool mine = needs_care(y[k]);
+            if (NE >= 2) mine |= needs_care(y[N + k]);
+            if (NE >= 3) mine |= needs_care(y[2 * N + k]);
+            if (mine) {
                 double o[4];
                 jac_terms_careful<JAC>(cold, c[k], traw[idx[k]], x[k], o);
                 e[k] = o[0]; j0[k] = o[1]; j1[k] = o[2]; j2[k] = o[3];
@@ -280,8 +275,8 @@ __device__ __forceinline__ void residuals_n(const Q& q, const double* c, const d
     double y[N], pw[N];
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-        slow |= needs_care(q, L[k]);
         y[k] = q.n * L[k];
+        slow |= needs_care(y[k]);
     }
     exp_core_n<N>(y, pw);
 #pragma unroll
@@ -289,7 +284,7 @@ __device__ __forceinline__ void residuals_n(const Q& q, const double* c, const d
     if (slow) {
 #pragma unroll
         for (int k = 0; k < N; ++k)
-            if (needs_care(q, L[k])) e[k] = residual_careful(q, c[k], traw[idx[k]], x[k]);
+            if (needs_care(y[k])) e[k] = residual_careful(q, c[k], traw[idx[k]], x[k]);
     }
 }
 

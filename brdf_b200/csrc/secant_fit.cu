@@ -28,16 +28,18 @@ struct SecantState {
 template <int JAC>
 __device__ __forceinline__ void model_row(const PassParams& q, double c, double L, double x, const double* __restrict__ traw,
                                           long i, double& hx, double& r0, double& r1, double& r2) {
-    if (needs_care(q, L)) {
+    constexpr int NE = (JAC == kJacCentral) ? 3 : 2;
+    double y[NE], pw[NE];
+    y[0] = q.n * L; y[1] = q.n_hi * L;
+    if (NE == 3) y[2] = q.n_lo * L;
+    bool slow = needs_care(y[0]) || needs_care(y[1]);
+    if (NE == 3) slow = slow || needs_care(y[2]);
+    if (slow) {
         double o[4];
         jac_terms_careful<JAC>(q, c, traw[i], x, o);
         hx = x - o[0]; r0 = o[1]; r1 = o[2]; r2 = o[3];
         return;
     }
-    constexpr int NE = (JAC == kJacCentral) ? 3 : 2;
-    double y[NE], pw[NE];
-    y[0] = q.n * L; y[1] = q.n_hi * L;
-    if (NE == 3) y[2] = q.n_lo * L;
     exp_core_n<NE>(y, pw);
     hx = __fma_rn(q.kd, c, q.cks * pw[0]);
     r0 = q.g0 * c;
