@@ -257,3 +257,22 @@ def test_full_size_properties(ctx):
     # survey probe of the reference on this exact generator: cost 10.4517173244 --
     # generator details (noise stream) differ from that probe, so only the scale is asserted
     assert 5.0 < b[2][1] < 20.0
+
+
+@pytest.mark.parametrize("drive", [A.DRIVE_PERSISTENT, A.DRIVE_HOST], ids=["persistent", "host"])
+def test_diagonal_scaling_matches_levmar(ctx, drive):
+    """dscl (lmbc_core.c:360-366, 536-570): scaled variables and bounds inside, caller coordinates outside,
+    covariance rescaled; both drivers, incl. the batched projected-gradient walk of the persistent kernel."""
+    c, td, th, x = synth.samples(20000, seed=4242)
+    angles = np.concatenate([c, td, th])
+    dscl = (0.5, 2.0, 10.0)
+    for pr in (O.REF_PERFACE, O.REF_GLOBAL):
+        want = O.levmar_bc_dif(O.oracle(), "oracle_", O.brdf_callback(), pr["p0"], x, pr["lb"], pr["ub"], pr["itmax"], pr["opts"],
+                               adata=O.make_extra(angles, 1), dscl=dscl, want_covar=True)
+        s = ctx.upload(c, td, x, 1)
+        ret, p, info, covar = ctx.fit_global(s, dict(pr), drive=drive, dscl=dscl, want_covar=True)
+        s.free()
+        assert (ret >= 0) == (want[0] >= 0)
+        np.testing.assert_allclose(p, want[1], rtol=PAR_RTOL)
+        np.testing.assert_allclose(info[1], want[2][1], rtol=COST_RTOL)
+        np.testing.assert_allclose(covar, want[3], rtol=5e-3, atol=1e-14)
