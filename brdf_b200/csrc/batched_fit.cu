@@ -33,8 +33,18 @@ struct BatchSpec {
 // G lanes per fit, S samples per lane held in registers (S == 0: samples re-read from memory)
 template <int G, int S>
 struct GroupEval {
-    static constexpr int kCostBatch = 1;
+    // Candidates of the projected-gradient walk evaluated together (lm_engine.cuh PgBatch).  Measured
+    // on B200 for 65 536 x 64: 1 -> 16.8 ms, 2 -> 18.7 ms, 4 -> 19.8 ms, 8 -> 26.2 ms: with no exchange
+    // to amortise, the discarded speculative evaluations cost more than the extra ILP gains, so the
+    // per-fit kernel walks one candidate at a time (the persistent global fit uses 8).
+#ifndef BG_BATCH_PG
+#define BG_BATCH_PG 1
+#endif
+    static constexpr int kCostBatch = (S > 0) ? BG_BATCH_PG : 1;
+    static constexpr int KB = kCostBatch;
     static constexpr int SR = S > 0 ? S : 1;
+    double* s_pts;   // shared memory of this lane group: KB x 3 candidate points
+    double* s_out;   // KB costs + KB "some residual non-finite" flags
     double c[SR], L[SR], x[SR];
     const double *gc, *gL, *gx, *traw;  // this fit's rows
     int nper, lane, model, jkind;
@@ -101,6 +111,67 @@ struct GroupEval {
         if (!lm_finite(esq)) bad = group_sum(nbad) != 0.0;  // uniform within the group
         return esq;
     }
+
+    __device__ __forceinline__ double* batch_points() const { return s_pts; }
+    __device__ __forceinline__ double batch_cost(int k) const { return s_out[k]; }
+    __device__ __forceinline__ bool batch_bad(int k) const { return s_out[KB + k] != 0.0; }
+
+    // up to KB trial points at once; the engine wrote them (every lane the same values) into s_pts
+    __device__ __forceinline__ void cost_many(int cnt, const double* /*dscl: batched fits are unscaled*/, int) const {
+        __syncwarp(mask);
+        CostPoint q[KB];
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+            const int kk = k < cnt ? k : 0;
+            const double pt[3] = {s_pts[3 * kk], s_pts[3 * kk + 1], s_pts[3 * kk + 2]};
+            q[k] = make_cost_point(pt, model);
+        }
+        double esq[KB], nbad[KB];
+#pragma unroll
+        for (int k = 0; k < KB; ++k) esq[k] = nbad[k] = 0.0;
+#pragma unroll
+        for (int s = 0; s < SR; ++s) {
+            const int idx = s * G + lane;
+            if (idx < nper) {
+                double y[KB], pw[KB];
+                bool slow = false;
+#pragma unroll
+                for (int k = 0; k < KB; ++k) {
+                    y[k] = q[k].n * L[s];
+                    slow |= needs_care(y[k]);
+                }
+                exp_core_n<KB>(y, pw);
+#pragma unroll
+                for (int k = 0; k < KB; ++k) {
+                    double e = x[s] - __fma_rn(q[k].kd, c[s], q[k].cks * pw[k]);
+                    if (slow && needs_care(y[k])) e = residual_careful(q[k], c[s], traw[idx], x[s]);
+                    esq[k] = __fma_rn(e, e, esq[k]);
+                    nbad[k] += lm_finite(e) ? 0.0 : 1.0;
+                }
+            }
+        }
+#pragma unroll
+        for (int off = G / 2; off; off >>= 1) {
+#pragma unroll
+            for (int k = 0; k < KB; ++k) esq[k] += __shfl_xor_sync(mask, esq[k], off, G);
+        }
+        bool any_bad = false;
+#pragma unroll
+        for (int k = 0; k < KB; ++k) any_bad |= !lm_finite(esq[k]);
+        if (any_bad) {  // uniform within the group
+#pragma unroll
+            for (int k = 0; k < KB; ++k) nbad[k] = group_sum(nbad[k]);
+        }
+        __syncwarp(mask);
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < KB; ++k) {
+                s_out[k] = esq[k];
+                s_out[KB + k] = (!lm_finite(esq[k]) && nbad[k] != 0.0) ? 1.0 : 0.0;
+            }
+        }
+        __syncwarp(mask);
+    }
 };
 
 template <int G, int S>
@@ -114,7 +185,11 @@ __global__ void __launch_bounds__(kBatchThreads, BG_BATCH_MIN_BLOCKS(G)) k_batch
     const int lane = threadIdx.x % G;
     const long base = fit * nper;
 
+    constexpr int kGroups = kBatchThreads / G;
+    __shared__ double s_scratch[kGroups * (3 + 2) * (GroupEval<G, S>::kCostBatch)];
     GroupEval<G, S> ev;
+    ev.s_pts = s_scratch + (threadIdx.x / G) * 5 * GroupEval<G, S>::kCostBatch;
+    ev.s_out = ev.s_pts + 3 * GroupEval<G, S>::kCostBatch;
     ev.gc = c + base; ev.gL = L + base; ev.gx = x + base; ev.traw = traw + base;
     ev.nper = nper; ev.lane = lane; ev.model = model; ev.jkind = spec.jkind; ev.delta = spec.delta;
     ev.mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
