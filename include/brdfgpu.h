@@ -293,6 +293,11 @@ int brdfgpu_lm_bc_reduced(brdfgpu_reduced_jac_t jac_cb, brdfgpu_reduced_cost_t c
 int brdfgpu_lm_unc_reduced(brdfgpu_reduced_jac_t jac_cb, brdfgpu_reduced_cost_t cost_cb, void *user,
                            double *p, int m, long n, int itmax, const double *opts, double *info,
                            double *covar);
+/* brdfgpu_lm_bc_reduced (without dscl / covar) driven through the resumable state-machine form of the
+ * control loop that the batched kernel runs, one fit per thread (csrc/lm_machine.cuh). */
+int brdfgpu_lm_bc_machine(brdfgpu_reduced_jac_t jac_cb, brdfgpu_reduced_cost_t cost_cb, void *user,
+                          double *p, int m, long n, const double *lb, const double *ub, int itmax,
+                          const double *opts, double *info);
 /* Test hook: on != 0 makes brdfgpu_lm_bc_reduced hand the projected-gradient candidates to the
  * evaluator eight at a time, the way the persistent fit kernel receives them (results must not
  * change).  Returns the previous setting; after a batched run, the largest batch that occurred. */
