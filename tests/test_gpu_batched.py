@@ -122,3 +122,17 @@ def test_full_size_batch_properties(ctx):
     assert np.array_equal(p2, p[1000:2000]) and np.array_equal(info2, info[1000:2000])
     good = np.isin(info[:, 6].astype(int), CONVERGED)
     assert good.mean() > 0.9
+
+
+def test_lockstep_kernel_matches_warp_per_fit(ctx, monkeypatch):
+    """The opt-in thread-per-fit kernel (resumable state machine, csrc/lm_machine.cuh) must give what the
+    default warp-per-fit kernel gives: same stop reasons, parameters to the parity tolerance."""
+    c, td, th, x, _ = synth.batched(3000, 16, seed=77)
+    base = ctx.solve_equation_batch(c, td, th, x, A.BLINN_PHONG)
+    monkeypatch.setenv("BRDFGPU_BATCH_LOCKSTEP", "128")
+    lock = ctx.solve_equation_batch(c, td, th, x, A.BLINN_PHONG)
+    both = np.isin(base[1][:, 6].astype(int), CONVERGED) & np.isin(lock[1][:, 6].astype(int), CONVERGED)
+    assert both.mean() > 0.8
+    close = np.isclose(base[0][both], lock[0][both], rtol=PAR_RTOL, atol=1e-9).all(axis=1)
+    assert close.mean() > 0.98, close.mean()
+    assert np.array_equal(base[2] >= 0, lock[2] >= 0)
