@@ -261,6 +261,25 @@ def run_gpu_arm(args):
     extra = {}
     if rank == 0 and world == 1 and not args.quick:
         extra = side_measurements(ctx, torch, stream, A, peak)
+    if world > 1 and not args.quick:
+        # batched mode on N GPUs (BASELINE configs[3]): independent fits, sharded by fit id, no communication
+        def batched_sharded(nfit_total):
+            lo, hi = rank * nfit_total // world, (rank + 1) * nfit_total // world
+            b = ctx.batch_synth(hi - lo, 64, seed=2026, first_fit=lo)
+            b.fit(A.REF_PERFACE)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(3):
+                b.fit(A.REF_PERFACE)
+            e1.record(stream)
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1) / 3], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            b.free()
+            return {"nfit_total": nfit_total, "samples_per_fit": 64, "ms": float(t.item()), "fits_per_s": nfit_total / (float(t.item()) * 1e-3)}
+        extra["batched"] = {"metric": "batched BRDF fits/sec", "preset": "REF_PERFACE", "n_gpus": world,
+                            "strong_65536_total": batched_sharded(65536), "weak_65536_per_gpu": batched_sharded(65536 * world)}
 
     # ---- e2e: the levmar-signature call with pinned host buffers ----
     e2e = None
