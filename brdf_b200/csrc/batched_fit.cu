@@ -42,6 +42,7 @@ struct GroupEval {
 #define BG_BATCH_PG 1
 #endif
     static constexpr int kCostBatch = (S > 0) ? BG_BATCH_PG : 1;
+    static constexpr bool kLanePgWalk = false;
     static constexpr int KB = kCostBatch;
     static constexpr int SR = S > 0 ? S : 1;
     double* s_pts;   // shared memory of this lane group: KB x 3 candidate points

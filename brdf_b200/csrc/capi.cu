@@ -92,6 +92,9 @@ extern "C" void brdfgpu_destroy(brdfgpu_ctx* ctx) {
         ctx->pooled = nullptr;
     }
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    brdfgpu_peer_detach(ctx);
+    cudaFree(ctx->peer_local);
+    ctx->peer_local = nullptr;
     cudaFree(ctx->d_partials); cudaFree(ctx->d_sync); cudaFree(ctx->d_result); cudaFree(ctx->d_fitio); cudaFree(ctx->d_cells);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     if (ctx->h_seq) cudaFreeHost((void*)ctx->h_seq);
@@ -108,7 +111,7 @@ extern "C" unsigned long long brdfgpu_launch_count(brdfgpu_ctx* ctx) {
 extern "C" int brdfgpu_fit_stats(brdfgpu_ctx* ctx, unsigned long long* out, int count) {
     ctx = ctx_or_default(ctx);
     if (!ctx || !out) return BRDFGPU_LM_ERROR;
-    for (int i = 0; i < count && i < 12; ++i) out[i] = ctx->fit_stats[i];
+    for (int i = 0; i < count && i < 20; ++i) out[i] = ctx->fit_stats[i];
     return 0;
 }
 extern "C" void* brdfgpu_stream(brdfgpu_ctx* ctx) {
@@ -502,6 +505,7 @@ extern "C" void brdfgpu_batch_free(brdfgpu_ctx* ctx, brdfgpu_batch* b) {
 namespace {
 struct CallbackEval {
     static constexpr int kCostBatch = 1;
+    static constexpr bool kLanePgWalk = false;
     brdfgpu_reduced_jac_t jac_cb;
     brdfgpu_reduced_cost_t cost_cb;
     void* user;

@@ -57,7 +57,7 @@ struct brdfgpu_ctx {
     // what the last global fit did: sweeps with a Jacobian, cost-only sweeps, trial points evaluated
     // (>= the levmar-counted ones: the projected-gradient walk is evaluated eight points per sweep),
     // samples resident in shared memory, CTAs
-    unsigned long long fit_stats[12] = {0};
+    unsigned long long fit_stats[20] = {0};
 
     // device buffers of the levmar-signature entry points, kept between calls (cudaMalloc/cudaFree
     // per call cost more than the fit itself at 10^6 samples)
@@ -136,6 +136,7 @@ struct GlobalFitOut {
     unsigned jac_passes, cost_passes, cost_points;
     long long cyc_sweep, cyc_exchange, cyc_total;  // SM cycles of CTA 0 / thread 0
     long long cyc_x[4];
+    long long cyc_ctl[7];  // control-code cycles by the kind of sweep they led to (SweepKind)
     double p[kMaxM];
     double info[10];
     double JtJ[kMaxM * kMaxM];

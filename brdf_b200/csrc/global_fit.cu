@@ -555,6 +555,7 @@ int model_jacobian(brdfgpu_ctx* ctx, const double* p, const double* angles_host,
 // ------------------------------------------------------------------------------------------------
 struct HostEval {
     static constexpr int kCostBatch = 1;
+    static constexpr bool kLanePgWalk = false;
     brdfgpu_ctx* ctx;
     const brdfgpu_samples* s;
     double delta;
@@ -692,6 +693,7 @@ __shared__ double s_cand[kGridCostBatch * 3];  // candidate points of the projec
 __shared__ double s_cand_cost[kGridCostBatch];
 __shared__ int s_cand_bad[kGridCostBatch];
 __shared__ long long s_cyc[6];  // thread 0: cycles in sweeps, exchanges, and the 4 exchange phases
+__shared__ long long s_ctl[8];  // thread 0: control-code cycles by the kind of request they led to; [7] = time of the last exchange end
 // TMA ring of the streamed part (sample sets beyond on-chip residency): 3 stages x 48 KB
 using PersistRing = TileRing<kPersistThreads, 3>;
 __shared__ PersistRing s_ring;
@@ -795,6 +797,7 @@ __device__ __forceinline__ void all_reduce(const double* acc, long long t_sweep_
         const long long t_d = clock64();
         s_cyc[0] += t_in - t_sweep_start; s_cyc[1] += t_d - t_in;
         s_cyc[2] += t_a - t_in; s_cyc[3] += t_b - t_a; s_cyc[4] += t_c - t_b; s_cyc[5] += t_d - t_c;
+        s_ctl[7] = t_d;
     }
 }
 
@@ -960,12 +963,19 @@ __device__ __forceinline__ void serve_sweeps() {
 // code redundantly cost more than the sweeps themselves.
 struct GridEval {
     static constexpr int kCostBatch = kGridCostBatch;
+#ifndef BG_LANE_PG_WALK
+#define BG_LANE_PG_WALK 1
+#endif
+    static constexpr bool kLanePgWalk = BG_LANE_PG_WALK != 0;
     int model, jkind;
     double delta;
     unsigned jac_passes, cost_passes, cost_points;
 
     __device__ __forceinline__ void post(int kind) {
-        if (threadIdx.x == 0) s_req.kind = kind;
+        if (threadIdx.x == 0) {
+            s_req.kind = kind;
+            s_ctl[kind] += clock64() - s_ctl[7];
+        }
         __syncthreads();
         if (kind != kQuit) run_sweep(kind);
     }
@@ -1029,6 +1039,83 @@ struct GridEval {
     }
     __device__ __forceinline__ double batch_cost(int c) const { return s_cand_cost[c]; }
     __device__ __forceinline__ bool batch_bad(int c) const { return s_cand_bad[c] != 0; }
+
+    // levmar's projected-gradient walk (lmbc_core.c:885-934) with one candidate per LANE of the control
+    // warp: lane c of a batch builds p - t*beta^c * g, projects it and makes its CostPoint; after the
+    // sweep it forms its own Dp, ||Dp||^2, g.Dp and the three tests; the first lane with an event
+    // (fatal / restart / found, in levmar's order of checks) decides and its state is broadcast.  Same
+    // candidates, same sweeps (batches of 1, 2, 4, 8 ...), same numbers as the sequential form in
+    // lm_engine.cuh -- only the ~1000 serial control instructions per batch are spread over lanes.
+    // Returns 0 = nothing found, 1 = found (point in pDp), 2 = non-finite residuals (stop 7).
+    __device__ __forceinline__ int pg_walk(const double* p, const double* g, double e_cur, const double* lb, const double* ub,
+                                           double& t, double t0, int& gprevtaken, double* pDp, double* Dp, double& Dp_L2,
+                                           double& e_new, int& nfev) {
+        const double alpha = 1e-4, beta = 0.9, tming = 1e-18;
+        const int lane = threadIdx.x;  // control warp: 0..31
+        const Box box{lb, ub};
+        int width = 1;
+        while (t > tming) {
+            // lane c: t_c = t * beta^c by the same repeated multiplication the sequential walk makes
+            double tc = t;
+            for (int c = 0; c < lane && c < width; ++c) tc *= beta;
+            const bool mine = lane < width && tc > tming;
+            const int nc = __popc(__ballot_sync(0xffffffffu, mine));  // candidates are a prefix of the lanes
+            double cand[3] = {0.0, 0.0, 0.0};
+            if (mine) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) cand[i] = p[i] - tc * g[i];
+                box_project<3>(cand, box, 3);
+                s_req.pts[lane] = make_cost_point(cand, model);
+            }
+            if (lane == 0) s_req.cnt = nc;
+            post(kSweepMany);
+            ++cost_passes;
+            cost_points += nc;
+            double e = mine ? s_res[lane] : 0.0;
+            bool bad = false;
+            unsigned need = __ballot_sync(0xffffffffu, mine && !lm_finite(e));
+            while (need) {  // rare: which of the non-finite sums come from non-finite residuals?
+                const int k = __ffs(need) - 1;
+                need &= need - 1;
+                const double nbad = count_bad(k);
+                if (lane == k) bad = nbad != 0.0;
+            }
+            // the tests of lmbc_core.c:905-932 for this lane's candidate
+            double d[3], dl2 = 0.0, gTd = 0.0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                d[i] = cand[i] - p[i];
+                dl2 += d[i] * d[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) gTd += g[i] * d[i];
+            const bool fatal = mine && !lm_finite(e) && bad;
+            const bool restart = mine && !fatal && gprevtaken && e <= e_cur + 2.0 * 0.99999 * gTd;
+            const bool found = mine && !fatal && !restart && e <= e_cur + 2.0 * alpha * gTd;
+            const unsigned events = __ballot_sync(0xffffffffu, fatal || restart || found);
+            const int src = events ? __ffs(events) - 1 : nc - 1;  // deciding lane, else the last candidate
+            nfev += src + 1;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                pDp[i] = __shfl_sync(0xffffffffu, cand[i], src);
+                Dp[i] = __shfl_sync(0xffffffffu, d[i], src);
+            }
+            Dp_L2 = __shfl_sync(0xffffffffu, dl2, src);
+            e_new = __shfl_sync(0xffffffffu, e, src);
+            const double t_src = __shfl_sync(0xffffffffu, tc, src);
+            if (events) {
+                const int kind = __shfl_sync(0xffffffffu, fatal ? 2 : (restart ? 3 : 1), src);
+                if (kind == 2) { t = t_src; return 2; }
+                if (kind == 1) { t = t_src; return 1; }
+                t = t0 * beta;  // restart: t = t0, then the loop increment still applies (:926-930)
+                gprevtaken = 0;
+            } else {
+                t = t_src * beta;
+            }
+            width = (2 * width < kGridCostBatch) ? 2 * width : kGridCostBatch;
+        }
+        return 0;
+    }
 };
 
 __global__ void __launch_bounds__(kPersistThreads, 1) k_persistent_fit(SampleView v, int model, GlobalFitSpec spec,
@@ -1061,6 +1148,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_persistent_fit(SampleVie
         s_ctx.cells = cells; s_ctx.peer = peer; s_ctx.abort_flag = &out->aborted;
         s_epoch = 0u; s_peer_epoch = peer.epoch; s_ring_seq = 0;
         for (int i = 0; i < 6; ++i) s_cyc[i] = 0;
+        for (int i = 0; i < 7; ++i) s_ctl[i] = 0;
+        s_ctl[7] = clock64();
     }
     __syncthreads();
 
@@ -1091,6 +1180,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_persistent_fit(SampleVie
         out->cyc_exchange = s_cyc[1];
         out->cyc_total = clock64() - t_start;
         for (int i = 0; i < 4; ++i) out->cyc_x[i] = s_cyc[2 + i];
+        for (int i = 0; i < 7; ++i) out->cyc_ctl[i] = s_ctl[i];
         for (int i = 0; i < 3; ++i) out->p[i] = p[i];
         for (int i = 0; i < 10; ++i) out->info[i] = info[i];
         for (int i = 0; i < 9; ++i) out->JtJ[i] = JtJ[i];
@@ -1261,6 +1351,7 @@ int global_fit(brdfgpu_ctx* ctx, const brdfgpu_samples* s, double* p, int m, con
         ctx->fit_stats[5] = (unsigned long long)h->cyc_sweep; ctx->fit_stats[6] = (unsigned long long)h->cyc_exchange;
         ctx->fit_stats[7] = (unsigned long long)h->cyc_total;
         for (int i = 0; i < 4; ++i) ctx->fit_stats[8 + i] = (unsigned long long)h->cyc_x[i];
+        for (int i = 0; i < 7; ++i) ctx->fit_stats[12 + i] = (unsigned long long)h->cyc_ctl[i];
         ret = h->ret;
         for (int i = 0; i < 3; ++i) p[i] = h->p[i];
         for (int i = 0; i < 10; ++i) fit_info[i] = h->info[i];

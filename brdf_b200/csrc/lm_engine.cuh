@@ -15,7 +15,8 @@
 // Evaluator concept:
 //     void   jac (const double* p, double* JtJ /*m*m row-major, full*/, double* Jte /*m*/);
 //     double cost(const double* p, bool& elems_nonfinite);
-//     static constexpr int kCostBatch;   // > 1: also cost_many(), see eval_cost_many_scaled
+//     static constexpr int kCostBatch;   // > 1: also batch_points() / cost_many() / batch_cost() / batch_bad() (PgBatch)
+//     static constexpr bool kLanePgWalk; // true: also pg_walk(), the projected-gradient walk one candidate per lane
 #pragma once
 
 #include <cfloat>
@@ -512,11 +513,23 @@ BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double*
                 // reduction); they are consumed strictly in levmar's order with levmar's tests, and
                 // candidates past the stopping one are discarded and not counted in nfev.
                 constexpr int KB = Eval::kCostBatch;
-                PgBatch<MM, Eval> batch;
-                double* pts = batch.points(ev);
                 bool pg_done = false;
                 int width = 1;  // most walks stop at their first candidates: speculate 1, 2, 4, ... KB points
                 t = gprevtaken ? t : t0;
+                if constexpr (Eval::kLanePgWalk) {
+                    // the evaluator runs the same walk with one candidate per LANE of its control warp
+                    // (generation, projection and the acceptance tests of a batch in parallel; the first
+                    // lane with an event decides, exactly as the sequential order would)
+                    if (!dscl) {
+                        const int outcome = ev.pg_walk(p, Jte, e_cur, lb, ub, t, t0, gprevtaken, pDp, Dp, Dp_L2, e_new, cnt.nfev);
+                        if (outcome == 2) { stop = 7; fatal = true; }
+                        found = outcome == 1;
+                        pg_done = true;
+                    }
+                }
+                if (!pg_done) {
+                PgBatch<MM, Eval> batch;
+                double* pts = batch.points(ev);
                 while (t > tming && !pg_done) {
                     int nc = 0;
                     double tt = t;
@@ -556,6 +569,7 @@ BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double*
                     }
                     if (!pg_done && !restarted) t = tt;
                     width = (2 * width < KB) ? 2 * width : KB;
+                }
                 }
                 if (fatal) goto done;
                 if (!found) { gprevtaken = 0; break; }

@@ -284,7 +284,7 @@ int global_fit_secant(brdfgpu_ctx* ctx, brdfgpu_samples* s, double* p, int m, in
     }
     ctx->fit_stats[0] = (unsigned long long)njap; ctx->fit_stats[1] = (unsigned long long)(nfev - njap * ((jkind == kJacForward) ? m : 2 * m));
     ctx->fit_stats[2] = ctx->fit_stats[1];
-    for (int i = 3; i < 12; ++i) ctx->fit_stats[i] = 0;
+    for (int i = 3; i < 20; ++i) ctx->fit_stats[i] = 0;
     return (stop != 4 && stop != 7) ? k : BRDFGPU_LM_ERROR;
 }
 

@@ -63,6 +63,8 @@ elif what == "micro":
                     line += " [kernel Mcyc: sweep %.2f exchange %.2f total %.2f, points %d]" % (
                         st["cyc_sweep"] / 1e6, st["cyc_exchange"] / 1e6, st["cyc_total"] / 1e6, st["cost_points"])
                     line += " x-phases/pass %s" % [int(v / passes) for v in st["cyc_exchange_phases"]]
+                    line += " ctl Mcyc %s jac=%d cost+many=%d" % ({k: round(v / 1e6, 2) for k, v in st["cyc_control_by_next_sweep"].items() if v},
+                                                                 st["jac_passes"], st["cost_passes"])
         print(line, flush=True)
         del s
 elif what == "gather":
