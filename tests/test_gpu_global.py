@@ -276,3 +276,32 @@ def test_diagonal_scaling_matches_levmar(ctx, drive):
         np.testing.assert_allclose(p, want[1], rtol=PAR_RTOL)
         np.testing.assert_allclose(info[1], want[2][1], rtol=COST_RTOL)
         np.testing.assert_allclose(covar, want[3], rtol=5e-3, atol=1e-14)
+
+
+@pytest.mark.parametrize("tma", ["0", "1"], ids=["register-prefetch", "tma-ring"])
+def test_sums_are_additive_over_shards(ctx, tma, monkeypatch):
+    """Size-independent property the multi-GPU mode rests on: J^T J, J^T e and ||e||^2 of a
+    sample set are the sums over any partition of it -- checked at 4e6 samples (ragged, odd shards) for
+    both streaming implementations of the Jacobian pass, against each other and against the oracle on a
+    prefix the CPU finishes in a second."""
+    monkeypatch.setenv("BRDFGPU_TMA", tma)
+    c2 = A.Context()          # BRDFGPU_TMA is read once per context
+    n = 4_000_001
+    p, delta = (0.55, 0.4, 9.5), 1.0
+    whole = c2.synth(n, seed=909)
+    total = c2.normal_eq(whole, p, delta)[:10]
+    c, t, x = whole.download()
+    cuts = [0, 1_000_003, 2_777_777, n]
+    parts = np.zeros(10)
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        s = c2.upload(c[lo:hi], t[lo:hi], x[lo:hi], 1)
+        parts += c2.normal_eq(s, p, delta)[:10]
+        s.free()
+    np.testing.assert_allclose(parts, total, rtol=1e-12)
+    assert np.isclose(c2.cost(whole, p)[0], total[9], rtol=1e-12)
+    m = 200_000
+    jac = GC.oracle_fd_jacobian(p, c[:m], t[:m], np.zeros(m), 1, delta)
+    e = x[:m] - GC.oracle_predict(p, c[:m], t[:m], np.zeros(m), 1)
+    s = c2.upload(c[:m], t[:m], x[:m], 1)
+    np.testing.assert_allclose(c2.normal_eq(s, p, delta)[:10], GC.normal_eq_from(jac, e), rtol=1e-9)
+    s.free(); whole.free(); c2.close()
