@@ -50,12 +50,16 @@ extern "C" int brdfgpu_create(int device, brdfgpu_ctx** out) {
     }
     brdfgpu_ctx* ctx = new brdfgpu_ctx;
     ctx->device = device;
-    // The fit kernels keep ~1 KB of per-thread stack; without this flag the driver shrinks the
-    // local-memory pool again after every such launch and re-grows it for the next one (a
-    // synchronising reallocation of tens of milliseconds).  Only takes effect if the primary
-    // context is not active yet; harmless otherwise.
-    if (cudaSetDeviceFlags(cudaDeviceLmemResizeToMax) != cudaSuccess) cudaGetLastError();
     e = cudaSetDevice(device);
+    if (e == cudaSuccess) {
+        // The fit kernels keep ~1 KB of per-thread stack; without this flag the driver shrinks the
+        // local-memory pool again after every such launch and re-grows it for the next one (a
+        // synchronising reallocation of tens of milliseconds -- host calls were 10-50x slower).
+        unsigned flags = 0;
+        if (cudaGetDeviceFlags(&flags) != cudaSuccess) { cudaGetLastError(); flags = 0; }
+        if (!(flags & cudaDeviceLmemResizeToMax) && cudaSetDeviceFlags(flags | cudaDeviceLmemResizeToMax) != cudaSuccess)
+            cudaGetLastError();  // an application that fixed its flags earlier keeps them
+    }
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->coop, cudaDevAttrCooperativeLaunch, device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);

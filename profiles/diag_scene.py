@@ -1,6 +1,9 @@
 import sys, time, os
 sys.path.insert(0,'.'); sys.path.insert(0,'tests')
 import numpy as np
+if os.environ.get("TORCH_FIRST"):
+    import torch
+    torch.cuda.set_device(0); torch.zeros(8, device="cuda"); torch.cuda.synchronize()
 import real_scenes as R
 from brdf_b200 import api as A
 ctx=A.Context(0)
