@@ -177,7 +177,11 @@ class Samples:
             lib().brdfgpu_samples_free(self.ctx.handle, self.handle)
             self.handle = None
 
-    __del__ = free
+    def __del__(self):   # at interpreter shutdown module globals may already be gone
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 class Batch:
@@ -205,7 +209,11 @@ class Batch:
             lib().brdfgpu_batch_free(self.ctx.handle, self.handle)
             self.handle = None
 
-    __del__ = free
+    def __del__(self):   # at interpreter shutdown module globals may already be gone
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 class Scene:
@@ -278,7 +286,11 @@ class Scene:
             lib().brdfgpu_scene_free(self.ctx.handle, self.handle)
             self.handle = None
 
-    __del__ = free
+    def __del__(self):   # at interpreter shutdown module globals may already be gone
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 class Context:
