@@ -42,7 +42,15 @@ struct GroupEval {
 #define BG_BATCH_PG 1
 #endif
     static constexpr int kCostBatch = (S > 0) ? BG_BATCH_PG : 1;
-    static constexpr bool kLanePgWalk = false;
+#ifndef BG_BATCH_LANE_WALK
+#define BG_BATCH_LANE_WALK 0
+#endif
+    // projected-gradient walk with BG_BATCH_LANE_WALK candidates per round, one per lane of the group
+    // (0 = the sequential walk of lm_engine.cuh); needs the samples in registers.  Bit-identical results
+    // (checked on the GPU), but measured slower for 65 536 x 64: 0 -> 16.8 ms, 2 -> 17.9, 4 -> 19.0,
+    // 8 -> 23.9: most walks of a small fit stop at their first candidates, the rest is wasted work.
+    static constexpr int kWalk = (S > 0) ? BG_BATCH_LANE_WALK : 0;
+    static constexpr bool kLanePgWalk = kWalk > 0;
     static constexpr int KB = kCostBatch;
     static constexpr int SR = S > 0 ? S : 1;
     double* s_pts;   // shared memory of this lane group: KB x 3 candidate points
@@ -112,6 +120,117 @@ struct GroupEval {
         bad = false;
         if (!lm_finite(esq)) bad = group_sum(nbad) != 0.0;  // uniform within the group
         return esq;
+    }
+
+    // levmar's projected-gradient walk (lmbc_core.c:885-934), kWalk candidates per round: lane c of the
+    // group builds and projects candidate c and later applies levmar's tests to it; the evaluation of
+    // the round is one pass over the lane's samples for all candidates (kWalk x S independent exp
+    // chains); the first lane with an event, in levmar's order of checks, decides.  Same candidates and
+    // same arithmetic per candidate as the sequential walk; candidates past the deciding one are
+    // discarded and not counted.  Returns 0 = nothing found, 1 = found (pDp), 2 = non-finite residuals.
+    __device__ __forceinline__ int pg_walk(const double* p, const double* g, double e_cur, const double* lb, const double* ub,
+                                           double& t, double t0, int& gprevtaken, double* pDp, double* Dp, double& Dp_L2,
+                                           double& e_new, int& nfev) const {
+        constexpr int W = kWalk > 0 ? kWalk : 1;
+        const double alpha = 1e-4, beta = 0.9, tming = 1e-18;
+        const Box box{lb, ub};
+        const int shift = ((threadIdx.x & 31) / G) * G;  // first lane of this group inside the warp
+        int width = 1;
+        while (t > tming) {
+            double tc = t;
+            for (int c = 0; c < lane && c < width; ++c) tc *= beta;
+            const bool mine = lane < width && tc > tming;
+            const int nc = __popc(__ballot_sync(mask, mine));
+            double cand[3] = {0.0, 0.0, 0.0};
+            CostPoint my_q = {0.0, 0.0, 0.0};
+            if (mine) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) cand[i] = p[i] - tc * g[i];
+                box_project<3>(cand, box, 3);
+                my_q = make_cost_point(cand, model);
+            }
+            CostPoint q[W];
+#pragma unroll
+            for (int k = 0; k < W; ++k) {
+                q[k].kd = __shfl_sync(mask, my_q.kd, k, G);
+                q[k].cks = __shfl_sync(mask, my_q.cks, k, G);
+                q[k].n = __shfl_sync(mask, my_q.n, k, G);
+            }
+            double esq[W], nbad[W];
+#pragma unroll
+            for (int k = 0; k < W; ++k) esq[k] = nbad[k] = 0.0;
+#pragma unroll
+            for (int s = 0; s < SR; ++s) {
+                const int idx = s * G + lane;
+                if (idx < nper) {
+                    double y[W], pw[W];
+                    bool slow = false;
+#pragma unroll
+                    for (int k = 0; k < W; ++k) {
+                        y[k] = q[k].n * L[s];
+                        slow |= (k < nc) && needs_care(y[k]);
+                    }
+                    exp_core_n<W>(y, pw);
+#pragma unroll
+                    for (int k = 0; k < W; ++k) {
+                        double e = x[s] - __fma_rn(q[k].kd, c[s], q[k].cks * pw[k]);
+                        if (slow && k < nc && needs_care(y[k])) e = residual_careful(q[k], c[s], traw[idx], x[s]);
+                        esq[k] = __fma_rn(e, e, esq[k]);
+                        nbad[k] += lm_finite(e) ? 0.0 : 1.0;
+                    }
+                }
+            }
+#pragma unroll
+            for (int off = G / 2; off; off >>= 1) {
+#pragma unroll
+                for (int k = 0; k < W; ++k) esq[k] += __shfl_xor_sync(mask, esq[k], off, G);
+            }
+            bool any_nonfinite = false;
+#pragma unroll
+            for (int k = 0; k < W; ++k) any_nonfinite |= (k < nc) && !lm_finite(esq[k]);
+            if (any_nonfinite) {  // uniform within the group
+#pragma unroll
+                for (int k = 0; k < W; ++k) nbad[k] = group_sum(nbad[k]);
+            }
+            double e = 0.0;
+            bool bad = false;
+#pragma unroll
+            for (int k = 0; k < W; ++k)
+                if (lane == k) { e = esq[k]; bad = nbad[k] != 0.0; }
+            double d[3], dl2 = 0.0, gTd = 0.0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                d[i] = cand[i] - p[i];
+                dl2 += d[i] * d[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) gTd += g[i] * d[i];
+            const bool fatal = mine && !lm_finite(e) && bad;
+            const bool restart = mine && !fatal && gprevtaken && e <= e_cur + 2.0 * 0.99999 * gTd;
+            const bool found = mine && !fatal && !restart && e <= e_cur + 2.0 * alpha * gTd;
+            const unsigned events = __ballot_sync(mask, fatal || restart || found) >> shift;
+            const int src = events ? __ffs(events) - 1 : nc - 1;
+            nfev += src + 1;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                pDp[i] = __shfl_sync(mask, cand[i], src, G);
+                Dp[i] = __shfl_sync(mask, d[i], src, G);
+            }
+            Dp_L2 = __shfl_sync(mask, dl2, src, G);
+            e_new = __shfl_sync(mask, e, src, G);
+            const double t_src = __shfl_sync(mask, tc, src, G);
+            if (events) {
+                const int kind = __shfl_sync(mask, fatal ? 2 : (restart ? 3 : 1), src, G);
+                if (kind == 2) { t = t_src; return 2; }
+                if (kind == 1) { t = t_src; return 1; }
+                t = t0 * beta;
+                gprevtaken = 0;
+            } else {
+                t = t_src * beta;
+            }
+            width = (2 * width < W) ? 2 * width : W;
+        }
+        return 0;
     }
 
     __device__ __forceinline__ double* batch_points() const { return s_pts; }
