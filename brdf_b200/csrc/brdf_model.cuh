@@ -288,6 +288,34 @@ __device__ __forceinline__ void residuals_n(const Q& q, const double* c, const d
     }
 }
 
+// the same N samples at TWO trial points: 2N interleaved exp chains, samples loaded once
+template <int N, class Q>
+__device__ __forceinline__ void residuals_n_x2(const Q& qa, const Q& qb, const double* c, const double* L, const double* x,
+                                               const double* __restrict__ traw, const long* idx, double* ea, double* eb) {
+    bool slow = false;
+    double y[2 * N], pw[2 * N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        y[k] = qa.n * L[k];
+        y[N + k] = qb.n * L[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 2 * N; ++k) slow |= needs_care(y[k]);
+    exp_core_n<2 * N>(y, pw);
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        ea[k] = x[k] - __fma_rn(qa.kd, c[k], qa.cks * pw[k]);
+        eb[k] = x[k] - __fma_rn(qb.kd, c[k], qb.cks * pw[N + k]);
+    }
+    if (slow) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            if (needs_care(y[k])) ea[k] = residual_careful(qa, c[k], traw[idx[k]], x[k]);
+            if (needs_care(y[N + k])) eb[k] = residual_careful(qb, c[k], traw[idx[k]], x[k]);
+        }
+    }
+}
+
 template <class Q>
 __device__ __forceinline__ double residual_of(const Q& q, double c, double L, double x,
                                               const double* __restrict__ traw, long i) {

@@ -687,7 +687,8 @@ __shared__ SweepRequest s_req;
 __shared__ unsigned s_epoch, s_peer_epoch;  // tags of the last grid / peer exchange (uniform in the CTA)
 __shared__ double s_red[(kPersistThreads / 32) * NACC];
 __shared__ double s_res[NACC];
-__shared__ double s_stage[kMaxPersistBlocks * NACC];
+constexpr int kStagePitch = kMaxPersistBlocks + 1;  // quantity-major with an odd pitch: conflict-free both ways
+__shared__ double s_stage[kStagePitch * NACC];
 __shared__ double s_pstage[kMaxRanks * NACC];
 __shared__ double s_cand[kGridCostBatch * 3];  // candidate points of the projected-gradient walk
 __shared__ double s_cand_cost[kGridCostBatch];
@@ -777,7 +778,7 @@ __device__ __forceinline__ void all_reduce(const double* acc, long long t_sweep_
         const int idx = threadIdx.x + j * kPersistThreads;
         if (idx < total) {
             const int b = idx / NV, k = idx - b * NV;
-            s_stage[idx] = c[j].has(tag) ? c[j].value() : wait_cell<false>(base + (long)b * NACC + k, tag, s_ctx.abort_flag);
+            s_stage[k * kStagePitch + b] = c[j].has(tag) ? c[j].value() : wait_cell<false>(base + (long)b * NACC + k, tag, s_ctx.abort_flag);
         }
     }
     __syncthreads();
@@ -785,7 +786,7 @@ __device__ __forceinline__ void all_reduce(const double* acc, long long t_sweep_
     // 4. fixed order: one warp per quantity, lanes stride the CTAs, butterfly
     for (int k = warp; k < NV; k += kWarps) {
         double t = 0.0;
-        for (int b = lane; b < grid; b += 32) t += s_stage[b * NV + k];
+        for (int b = lane; b < grid; b += 32) t += s_stage[k * kStagePitch + b];
 #pragma unroll
         for (int off = 16; off; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
         if (lane == 0) s_res[k] = t;
@@ -852,6 +853,35 @@ __device__ __forceinline__ double resident_cost(const CostPoint& q, unsigned sc,
     return a0 + a1;
 }
 
+// two trial points at once over the resident samples (eight exp chains per thread; each point's sum is
+// accumulated in exactly the order resident_cost uses, so batching never changes a value)
+__device__ __forceinline__ void resident_cost_x2(const CostPoint& qa, const CostPoint& qb, unsigned sc, unsigned sl, unsigned sx,
+                                                 int res_pairs, long res_first, const double* traw, double* out_a, double* out_b) {
+    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+    int i = threadIdx.x;
+    for (; i + kPersistThreads < res_pairs; i += 2 * kPersistThreads) {
+        const int i2 = i + kPersistThreads;
+        const double2 c = lds_pair(sc, i), l = lds_pair(sl, i), x = lds_pair(sx, i);
+        const double2 d = lds_pair(sc, i2), m = lds_pair(sl, i2), y = lds_pair(sx, i2);
+        const double cc[4] = {c.x, c.y, d.x, d.y}, ll[4] = {l.x, l.y, m.x, m.y}, xx[4] = {x.x, x.y, y.x, y.y};
+        const long g = 2 * (res_first + i), h = 2 * (res_first + i2);
+        const long idx[4] = {g, g + 1, h, h + 1};
+        double ea[4], eb[4];
+        residuals_n_x2<4>(qa, qb, cc, ll, xx, traw, idx, ea, eb);
+        a0 = __fma_rn(ea[0], ea[0], a0); a0 = __fma_rn(ea[1], ea[1], a0);
+        a1 = __fma_rn(ea[2], ea[2], a1); a1 = __fma_rn(ea[3], ea[3], a1);
+        b0 = __fma_rn(eb[0], eb[0], b0); b0 = __fma_rn(eb[1], eb[1], b0);
+        b1 = __fma_rn(eb[2], eb[2], b1); b1 = __fma_rn(eb[3], eb[3], b1);
+    }
+    if (i < res_pairs) {
+        const double2 c = lds_pair(sc, i), l = lds_pair(sl, i), x = lds_pair(sx, i);
+        accumulate_cost_pair(qa, c, l, x, traw, 2 * (res_first + i), &a0);
+        accumulate_cost_pair(qb, c, l, x, traw, 2 * (res_first + i), &b0);
+    }
+    *out_a = a0 + a1;
+    *out_b = b0 + b1;
+}
+
 __device__ __noinline__ void cost_sweep() {
     const long long t0 = clock64();
     const CostPoint q = s_req.pts[0];
@@ -907,8 +937,10 @@ __device__ __noinline__ void many_sweep() {
     for (int k = 0; k < kGridCostBatch; ++k) acc[k] = 0.0;
     // resident slice: candidate-outer, parameters in registers, samples re-read from shared memory
 #pragma unroll
-    for (int k = 0; k < kGridCostBatch; ++k)
-        if (k < cnt) acc[k] = resident_cost(s_req.pts[k], sc, sl, sx, res_pairs, res_first, traw);
+    for (int k = 0; k < kGridCostBatch; k += 2) {
+        if (k + 1 < cnt) resident_cost_x2(s_req.pts[k], s_req.pts[k + 1], sc, sl, sx, res_pairs, res_first, traw, &acc[k], &acc[k + 1]);
+        else if (k < cnt) acc[k] = resident_cost(s_req.pts[k], sc, sl, sx, res_pairs, res_first, traw);
+    }
     // streamed remainder: sample-outer (one trip through the ring for all candidates)
     const SampleView v = s_ctx.v;
     if (s_ctx.stream_first < (v.n >> 1)) {
