@@ -316,13 +316,14 @@ class Context:
 
     def fit_stats(self):
         """dict(jac_passes, cost_passes, cost_points, resident_samples, ctas) of the last global fit"""
-        buf = (C.c_ulonglong * 20)()
-        self._ok(lib().brdfgpu_fit_stats(self.handle, buf, 20))
+        buf = (C.c_ulonglong * 24)()
+        self._ok(lib().brdfgpu_fit_stats(self.handle, buf, 24))
         return dict(jac_passes=int(buf[0]), cost_passes=int(buf[1]), cost_points=int(buf[2]), resident_samples=int(buf[3]),
                     ctas=int(buf[4]), cyc_sweep=int(buf[5]), cyc_exchange=int(buf[6]), cyc_total=int(buf[7]),
                     cyc_exchange_phases=[int(buf[8 + i]) for i in range(4)],
                     cyc_control_by_next_sweep=dict(zip(("quit", "jac_fwd", "jac_central", "jac_analytic", "cost", "many", "bad"),
-                                                       (int(buf[12 + i]) for i in range(7)))))
+                                                       (int(buf[12 + i]) for i in range(7)))),
+                    spec_jac_issued=int(buf[19]), spec_jac_hits=int(buf[20]))
 
     def synchronize(self):
         self._ok(lib().brdfgpu_synchronize(self.handle))

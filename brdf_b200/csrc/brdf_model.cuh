@@ -181,11 +181,18 @@ __device__ __forceinline__ void accumulate_normal(double j0, double j1, double j
 // A zero exponent with an ordinary t gives y = 0 and exp_core(0) == 1 == pow(t, 0) exactly.
 __device__ __forceinline__ bool needs_care(double y) { return !(fabs(y) <= kFastExpLimit); }
 
+// model value on the careful path: products and sum rounded separately, as the reference callback
+// compiled without contraction does.  One spelling for every pass, so the residual of a sample at a
+// point has the same bits whether a cost sweep or a Jacobian sweep computes it (speculative Jacobians).
+__device__ __forceinline__ double model_value_careful(double kd, double c, double cks, double pw) {
+    return __dadd_rn(__dmul_rn(kd, c), __dmul_rn(cks, pw));
+}
+
 // careful path of one Jacobian sample: literal levmar differences of full model values
 template <int JAC>
 __device__ __forceinline__ void jac_terms_careful(const PassParams& q, double c, double traw, double x, double* out4) {
     const double pw = pow_careful(traw, q.n);
-    const double hx = q.kd * c + q.cks * pw;
+    const double hx = model_value_careful(q.kd, c, q.cks, pw);
     double j0, j1, j2;
     if (JAC == kJacForward) {  // jac[i][j] = (f(p + d_j e_j) - f(p)) * (1/d_j), misc_core.c:160-170
         const double pw_hi = pow_careful(traw, q.n_hi);
@@ -203,7 +210,7 @@ __device__ __forceinline__ void jac_terms_careful(const PassParams& q, double c,
         j1 = q.coef * pw;
         j2 = q.ks * pw * (q.dcoef + q.coef * log_careful(traw));
     }
-    out4[0] = x - hx; out4[1] = j0; out4[2] = j1; out4[3] = j2;
+    out4[0] = __dsub_rn(x, hx); out4[1] = j0; out4[2] = j1; out4[3] = j2;
 }
 
 // N samples of a fused residual + Jacobian + normal-equation pass.  The fast path of all N samples
@@ -265,7 +272,7 @@ __device__ __forceinline__ void accumulate_jac(const PassParams& q, double c, do
 // residual e = x - f(p) (same arithmetic in every pass).  Q is PassParams or CostPoint.
 template <class Q>
 __device__ __forceinline__ double residual_careful(const Q& q, double c, double traw, double x) {
-    return x - (q.kd * c + q.cks * pow_careful(traw, q.n));
+    return __dsub_rn(x, model_value_careful(q.kd, c, q.cks, pow_careful(traw, q.n)));
 }
 
 template <int N, class Q>

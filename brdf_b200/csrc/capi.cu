@@ -115,7 +115,7 @@ extern "C" unsigned long long brdfgpu_launch_count(brdfgpu_ctx* ctx) {
 extern "C" int brdfgpu_fit_stats(brdfgpu_ctx* ctx, unsigned long long* out, int count) {
     ctx = ctx_or_default(ctx);
     if (!ctx || !out) return BRDFGPU_LM_ERROR;
-    for (int i = 0; i < count && i < 20; ++i) out[i] = ctx->fit_stats[i];
+    for (int i = 0; i < count && i < 24; ++i) out[i] = ctx->fit_stats[i];
     return 0;
 }
 extern "C" void* brdfgpu_stream(brdfgpu_ctx* ctx) {

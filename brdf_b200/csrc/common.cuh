@@ -57,7 +57,7 @@ struct brdfgpu_ctx {
     // what the last global fit did: sweeps with a Jacobian, cost-only sweeps, trial points evaluated
     // (>= the levmar-counted ones: the projected-gradient walk is evaluated eight points per sweep),
     // samples resident in shared memory, CTAs
-    unsigned long long fit_stats[20] = {0};
+    unsigned long long fit_stats[24] = {0};
 
     // device buffers of the levmar-signature entry points, kept between calls (cudaMalloc/cudaFree
     // per call cost more than the fit itself at 10^6 samples)
@@ -124,7 +124,7 @@ inline int pass_blocks(const brdfgpu_ctx* ctx, long n, int ctas_per_sm) {
 
 // ---- global_fit.cu ----
 struct GlobalFitSpec {
-    int m, itmax, jac_mode, has_lb, has_ub, has_dscl, unconstrained;
+    int m, itmax, jac_mode, has_lb, has_ub, has_dscl, unconstrained, spec_jac;
     double delta;  // |opts[4]|
     double p[kMaxM], lb[kMaxM], ub[kMaxM], dscl[kMaxM];
     LmOptions opt;
@@ -133,7 +133,7 @@ struct GlobalFitOut {
     int ret;
     unsigned peer_epoch;  // exchange tag after the fit (all ranks advance in lock step)
     int aborted;          // an exchange partner never delivered: the fit was abandoned
-    unsigned jac_passes, cost_passes, cost_points;
+    unsigned jac_passes, cost_passes, cost_points, spec_issued, spec_hits;
     long long cyc_sweep, cyc_exchange, cyc_total;  // SM cycles of CTA 0 / thread 0
     long long cyc_x[4];
     long long cyc_ctl[7];  // control-code cycles by the kind of sweep they led to (SweepKind)

@@ -693,6 +693,7 @@ __shared__ double s_pstage[kMaxRanks * NACC];
 __shared__ double s_cand[kGridCostBatch * 3];  // candidate points of the projected-gradient walk
 __shared__ double s_cand_cost[kGridCostBatch];
 __shared__ int s_cand_bad[kGridCostBatch];
+__shared__ double s_memo[3 + 9];  // speculative Jacobian: the point, then A00..A22, G0..G2 (GridEval::cost_site)
 __shared__ long long s_cyc[6];  // thread 0: cycles in sweeps, exchanges, and the 4 exchange phases
 __shared__ long long s_ctl[8];  // thread 0: control-code cycles by the kind of request they led to; [7] = time of the last exchange end
 // TMA ring of the streamed part (sample sets beyond on-chip residency): 3 stages x 48 KB
@@ -803,6 +804,9 @@ __device__ __forceinline__ void all_reduce(const double* acc, long long t_sweep_
 }
 
 // ---- sweeps (all threads of the CTA) ----
+// ||e||^2 of a Jacobian sweep is accumulated in exactly the order the cost sweeps use (two running sums
+// over alternate pairs, resident part first, then the streamed part), so a trial point evaluated by a
+// Jacobian sweep (speculation, GridEval::cost_site) gets the very bits a cost sweep would give it.
 template <int JAC>
 __device__ __noinline__ void jac_sweep() {
     const long long t0 = clock64();
@@ -814,17 +818,44 @@ __device__ __noinline__ void jac_sweep() {
     double acc[NACC];
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
-    for (int i = threadIdx.x; i < res_pairs; i += kPersistThreads) {
+    double esq_a = 0.0, esq_b = 0.0;
+    int i = threadIdx.x;
+    for (; i + kPersistThreads < res_pairs; i += 2 * kPersistThreads) {
+        const int i2 = i + kPersistThreads;
         const double2 c = lds_pair(sc, i), l = lds_pair(sl, i), x = lds_pair(sx, i);
+        const double2 d = lds_pair(sc, i2), m = lds_pair(sl, i2), y = lds_pair(sx, i2);
+        acc[ESQ] = esq_a;
         accumulate_jac_pair<JAC>(q, s_req.q, c, l, x, traw, 2 * (res_first + i), acc);
+        esq_a = acc[ESQ];
+        acc[ESQ] = esq_b;
+        accumulate_jac_pair<JAC>(q, s_req.q, d, m, y, traw, 2 * (res_first + i2), acc);
+        esq_b = acc[ESQ];
     }
+    if (i < res_pairs) {
+        const double2 c = lds_pair(sc, i), l = lds_pair(sl, i), x = lds_pair(sx, i);
+        acc[ESQ] = esq_a;
+        accumulate_jac_pair<JAC>(q, s_req.q, c, l, x, traw, 2 * (res_first + i), acc);
+        esq_a = acc[ESQ];
+    }
+    acc[ESQ] = esq_a + esq_b;
     if (s_ctx.stream_first < (s_ctx.v.n >> 1)) {
         const SampleView v = s_ctx.v;
+        const double esq_res = acc[ESQ];
+        double sa = 0.0, sb = 0.0;
         const long seq = s_ring.stream(v, s_ctx.stream_first, s_ring_seq,
             [&](double2 c0, double2 l0, double2 x0, long i0, double2 c1, double2 l1, double2 x1, long i1, int valid) {
-                if (valid >= 1) accumulate_jac_pair<JAC>(q, s_req.q, c0, l0, x0, v.traw, i0, acc);
-                if (valid >= 2) accumulate_jac_pair<JAC>(q, s_req.q, c1, l1, x1, v.traw, i1, acc);
+                if (valid >= 1) {
+                    acc[ESQ] = sa;
+                    accumulate_jac_pair<JAC>(q, s_req.q, c0, l0, x0, v.traw, i0, acc);
+                    sa = acc[ESQ];
+                }
+                if (valid >= 2) {
+                    acc[ESQ] = sb;
+                    accumulate_jac_pair<JAC>(q, s_req.q, c1, l1, x1, v.traw, i1, acc);
+                    sb = acc[ESQ];
+                }
             });
+        acc[ESQ] = esq_res + (sa + sb);
         __syncthreads();  // everybody has read s_ring_seq
         if (threadIdx.x == 0) s_ring_seq = seq;
     }
@@ -999,9 +1030,18 @@ struct GridEval {
 #define BG_LANE_PG_WALK 1
 #endif
     static constexpr bool kLanePgWalk = BG_LANE_PG_WALK != 0;
+    // Speculative Jacobians (lm_engine.cuh): a cost request at a point that is likely to become the next
+    // iterate is served by a Jacobian sweep (same ||e||^2 bits, see jac_sweep) and the sums are kept in
+    // s_memo; jac() at a bit-identical point then needs no sweep, no exchange and no control round.
+    // Prediction per site is "what happened last time": the LM trial was accepted / the line search
+    // accepted probe number k / the projected-gradient walk took its first candidate.  Every CTA (and
+    // rank) sees identical sums, so all of them predict alike.
+    static constexpr bool kSpecJac = true;
     int model, jkind;
     double delta;
-    unsigned jac_passes, cost_passes, cost_points;
+    unsigned jac_passes, cost_passes, cost_points, spec_issued, spec_hits;
+    bool spec_on, memo_valid, sp_trial, sp_pg;
+    int sp_ls;  // probe number the last line search accepted (0: it failed)
 
     __device__ __forceinline__ void post(int kind) {
         if (threadIdx.x == 0) {
@@ -1012,16 +1052,60 @@ struct GridEval {
         if (kind != kQuit) run_sweep(kind);
     }
 
-    __device__ __forceinline__ void jac(const double* p, double* JtJ, double* Jte) {
-        const PassParams q = make_pass_params(p, model, delta, jkind);
-        if (threadIdx.x == 0) s_req.q = q;
-        post(jkind == kJacForward ? kSweepJacForward : jkind == kJacCentral ? kSweepJacCentral : kSweepJacAnalytic);
-        ++jac_passes;
-        JtJ[0] = s_res[A00]; JtJ[1] = s_res[A01]; JtJ[2] = s_res[A02];
-        JtJ[3] = s_res[A01]; JtJ[4] = s_res[A11]; JtJ[5] = s_res[A12];
-        JtJ[6] = s_res[A02]; JtJ[7] = s_res[A12]; JtJ[8] = s_res[A22];
-        Jte[0] = s_res[G0]; Jte[1] = s_res[G1]; Jte[2] = s_res[G2];
+    __device__ __forceinline__ int jac_sweep_kind() const {
+        return jkind == kJacForward ? kSweepJacForward : jkind == kJacCentral ? kSweepJacCentral : kSweepJacAnalytic;
     }
+    static __device__ __forceinline__ bool same_bits(double a, double b) {
+        return __double_as_longlong(a) == __double_as_longlong(b);
+    }
+
+    __device__ __forceinline__ void jac(const double* p, double* JtJ, double* Jte) {
+        const double* r = s_res;
+        if (memo_valid && same_bits(p[0], s_memo[0]) && same_bits(p[1], s_memo[1]) && same_bits(p[2], s_memo[2])) {
+            ++spec_hits;  // the sums of this very point are already here
+            r = s_memo + 3;
+        } else {
+            const PassParams q = make_pass_params(p, model, delta, jkind);
+            if (threadIdx.x == 0) s_req.q = q;
+            post(jac_sweep_kind());
+            ++jac_passes;
+        }
+        memo_valid = false;
+        JtJ[0] = r[A00]; JtJ[1] = r[A01]; JtJ[2] = r[A02];
+        JtJ[3] = r[A01]; JtJ[4] = r[A11]; JtJ[5] = r[A12];
+        JtJ[6] = r[A02]; JtJ[7] = r[A12]; JtJ[8] = r[A22];
+        Jte[0] = r[G0]; Jte[1] = r[G1]; Jte[2] = r[G2];
+    }
+
+    // ||x - f(p)||^2 through a Jacobian sweep at p; the normal-equation sums are kept for jac(p)
+    __device__ __forceinline__ double cost_with_jac(const double* p, bool& bad) {
+        const PassParams q = make_pass_params(p, model, delta, jkind);
+        const CostPoint cp = make_cost_point(p, model);
+        __syncwarp();  // nobody still reads the previous memo
+        if (threadIdx.x == 0) {
+            s_req.q = q;
+            s_req.pts[0] = cp;  // count_bad(0), should the sum come out non-finite
+            s_memo[0] = p[0]; s_memo[1] = p[1]; s_memo[2] = p[2];
+        }
+        post(jac_sweep_kind());
+        ++jac_passes;
+        ++spec_issued;
+        const double esq = s_res[ESQ];
+        if (threadIdx.x < 9) s_memo[3 + threadIdx.x] = s_res[threadIdx.x];  // A00..A22, G0..G2 are 0..8
+        __syncwarp();
+        memo_valid = true;
+        bad = false;
+        if (!lm_finite(esq)) bad = count_bad(0) != 0.0;
+        return esq;
+    }
+
+    // lm_engine.cuh sites: 0 = the LM trial point, k >= 1 = line-search probe number k
+    __device__ __forceinline__ double cost_site(int site, const double* p, bool& bad) {
+        const bool spec = spec_on && (site == kSiteTrial ? sp_trial : site == sp_ls);
+        return spec ? cost_with_jac(p, bad) : cost(p, bad);
+    }
+    __device__ __forceinline__ void trial_outcome(bool accepted) { sp_trial = accepted; }
+    __device__ __forceinline__ void ls_outcome(int accepted_probe) { sp_ls = accepted_probe; }
 
     __device__ __forceinline__ double count_bad(int k) {
         if (threadIdx.x == 0) s_req.cnt = k;
@@ -1086,6 +1170,7 @@ struct GridEval {
         const int lane = threadIdx.x;  // control warp: 0..31
         const Box box{lb, ub};
         int width = 1;
+        bool first_batch = true;
         while (t > tming) {
             // lane c: t_c = t * beta^c by the same repeated multiplication the sequential walk makes
             double tc = t;
@@ -1099,11 +1184,28 @@ struct GridEval {
                 box_project<3>(cand, box, 3);
                 s_req.pts[lane] = make_cost_point(cand, model);
             }
-            if (lane == 0) s_req.cnt = nc;
-            post(kSweepMany);
-            ++cost_passes;
+            // the walk took its first candidate last time: evaluate this one by a Jacobian sweep and keep
+            // the sums for the next iteration (same ||e||^2 bits as the cost sweep)
+            const bool spec = spec_on && sp_pg && first_batch && nc == 1;
+            if (spec) {
+                __syncwarp();
+                if (lane == 0) {
+                    s_req.q = make_pass_params(cand, model, delta, jkind);
+                    s_memo[0] = cand[0]; s_memo[1] = cand[1]; s_memo[2] = cand[2];
+                }
+                post(jac_sweep_kind());
+                ++jac_passes;
+                ++spec_issued;
+                if (lane < 9) s_memo[3 + lane] = s_res[lane];
+                __syncwarp();
+                memo_valid = true;
+            } else {
+                if (lane == 0) s_req.cnt = nc;
+                post(kSweepMany);
+                ++cost_passes;
+            }
             cost_points += nc;
-            double e = mine ? s_res[lane] : 0.0;
+            double e = mine ? s_res[spec ? (int)ESQ : lane] : 0.0;
             bool bad = false;
             unsigned need = __ballot_sync(0xffffffffu, mine && !lm_finite(e));
             while (need) {  // rare: which of the non-finite sums come from non-finite residuals?
@@ -1137,15 +1239,17 @@ struct GridEval {
             const double t_src = __shfl_sync(0xffffffffu, tc, src);
             if (events) {
                 const int kind = __shfl_sync(0xffffffffu, fatal ? 2 : (restart ? 3 : 1), src);
-                if (kind == 2) { t = t_src; return 2; }
-                if (kind == 1) { t = t_src; return 1; }
+                if (kind == 2) { t = t_src; sp_pg = false; return 2; }
+                if (kind == 1) { t = t_src; sp_pg = first_batch && src == 0; return 1; }
                 t = t0 * beta;  // restart: t = t0, then the loop increment still applies (:926-930)
                 gprevtaken = 0;
             } else {
                 t = t_src * beta;
             }
+            first_batch = false;
             width = (2 * width < kGridCostBatch) ? 2 * width : kGridCostBatch;
         }
+        sp_pg = false;
         return 0;
     }
 };
@@ -1192,7 +1296,10 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_persistent_fit(SampleVie
     const long long t_start = clock64();
     GridEval ev;
     ev.model = model; ev.jkind = spec.jac_mode; ev.delta = spec.delta;
-    ev.jac_passes = ev.cost_passes = ev.cost_points = 0u;
+    ev.jac_passes = ev.cost_passes = ev.cost_points = ev.spec_issued = ev.spec_hits = 0u;
+    ev.spec_on = spec.spec_jac != 0;
+    ev.memo_valid = ev.sp_trial = ev.sp_pg = false;
+    ev.sp_ls = 0;
     double p[3], info[10], JtJ[9];
     for (int i = 0; i < 3; ++i) p[i] = spec.p[i];
     int ret;
@@ -1208,6 +1315,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_persistent_fit(SampleVie
         out->jac_passes = ev.jac_passes;
         out->cost_passes = ev.cost_passes;
         out->cost_points = ev.cost_points;
+        out->spec_issued = ev.spec_issued;
+        out->spec_hits = ev.spec_hits;
         out->cyc_sweep = s_cyc[0];
         out->cyc_exchange = s_cyc[1];
         out->cyc_total = clock64() - t_start;
@@ -1341,6 +1450,9 @@ int global_fit(brdfgpu_ctx* ctx, const brdfgpu_samples* s, double* p, int m, con
         spec.m = m; spec.itmax = itmax; spec.jac_mode = jkind; spec.delta = delta; spec.opt = o;
         spec.has_lb = lb != nullptr; spec.has_ub = ub != nullptr; spec.has_dscl = dscl != nullptr;
         spec.unconstrained = unconstrained;
+        // BRDFGPU_SPEC_JAC=0 switches the speculative Jacobians off (A/B tests: results must not change)
+        const char* sj = getenv("BRDFGPU_SPEC_JAC");
+        spec.spec_jac = !(sj && sj[0] == '0');
         for (int i = 0; i < 3; ++i) {
             spec.p[i] = p[i];
             if (lb) spec.lb[i] = lbs[i];
@@ -1384,6 +1496,7 @@ int global_fit(brdfgpu_ctx* ctx, const brdfgpu_samples* s, double* p, int m, con
         ctx->fit_stats[7] = (unsigned long long)h->cyc_total;
         for (int i = 0; i < 4; ++i) ctx->fit_stats[8 + i] = (unsigned long long)h->cyc_x[i];
         for (int i = 0; i < 7; ++i) ctx->fit_stats[12 + i] = (unsigned long long)h->cyc_ctl[i];
+        ctx->fit_stats[19] = h->spec_issued; ctx->fit_stats[20] = h->spec_hits;
         ret = h->ret;
         for (int i = 0; i < 3; ++i) p[i] = h->p[i];
         for (int i = 0; i < 10; ++i) fit_info[i] = h->info[i];

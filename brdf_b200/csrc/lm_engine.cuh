@@ -17,10 +17,21 @@
 //     double cost(const double* p, bool& elems_nonfinite);
 //     static constexpr int kCostBatch;   // > 1: also batch_points() / cost_many() / batch_cost() / batch_bad() (PgBatch)
 //     static constexpr bool kLanePgWalk; // true: also pg_walk(), the projected-gradient walk one candidate per lane
+//     static constexpr bool kSpecJac;    // optional, true: also cost_site() / trial_outcome() / ls_outcome() (below)
+//
+// Speculative Jacobians (evaluators with kSpecJac).  A point that is evaluated because it may become
+// the next iterate -- the LM trial point, a line-search probe, the first projected-gradient candidate
+// -- needs ||x - f||^2 now and, if it is taken, J^T J / J^T e at the very same point one step later.
+// One fused sweep yields both, so such an evaluator may answer a cost request with a Jacobian sweep
+// and keep the sums; jac() at a bit-identical point then costs nothing.  The engine only names the
+// SITE of each evaluation and reports what happened to it; whether to speculate is the evaluator's
+// business (the persistent kernel predicts "same as last time" per site).  Values, decisions and
+// the nfev / njev counters are the same with and without speculation.
 #pragma once
 
 #include <cfloat>
 #include <cmath>
+#include <type_traits>
 
 #ifdef __CUDACC__
 #define BG_HD __host__ __device__
@@ -218,6 +229,27 @@ struct LmCounters {
     int nfev, njev, nlss;
 };
 
+// evaluation sites named to evaluators with kSpecJac: the LM trial point, or line-search probe k >= 2
+constexpr int kSiteTrial = 0;
+template <class E, class = void>
+struct SpecJac : std::false_type {};
+template <class E>
+struct SpecJac<E, std::void_t<decltype(E::kSpecJac)>> : std::integral_constant<bool, E::kSpecJac> {};
+
+template <class Eval>
+BG_HDI double eval_cost_site(Eval& ev, int site, const double* p, bool& bad) {
+    if constexpr (SpecJac<Eval>::value) return ev.cost_site(site, p, bad);
+    else return ev.cost(p, bad);
+}
+template <class Eval>
+BG_HDI void note_trial_outcome(Eval& ev, bool accepted) {
+    if constexpr (SpecJac<Eval>::value) ev.trial_outcome(accepted);
+}
+template <class Eval>
+BG_HDI void note_ls_outcome(Eval& ev, int accepted_probe /* 0: the search failed */) {
+    if constexpr (SpecJac<Eval>::value) ev.ls_outcome(accepted_probe);
+}
+
 // Calls the evaluator in the caller's (unscaled) coordinates; with diagonal scaling D the control
 // loop works on q = D^-1 p and J_q = J_p D (lmbc_core.c:360-366, 555-570), i.e.
 // JtJ_ij *= d_i d_j and Jte_i *= d_i -- the scaled sums are formed from the unscaled ones here
@@ -243,6 +275,15 @@ BG_HDI double eval_cost_scaled(Eval& ev, const double* q, const double* dscl, in
     double ps[MM];
     LM_FOR_REV(i) ps[i] = q[i] * dscl[i];
     return ev.cost(ps, bad);
+}
+
+// the LM trial point: the same products q_i * d_i eval_jac_scaled forms, so a kept Jacobian is found again
+template <int MM, class Eval>
+BG_HDI double eval_trial_scaled(Eval& ev, const double* q, const double* dscl, int m, bool& bad) {
+    if (!dscl) return eval_cost_site(ev, kSiteTrial, q, bad);
+    double ps[MM];
+    LM_FOR_REV(i) ps[i] = q[i] * dscl[i];
+    return eval_cost_site(ev, kSiteTrial, ps, bad);
 }
 
 // Candidate points of the projected-gradient walk.  Evaluators with kCostBatch > 1 own the storage
@@ -325,7 +366,7 @@ BG_HDI int lm_line_search(Eval& ev, int m, const double* xc, double fc, const do
             t = known_f;
             known_pt = nullptr;
         } else if (!dscl) {
-            t = ev.cost(xnew, bad);
+            t = eval_cost_site(ev, kLsItMax - it, xnew, bad);  // probe number 1, 2, ... as the site
         } else {  // :262-266 scales the point in place and back (not an exact round trip)
             LM_FOR_REV(i) xnew[i] *= dscl[i];
             t = ev.cost(xnew, bad);
@@ -335,8 +376,14 @@ BG_HDI int lm_line_search(Eval& ev, int m, const double* xc, double fc, const do
         fpls = 0.5 * t;
         fnew_sumsq = t;
 
-        if (fpls <= fc + slp * alpha * lambda) return 0;
-        if (lambda < rmnlmb) return 1;
+        if (fpls <= fc + slp * alpha * lambda) {
+            note_ls_outcome(ev, kLsItMax - it);
+            return 0;
+        }
+        if (lambda < rmnlmb) {
+            note_ls_outcome(ev, 0);
+            return 1;
+        }
 
         if (!lm_finite(fpls)) {
             lambda *= 0.1;
@@ -364,6 +411,7 @@ BG_HDI int lm_line_search(Eval& ev, int m, const double* xc, double fc, const do
             else lambda = tlmbda;
         }
     }
+    note_ls_outcome(ev, 0);
     return 1;
 }
 
@@ -454,10 +502,11 @@ BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double*
             if (Dp_L2 <= o.eps2_sq * p_L2) { stop = 2; break; }
             if (Dp_L2 >= (p_L2 + o.eps2) / (kEpsilon * kEpsilon)) { stop = 4; break; }
 
-            e_new = eval_cost_scaled<MM>(ev, pDp, dscl, m, bad);
+            e_new = eval_trial_scaled<MM>(ev, pDp, dscl, m, bad);
             ++cnt.nfev;
             // :748 -- overflow of the sum alone is tolerated, non-finite residuals are not
             if (!lm_finite(e_new) && bad) { stop = 7; break; }
+            note_trial_outcome(ev, e_new <= gamma * e_cur);
 
             if (e_new <= gamma * e_cur) {  // LM step accepted, :753-785
                 dL = 0.0;
@@ -651,13 +700,14 @@ BG_HDI int lm_der(Eval& ev, int m, double* p, const LmOptions& o, double* info, 
                 if (Dp_L2 <= o.eps2_sq * p_L2) { stop = 2; break; }
                 if (Dp_L2 >= (p_L2 + o.eps2) / (kEpsilon * kEpsilon)) { stop = 4; break; }
 
-                e_new = ev.cost(pDp, bad);
+                e_new = eval_cost_site(ev, kSiteTrial, pDp, bad);
                 ++cnt.nfev;
                 if (!lm_finite(e_new)) { stop = 7; break; }
 
                 dL = 0.0;
                 LM_FOR(i) dL += Dp[i] * (mu * Dp[i] + Jte[i]);
                 dF = e_cur - e_new;
+                note_trial_outcome(ev, dL > 0.0 && dF > 0.0);
                 if (dL > 0.0 && dF > 0.0) {
                     tmp = (2.0 * dF / dL - 1.0);
                     tmp = 1.0 - tmp * tmp * tmp;
