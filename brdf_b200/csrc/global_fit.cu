@@ -616,6 +616,7 @@ struct HostEval {
 constexpr int kPersistThreads = BG_PERSIST_THREADS;  // 512: 16 warps, <= 128 registers per thread
 constexpr int kMaxPersistBlocks = 160;  // >= SM count (148 on B200)
 constexpr int kGridCostBatch = 8;       // trial points per cost_many() sweep (<= NACC)
+constexpr int NSUM = NACC + 1;          // sums of the widest sweep: a Jacobian at one point + the cost at another
 constexpr long long kSpinCycles = 6000000000LL;  // ~3 s at 2 GHz, then the fit is abandoned
 
 // A cell is two 64-bit words {value.lo | tag << 32, value.hi | tag << 32}; each word is one scalar
@@ -663,6 +664,7 @@ __device__ __forceinline__ unsigned next_tag(unsigned e) { return e + 1u ? e + 1
 enum SweepKind { kQuit = 0, kSweepJacForward, kSweepJacCentral, kSweepJacAnalytic, kSweepCost, kSweepMany, kSweepBad };
 struct SweepRequest {
     int kind, cnt;  // cnt: trial points of kSweepMany / index of the point of kSweepBad
+    int extra;      // Jacobian sweeps: also ||x - f||^2 at pts[0] (sum number NACC)
     PassParams q;   // Jacobian sweeps
     CostPoint pts[kGridCostBatch];
 };
@@ -677,7 +679,7 @@ struct FitContext {
     int res_pairs;        // pairs held by this CTA
     long res_first;       // global index of its first pair
     long stream_first;    // pairs >= stream_first are streamed from global memory by the whole grid
-    uint4* cells;         // [2 parities][gridDim.x][NACC]
+    uint4* cells;         // [2 parities][gridDim.x][NSUM]
     PeerView peer;        // nranks == 1: no cross-GPU step
     int* abort_flag;      // global
 };
@@ -685,15 +687,16 @@ struct FitContext {
 __shared__ FitContext s_ctx;
 __shared__ SweepRequest s_req;
 __shared__ unsigned s_epoch, s_peer_epoch;  // tags of the last grid / peer exchange (uniform in the CTA)
-__shared__ double s_red[(kPersistThreads / 32) * NACC];
-__shared__ double s_res[NACC];
+__shared__ double s_red[(kPersistThreads / 32) * NSUM];
+__shared__ double s_res[NSUM];
 constexpr int kStagePitch = kMaxPersistBlocks + 1;  // quantity-major with an odd pitch: conflict-free both ways
-__shared__ double s_stage[kStagePitch * NACC];
-__shared__ double s_pstage[kMaxRanks * NACC];
+__shared__ double s_stage[kStagePitch * NSUM];
+__shared__ double s_pstage[kMaxRanks * NSUM];
 __shared__ double s_cand[kGridCostBatch * 3];  // candidate points of the projected-gradient walk
 __shared__ double s_cand_cost[kGridCostBatch];
 __shared__ int s_cand_bad[kGridCostBatch];
-__shared__ double s_memo[3 + 9];  // speculative Jacobian: the point, then A00..A22, G0..G2 (GridEval::cost_site)
+__shared__ double s_memo[3 + NACC];  // speculative Jacobian: the point, then A00..A22, G0..G2, ||e||^2 (GridEval::cost_site)
+__shared__ double s_hint[3];         // first projected-gradient candidate announced by the line search (GridEval::ls_fallback)
 __shared__ long long s_cyc[6];  // thread 0: cycles in sweeps, exchanges, and the 4 exchange phases
 __shared__ long long s_ctl[8];  // thread 0: control-code cycles by the kind of request they led to; [7] = time of the last exchange end
 // TMA ring of the streamed part (sample sets beyond on-chip residency): 3 stages x 48 KB
@@ -755,31 +758,31 @@ __device__ __forceinline__ void all_reduce(const double* acc, long long t_sweep_
     const long long t_a = clock64();
     // 2. across the 16 warps: 16 lanes per quantity, 4 butterfly steps; publish
     const unsigned tag = next_tag(s_epoch);
-    uint4* base = s_ctx.cells + (long)(tag & 1u) * grid * NACC;
+    uint4* base = s_ctx.cells + (long)(tag & 1u) * grid * NSUM;
     if (threadIdx.x < ((NV * kWarps + 31) & ~31)) {
         const int k = threadIdx.x / kWarps, w = threadIdx.x % kWarps;
         double t = (k < NV) ? s_red[w * NV + k] : 0.0;
 #pragma unroll
         for (int off = kWarps / 2; off; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off, kWarps);
-        if (k < NV && w == 0) store_cell<false>(base + (long)blockIdx.x * NACC + k, t, tag);
+        if (k < NV && w == 0) store_cell<false>(base + (long)blockIdx.x * NSUM + k, t, tag);
     }
     const long long t_b = clock64();
     // 3. every thread collects up to 4 cells: all loads go out together, late ones are re-polled
-    constexpr int kPerThread = (kMaxPersistBlocks * NACC + kPersistThreads - 1) / kPersistThreads;
+    constexpr int kPerThread = (kMaxPersistBlocks * NSUM + kPersistThreads - 1) / kPersistThreads;
     const int total = grid * NV;
     Cell c[kPerThread];
 #pragma unroll
     for (int j = 0; j < kPerThread; ++j) {
         const int idx = threadIdx.x + j * kPersistThreads;
         const int b = idx / NV, k = idx - b * NV;
-        if (idx < total) c[j] = load_cell<false>(base + (long)b * NACC + k);
+        if (idx < total) c[j] = load_cell<false>(base + (long)b * NSUM + k);
     }
 #pragma unroll
     for (int j = 0; j < kPerThread; ++j) {
         const int idx = threadIdx.x + j * kPersistThreads;
         if (idx < total) {
             const int b = idx / NV, k = idx - b * NV;
-            s_stage[k * kStagePitch + b] = c[j].has(tag) ? c[j].value() : wait_cell<false>(base + (long)b * NACC + k, tag, s_ctx.abort_flag);
+            s_stage[k * kStagePitch + b] = c[j].has(tag) ? c[j].value() : wait_cell<false>(base + (long)b * NSUM + k, tag, s_ctx.abort_flag);
         }
     }
     __syncthreads();
@@ -807,10 +810,14 @@ __device__ __forceinline__ void all_reduce(const double* acc, long long t_sweep_
 // ||e||^2 of a Jacobian sweep is accumulated in exactly the order the cost sweeps use (two running sums
 // over alternate pairs, resident part first, then the streamed part), so a trial point evaluated by a
 // Jacobian sweep (speculation, GridEval::cost_site) gets the very bits a cost sweep would give it.
-template <int JAC>
+// EXTRA: the same sweep also sums ||x - f||^2 at the trial point s_req.pts[0] (sum number NACC), again
+// in the order of the cost sweeps.
+template <int JAC, bool EXTRA>
 __device__ __noinline__ void jac_sweep() {
     const long long t0 = clock64();
     const PassParams q = s_req.q;
+    const CostPoint xq = s_req.pts[0];
+    double xa = 0.0, xb = 0.0;
     const unsigned sc = s_ctx.sc, sl = s_ctx.sl, sx = s_ctx.sx;
     const int res_pairs = s_ctx.res_pairs;
     const long res_first = s_ctx.res_first;
@@ -830,18 +837,21 @@ __device__ __noinline__ void jac_sweep() {
         acc[ESQ] = esq_b;
         accumulate_jac_pair<JAC>(q, s_req.q, d, m, y, traw, 2 * (res_first + i2), acc);
         esq_b = acc[ESQ];
+        if (EXTRA) accumulate_cost_2pairs(xq, c, l, x, 2 * (res_first + i), d, m, y, 2 * (res_first + i2), traw, &xa, &xb);
     }
     if (i < res_pairs) {
         const double2 c = lds_pair(sc, i), l = lds_pair(sl, i), x = lds_pair(sx, i);
         acc[ESQ] = esq_a;
         accumulate_jac_pair<JAC>(q, s_req.q, c, l, x, traw, 2 * (res_first + i), acc);
         esq_a = acc[ESQ];
+        if (EXTRA) accumulate_cost_pair(xq, c, l, x, traw, 2 * (res_first + i), &xa);
     }
     acc[ESQ] = esq_a + esq_b;
+    double extra[1] = {xa + xb};
     if (s_ctx.stream_first < (s_ctx.v.n >> 1)) {
         const SampleView v = s_ctx.v;
         const double esq_res = acc[ESQ];
-        double sa = 0.0, sb = 0.0;
+        double sa = 0.0, sb = 0.0, ya = 0.0, yb = 0.0;
         const long seq = s_ring.stream(v, s_ctx.stream_first, s_ring_seq,
             [&](double2 c0, double2 l0, double2 x0, long i0, double2 c1, double2 l1, double2 x1, long i1, int valid) {
                 if (valid >= 1) {
@@ -854,16 +864,30 @@ __device__ __noinline__ void jac_sweep() {
                     accumulate_jac_pair<JAC>(q, s_req.q, c1, l1, x1, v.traw, i1, acc);
                     sb = acc[ESQ];
                 }
+                if (EXTRA) {
+                    if (valid == 2) accumulate_cost_2pairs(xq, c0, l0, x0, i0, c1, l1, x1, i1, v.traw, &ya, &yb);
+                    else if (valid == 1) accumulate_cost_pair(xq, c0, l0, x0, v.traw, i0, &ya);
+                }
             });
         acc[ESQ] = esq_res + (sa + sb);
+        extra[0] += ya + yb;
         __syncthreads();  // everybody has read s_ring_seq
         if (threadIdx.x == 0) s_ring_seq = seq;
     }
     if ((s_ctx.v.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
         const long j = s_ctx.v.n - 1;
         accumulate_jac<JAC>(s_req.q, s_ctx.v.c[j], s_ctx.v.L[j], s_ctx.v.x[j], traw, j, acc);
+        if (EXTRA) accumulate_cost(xq, s_ctx.v.c[j], s_ctx.v.L[j], s_ctx.v.x[j], traw, j, extra);
     }
-    all_reduce<NACC>(acc, t0);
+    if (EXTRA) {
+        double all[NSUM];
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) all[k] = acc[k];
+        all[NACC] = extra[0];
+        all_reduce<NSUM>(all, t0);
+    } else {
+        all_reduce<NACC>(acc, t0);
+    }
 }
 
 // sum of squared residuals at one point over this thread's share of the resident samples
@@ -1002,9 +1026,9 @@ __device__ __noinline__ void many_sweep() {
 
 __device__ __forceinline__ void run_sweep(int kind) {
     switch (kind) {
-        case kSweepJacForward: jac_sweep<kJacForward>(); break;
-        case kSweepJacCentral: jac_sweep<kJacCentral>(); break;
-        case kSweepJacAnalytic: jac_sweep<kJacAnalytic>(); break;
+        case kSweepJacForward: if (s_req.extra) jac_sweep<kJacForward, true>(); else jac_sweep<kJacForward, false>(); break;
+        case kSweepJacCentral: if (s_req.extra) jac_sweep<kJacCentral, true>(); else jac_sweep<kJacCentral, false>(); break;
+        case kSweepJacAnalytic: if (s_req.extra) jac_sweep<kJacAnalytic, true>(); else jac_sweep<kJacAnalytic, false>(); break;
         case kSweepCost: cost_sweep(); break;
         case kSweepMany: many_sweep(); break;
         default: bad_sweep(); break;
@@ -1040,8 +1064,9 @@ struct GridEval {
     int model, jkind;
     double delta;
     unsigned jac_passes, cost_passes, cost_points, spec_issued, spec_hits;
-    bool spec_on, memo_valid, sp_trial, sp_pg;
-    int sp_ls;  // probe number the last line search accepted (0: it failed)
+    bool spec_on, fuse_on, width_on, memo_valid, sp_trial, sp_pg, hint_valid;
+    int sp_ls;    // probe number the last line search accepted (0: it failed)
+    int pg_last;  // candidates the last projected-gradient walk consumed
 
     __device__ __forceinline__ void post(int kind) {
         if (threadIdx.x == 0) {
@@ -1059,16 +1084,35 @@ struct GridEval {
         return __double_as_longlong(a) == __double_as_longlong(b);
     }
 
+    // post a Jacobian sweep at q; extra: also the cost at s_req.pts[0]
+    __device__ __forceinline__ void post_jac(const PassParams& q, int extra) {
+        if (threadIdx.x == 0) {
+            s_req.q = q;
+            s_req.extra = extra;
+        }
+        post(jac_sweep_kind());
+        ++jac_passes;
+    }
+    // keep the sums of the Jacobian sweep that just ended, as the Jacobian (and cost) of `pt`
+    __device__ __forceinline__ void keep_jac(const double* pt) {
+        __syncwarp();  // nobody still reads the previous memo
+        if (threadIdx.x < NACC) s_memo[3 + threadIdx.x] = s_res[threadIdx.x];  // A00..A22, G0..G2, ESQ are 0..9
+        if (threadIdx.x == 0) { s_memo[0] = pt[0]; s_memo[1] = pt[1]; s_memo[2] = pt[2]; }
+        __syncwarp();
+        memo_valid = true;
+        ++spec_issued;
+    }
+    __device__ __forceinline__ bool memo_is(const double* pt) const {
+        return memo_valid && same_bits(pt[0], s_memo[0]) && same_bits(pt[1], s_memo[1]) && same_bits(pt[2], s_memo[2]);
+    }
+
     __device__ __forceinline__ void jac(const double* p, double* JtJ, double* Jte) {
         const double* r = s_res;
-        if (memo_valid && same_bits(p[0], s_memo[0]) && same_bits(p[1], s_memo[1]) && same_bits(p[2], s_memo[2])) {
+        if (memo_is(p)) {
             ++spec_hits;  // the sums of this very point are already here
             r = s_memo + 3;
         } else {
-            const PassParams q = make_pass_params(p, model, delta, jkind);
-            if (threadIdx.x == 0) s_req.q = q;
-            post(jac_sweep_kind());
-            ++jac_passes;
+            post_jac(make_pass_params(p, model, delta, jkind), 0);
         }
         memo_valid = false;
         JtJ[0] = r[A00]; JtJ[1] = r[A01]; JtJ[2] = r[A02];
@@ -1079,30 +1123,53 @@ struct GridEval {
 
     // ||x - f(p)||^2 through a Jacobian sweep at p; the normal-equation sums are kept for jac(p)
     __device__ __forceinline__ double cost_with_jac(const double* p, bool& bad) {
-        const PassParams q = make_pass_params(p, model, delta, jkind);
-        const CostPoint cp = make_cost_point(p, model);
-        __syncwarp();  // nobody still reads the previous memo
-        if (threadIdx.x == 0) {
-            s_req.q = q;
-            s_req.pts[0] = cp;  // count_bad(0), should the sum come out non-finite
-            s_memo[0] = p[0]; s_memo[1] = p[1]; s_memo[2] = p[2];
-        }
-        post(jac_sweep_kind());
-        ++jac_passes;
-        ++spec_issued;
+        if (threadIdx.x == 0) s_req.pts[0] = make_cost_point(p, model);  // count_bad(0), should the sum come out non-finite
+        post_jac(make_pass_params(p, model, delta, jkind), 0);
         const double esq = s_res[ESQ];
-        if (threadIdx.x < 9) s_memo[3 + threadIdx.x] = s_res[threadIdx.x];  // A00..A22, G0..G2 are 0..8
-        __syncwarp();
-        memo_valid = true;
+        keep_jac(p);
         bad = false;
         if (!lm_finite(esq)) bad = count_bad(0) != 0.0;
         return esq;
     }
 
+    // ||x - f(p)||^2 and, in the same sweep, the Jacobian (and cost) at the announced first candidate of the
+    // projected-gradient walk that follows if this last line-search probe is not accepted
+    __device__ __forceinline__ double cost_and_fallback_jac(const double* p, bool& bad) {
+        const double h[3] = {s_hint[0], s_hint[1], s_hint[2]};
+        if (threadIdx.x == 0) s_req.pts[0] = make_cost_point(p, model);
+        post_jac(make_pass_params(h, model, delta, jkind), 1);
+        const double esq = s_res[NACC];
+        keep_jac(h);
+        bad = false;
+        if (!lm_finite(esq)) bad = count_bad(0) != 0.0;
+        return esq;
+    }
+
+    // first candidate of a projected-gradient walk from p along -g with step t (lmbc_core.c:886-889);
+    // one spelling for the announcement and the walk itself, so the bits agree
+    static __device__ __forceinline__ void pg_candidate(const double* p, const double* g, double tc, const Box& box, double* cand) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) cand[i] = p[i] - tc * g[i];
+        box_project<3>(cand, box, 3);
+    }
+    __device__ __forceinline__ void ls_fallback(const double* p, const double* g, double t, const double* lb, const double* ub) {
+        if (!fuse_on || !sp_pg) return;  // only while the walks keep taking their first candidate
+        double cand[3];
+        pg_candidate(p, g, t, Box{lb, ub}, cand);
+        __syncwarp();
+        if (threadIdx.x == 0) { s_hint[0] = cand[0]; s_hint[1] = cand[1]; s_hint[2] = cand[2]; }
+        __syncwarp();
+        hint_valid = true;
+    }
+
     // lm_engine.cuh sites: 0 = the LM trial point, k >= 1 = line-search probe number k
     __device__ __forceinline__ double cost_site(int site, const double* p, bool& bad) {
         const bool spec = spec_on && (site == kSiteTrial ? sp_trial : site == sp_ls);
-        return spec ? cost_with_jac(p, bad) : cost(p, bad);
+        const bool fallback = hint_valid && !spec;
+        hint_valid = false;
+        if (spec) return cost_with_jac(p, bad);
+        if (fallback) return cost_and_fallback_jac(p, bad);
+        return cost(p, bad);
     }
     __device__ __forceinline__ void trial_outcome(bool accepted) { sp_trial = accepted; }
     __device__ __forceinline__ void ls_outcome(int accepted_probe) { sp_ls = accepted_probe; }
@@ -1169,8 +1236,11 @@ struct GridEval {
         const double alpha = 1e-4, beta = 0.9, tming = 1e-18;
         const int lane = threadIdx.x;  // control warp: 0..31
         const Box box{lb, ub};
+        // walks tend to repeat: start with the batch width the last walk needed (1, 2, 4 or 8 candidates)
         int width = 1;
+        if (width_on) while (width < pg_last && width < kGridCostBatch) width *= 2;
         bool first_batch = true;
+        int consumed = 0;
         while (t > tming) {
             // lane c: t_c = t * beta^c by the same repeated multiplication the sequential walk makes
             double tc = t;
@@ -1179,33 +1249,33 @@ struct GridEval {
             const int nc = __popc(__ballot_sync(0xffffffffu, mine));  // candidates are a prefix of the lanes
             double cand[3] = {0.0, 0.0, 0.0};
             if (mine) {
-#pragma unroll
-                for (int i = 0; i < 3; ++i) cand[i] = p[i] - tc * g[i];
-                box_project<3>(cand, box, 3);
+                pg_candidate(p, g, tc, box, cand);
                 s_req.pts[lane] = make_cost_point(cand, model);
             }
-            // the walk took its first candidate last time: evaluate this one by a Jacobian sweep and keep
-            // the sums for the next iteration (same ||e||^2 bits as the cost sweep)
-            const bool spec = spec_on && sp_pg && first_batch && nc == 1;
-            if (spec) {
-                __syncwarp();
-                if (lane == 0) {
-                    s_req.q = make_pass_params(cand, model, delta, jkind);
-                    s_memo[0] = cand[0]; s_memo[1] = cand[1]; s_memo[2] = cand[2];
-                }
-                post(jac_sweep_kind());
-                ++jac_passes;
-                ++spec_issued;
-                if (lane < 9) s_memo[3 + lane] = s_res[lane];
-                __syncwarp();
-                memo_valid = true;
+            // (a) the line search announced this walk's first candidate and it was evaluated with the last
+            //     probe: nothing to do; (b) the walk took its first candidate last time: evaluate this one by
+            //     a Jacobian sweep and keep the sums for the next iteration; (c) a plain batch of cost points
+            bool known = false, spec = false;
+            if (first_batch && nc == 1) {
+                known = __shfl_sync(0xffffffffu, (int)(memo_is(cand) && lm_finite(s_memo[3 + ESQ])), 0) != 0;
+                spec = !known && spec_on && sp_pg;
+            }
+            if (known) {
+                // value in s_memo[3 + ESQ]
+            } else if (spec) {
+                post_jac(make_pass_params(cand, model, delta, jkind), 0);  // lane 0's values are the ones that count
+                double c0[3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) c0[i] = __shfl_sync(0xffffffffu, cand[i], 0);
+                keep_jac(c0);
+                cost_points += nc;
             } else {
                 if (lane == 0) s_req.cnt = nc;
                 post(kSweepMany);
                 ++cost_passes;
+                cost_points += nc;
             }
-            cost_points += nc;
-            double e = mine ? s_res[spec ? (int)ESQ : lane] : 0.0;
+            double e = mine ? (known ? s_memo[3 + ESQ] : s_res[spec ? (int)ESQ : lane]) : 0.0;
             bool bad = false;
             unsigned need = __ballot_sync(0xffffffffu, mine && !lm_finite(e));
             while (need) {  // rare: which of the non-finite sums come from non-finite residuals?
@@ -1239,17 +1309,20 @@ struct GridEval {
             const double t_src = __shfl_sync(0xffffffffu, tc, src);
             if (events) {
                 const int kind = __shfl_sync(0xffffffffu, fatal ? 2 : (restart ? 3 : 1), src);
+                consumed += src + 1;
                 if (kind == 2) { t = t_src; sp_pg = false; return 2; }
-                if (kind == 1) { t = t_src; sp_pg = first_batch && src == 0; return 1; }
+                if (kind == 1) { t = t_src; sp_pg = first_batch && src == 0; pg_last = consumed; return 1; }
                 t = t0 * beta;  // restart: t = t0, then the loop increment still applies (:926-930)
                 gprevtaken = 0;
             } else {
+                consumed += nc;
                 t = t_src * beta;
             }
             first_batch = false;
             width = (2 * width < kGridCostBatch) ? 2 * width : kGridCostBatch;
         }
         sp_pg = false;
+        pg_last = consumed;
         return 0;
     }
 };
@@ -1297,9 +1370,11 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_persistent_fit(SampleVie
     GridEval ev;
     ev.model = model; ev.jkind = spec.jac_mode; ev.delta = spec.delta;
     ev.jac_passes = ev.cost_passes = ev.cost_points = ev.spec_issued = ev.spec_hits = 0u;
-    ev.spec_on = spec.spec_jac != 0;
-    ev.memo_valid = ev.sp_trial = ev.sp_pg = false;
-    ev.sp_ls = 0;
+    ev.spec_on = (spec.spec_jac & 1) != 0;
+    ev.fuse_on = (spec.spec_jac & 2) != 0;
+    ev.width_on = (spec.spec_jac & 4) != 0;
+    ev.memo_valid = ev.sp_trial = ev.sp_pg = ev.hint_valid = false;
+    ev.sp_ls = ev.pg_last = 0;
     double p[3], info[10], JtJ[9];
     for (int i = 0; i < 3; ++i) p[i] = spec.p[i];
     int ret;
@@ -1451,8 +1526,10 @@ int global_fit(brdfgpu_ctx* ctx, const brdfgpu_samples* s, double* p, int m, con
         spec.has_lb = lb != nullptr; spec.has_ub = ub != nullptr; spec.has_dscl = dscl != nullptr;
         spec.unconstrained = unconstrained;
         // BRDFGPU_SPEC_JAC=0 switches the speculative Jacobians off (A/B tests: results must not change)
+        // (a bit mask for experiments: 1 = speculate at the trial / line-search / first-candidate sites, 2 = fuse the
+        // announced first candidate into the last line-search probe, 4 = start a walk at the last walk's width)
         const char* sj = getenv("BRDFGPU_SPEC_JAC");
-        spec.spec_jac = !(sj && sj[0] == '0');
+        spec.spec_jac = sj ? atoi(sj) : 7;
         for (int i = 0; i < 3; ++i) {
             spec.p[i] = p[i];
             if (lb) spec.lb[i] = lbs[i];
@@ -1465,7 +1542,7 @@ int global_fit(brdfgpu_ctx* ctx, const brdfgpu_samples* s, double* p, int m, con
         uint4* cells = ctx->d_cells;
         long resident_pairs = plan.resident_pairs;
         // tags restart at 1 every launch: clear the cells this grid will use and the abort flag
-        BG_CUDA_OK(ctx, cudaMemsetAsync(cells, 0, sizeof(uint4) * 2 * (size_t)plan.grid * NACC, ctx->stream));
+        BG_CUDA_OK(ctx, cudaMemsetAsync(cells, 0, sizeof(uint4) * 2 * (size_t)plan.grid * NSUM, ctx->stream));
         BG_CUDA_OK(ctx, cudaMemsetAsync(d_out, 0, sizeof(GlobalFitOut), ctx->stream));
         PeerView peer;
         memset(&peer, 0, sizeof(peer));

@@ -249,6 +249,14 @@ template <class Eval>
 BG_HDI void note_ls_outcome(Eval& ev, int accepted_probe /* 0: the search failed */) {
     if constexpr (SpecJac<Eval>::value) ev.ls_outcome(accepted_probe);
 }
+// The line search is about to evaluate its LAST probe (lambda is already below the minimum step): if
+// that probe is not accepted the search fails and the projected-gradient walk starts from p with
+// gradient g at step length t -- its first candidate is known now, so the evaluator may evaluate it
+// (and its Jacobian) in the same sweep as the probe.
+template <class Eval>
+BG_HDI void note_ls_fallback(Eval& ev, const double* p, const double* g, double t, const double* lb, const double* ub) {
+    if constexpr (SpecJac<Eval>::value) ev.ls_fallback(p, g, t, lb, ub);
+}
 
 // Calls the evaluator in the caller's (unscaled) coordinates; with diagonal scaling D the control
 // loop works on q = D^-1 p and J_q = J_p D (lmbc_core.c:360-366, 555-570), i.e.
@@ -329,7 +337,7 @@ template <int MM, class Eval>
 BG_HDI int lm_line_search(Eval& ev, int m, const double* xc, double fc, const double* g, double* step,
                           double alpha, double* xnew, double& fnew_sumsq, const Box& box,
                           const double* dscl, double stepmx, double steptl, LmCounters& cnt,
-                          const double* known_pt, double known_f) {
+                          const double* known_pt, double known_f, double pg_t) {
     bool firstback = true, bad;
     double sln, slp, rln, rmnlmb, lambda, tlmbda = 0.0, plmbda = 0.0, pfpls = 0.0, fpls, t;
 
@@ -366,6 +374,7 @@ BG_HDI int lm_line_search(Eval& ev, int m, const double* xc, double fc, const do
             t = known_f;
             known_pt = nullptr;
         } else if (!dscl) {
+            if (lambda < rmnlmb) note_ls_fallback(ev, xc, g, pg_t, box.lb, box.ub);
             t = eval_cost_site(ev, kLsItMax - it, xnew, bad);  // probe number 1, 2, ... as the site
         } else {  // :262-266 scales the point in place and back (not an exact round trip)
             LM_FOR_REV(i) xnew[i] *= dscl[i];
@@ -533,6 +542,12 @@ BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double*
                 Jte[i] = -Jte[i];
                 gTd += Jte[i] * Dp[i];
             }
+            // first step length of a projected-gradient walk from here (:876-879)
+            tmp = 0.0;
+            LM_FOR(i) tmp += Jte[i] * Jte[i];
+            tmp = sqrt(tmp);
+            tmp = 100.0 / (1.0 + tmp);
+            t0 = (tmp <= tini) ? tmp : tini;
             if (gTd <= -rho * pow(Dp_L2, kPow / 2.0)) {
                 const double steptl = 1e3 * sqrt(DBL_EPSILON);
                 tmp = sqrt(p_L2);
@@ -541,7 +556,7 @@ BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double*
                 double trial_pt[MM];
                 LM_FOR(i) trial_pt[i] = pDp[i];
                 const int rc = lm_line_search<MM>(ev, m, p, e_cur, Jte, Dp, alpha, pDp, e_new, box, dscl,
-                                                  stepmx, steptl, cnt, trial_pt, e_new);
+                                                  stepmx, steptl, cnt, trial_pt, e_new, gprevtaken ? t : t0);
                 if (rc != 0 || !lm_finite(e_new)) use_pg = true;
                 else gprevtaken = 0;
             } else {
@@ -549,12 +564,7 @@ BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double*
             }
 
             if (use_pg) {  // projected gradient search, :871-946
-                bool found = false, fatal = false;
-                tmp = 0.0;
-                LM_FOR(i) tmp += Jte[i] * Jte[i];
-                tmp = sqrt(tmp);
-                tmp = 100.0 / (1.0 + tmp);
-                t0 = (tmp <= tini) ? tmp : tini;
+                bool found = false, fatal = false;  // t0: computed above, before the line search
 
                 // levmar walks t, t*beta, t*beta^2, ... one function evaluation at a time (:885-934).
                 // The candidate points of that walk depend only on p and J^T e, so an evaluator may

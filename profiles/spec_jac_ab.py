@@ -37,10 +37,19 @@ cases = [("REF_GLOBAL 1e6", 1_000_000, 0, A.REF_GLOBAL, {}),
 for name, n, start, preset, kw in cases:
     s = ctx.synth(n, SEED, start=start)
     out = {}
-    for mode in ("0", "1"):
+    for mode in ("0", "1", "3", "5", "7"):
         os.environ["BRDFGPU_SPEC_JAC"] = mode
         out[mode] = run(s, preset, **kw)
-    a, b = out["0"], out["1"]
+        st = out[mode][4]
+        sw = st["jac_passes"] + st["cost_passes"]
+        ctl = st["cyc_total"] - st["cyc_sweep"] - st["cyc_exchange"]
+        print("   mode %s: %.3f ms, %d sweeps, per sweep: %d cyc = sweep %d + exchange %d + control %d; control by next: %s"
+              % (mode, out[mode][0], sw, st["cyc_total"] // sw, st["cyc_sweep"] // sw, st["cyc_exchange"] // sw, ctl // sw,
+                 {k: v // 1000 for k, v in st["cyc_control_by_next_sweep"].items() if v}))
+    a, b = out["0"], out["7"]
+    for mode in ("1", "3", "5"):
+        m = out[mode]
+        assert m[2].tobytes() == a[2].tobytes() and m[3].tobytes() == a[3].tobytes(), mode
     same = a[2].tobytes() == b[2].tobytes() and a[3].tobytes() == b[3].tobytes() and a[1] == b[1]
     sa, sb = a[4], b[4]
     print("%-28s off %.3f ms (%d jac + %d cost sweeps) | on %.3f ms (%d jac + %d cost sweeps, %d speculated, %d hits) | it %d nfev %d stop %d | identical=%s"
