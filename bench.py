@@ -256,7 +256,9 @@ def run_gpu_arm(args):
                         "memory for the whole fit and the projected-gradient walk evaluates up to 8 trial points per sweep, "
                         "so almost none of these bytes move through HBM (ncu: 38 MB of DRAM traffic per launch) and "
                         "'achieved' is an algorithmic rate, not HBM utilisation; the kernel is bound by the FP64 pipe and "
-                        "the per-evaluation exchange latency.  roofline_hbm is the HBM-resident regime (10^8 samples)."}
+                        "the per-evaluation exchange latency.  roofline_hbm is the HBM-resident regime (10^8 samples).  "
+                        "Speculative Jacobians (fit_stats.spec_jac_*) answer some cost evaluations with a Jacobian sweep "
+                        "whose sums the next iteration reuses; evaluations are counted as levmar counts them either way."}
 
     extra = {}
     if rank == 0 and world == 1 and not args.quick:

@@ -305,3 +305,48 @@ def test_sums_are_additive_over_shards(ctx, tma, monkeypatch):
     s = c2.upload(c[:m], t[:m], x[:m], 1)
     np.testing.assert_allclose(c2.normal_eq(s, p, delta)[:10], GC.normal_eq_from(jac, e), rtol=1e-9)
     s.free(); whole.free(); c2.close()
+
+
+@pytest.mark.parametrize("case", ["ref_global", "ref_global_small", "ref_perface", "analytic", "phong", "dscl", "negative_cosines",
+                                  "streamed"])
+def test_speculative_jacobians_change_nothing(ctx, case, monkeypatch):
+    """The persistent fit answers cost requests at likely next iterates with Jacobian sweeps, fuses the
+    last line-search probe with the Jacobian at the first projected-gradient candidate and starts walks
+    at the last walk's batch width.  All of it is speculation about WHICH sweeps to run: p and every
+    entry of info[] (including the nfev / njev counters) must equal the unspeculated run bit for bit,
+    while fewer sweeps are made."""
+    n, model, preset, kw = 300_001, 1, A.REF_GLOBAL, {}
+    if case == "ref_global_small":
+        n = 20_001
+    elif case == "ref_perface":
+        preset = A.REF_PERFACE
+    elif case == "analytic":
+        kw = {"jac_mode": A.JAC_ANALYTIC}
+    elif case == "phong":
+        model = 0
+    elif case == "dscl":
+        kw = {"dscl": (1.0, 0.5, 10.0)}
+    elif case == "streamed":
+        n = 2_500_001   # beyond on-chip residency: part of the samples goes through the TMA ring every sweep
+    c, td, th, x = synth.samples(n, model_id=model, seed=77)
+    t = (td if model == 1 else th).copy()
+    if case == "negative_cosines":   # careful path (libm pow semantics) inside both kinds of sweep
+        t[::97] *= -1.0
+        t[5] = 0.0
+    s = ctx.upload(c, t, x, model)
+    runs = {}
+    for mask in ("0", "1", "3", "7"):
+        monkeypatch.setenv("BRDFGPU_SPEC_JAC", mask)
+        ret, p, info = ctx.fit_global(s, preset, **kw)
+        runs[mask] = (ret, p.tobytes(), info.tobytes(), ctx.fit_stats())
+    base = runs["0"]
+    assert base[3]["spec_jac_issued"] == 0 and base[3]["spec_jac_hits"] == 0
+    for mask in ("1", "3", "7"):
+        r = runs[mask]
+        assert r[0] == base[0] and r[1] == base[1] and r[2] == base[2], mask
+    full = runs["7"][3]
+    assert full["spec_jac_hits"] <= full["spec_jac_issued"]
+    if case not in ("negative_cosines",):
+        assert full["spec_jac_hits"] > 0
+        assert full["jac_passes"] + full["cost_passes"] < base[3]["jac_passes"] + base[3]["cost_passes"]
+    s.free()
