@@ -157,6 +157,13 @@ def run_reference_arm(args):
 # GPU arm
 # ----------------------------------------------------------------------------------------------
 def run_gpu_arm(args):
+    # stdout carries exactly ONE line (the JSON); libraries that write there (NCCL prints its version banner to
+    # stdout when NCCL_DEBUG is set) are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    json_out = os.fdopen(json_fd, "w")
+
     import torch
 
     from brdf_b200 import api as A
@@ -369,7 +376,8 @@ def run_gpu_arm(args):
                           "sweeps_per_fit": passes / args.steps, "fit_stats": st},
                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
         out.update(extra)
-        print(json.dumps(out))
+        json_out.write(json.dumps(out) + "\n")
+        json_out.flush()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -94,6 +94,11 @@ SIGNATURES = {
     "brdfgpu_batch_count": (C.c_long, [_V]),
     "brdfgpu_batch_free": (None, [_V, _V]),
     "brdfgpu_led_table": (None, [dptr]),
+    "brdfgpu_read_cal": (C.c_int, [C.c_char_p, dptr]),
+    "brdfgpu_read_obj": (C.c_int, [C.c_char_p, dptr, iptr, iptr, iptr]),
+    "brdfgpu_read_png": (C.c_int, [C.c_char_p, _V, iptr, iptr]),
+    "brdfgpu_scene_load": (C.c_int, [_V, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(_V), dptr]),
+    "brdfgpu_scene_dims": (C.c_int, [_V, iptr]),
     "brdfgpu_scene_create": (C.c_int, [_V, dptr, C.c_int, iptr, C.c_int, C.POINTER(_V), C.c_int, C.c_int, C.c_int, _V, dptr, C.POINTER(_V)]),
     "brdfgpu_scene_free": (None, [_V, _V]),
     "brdfgpu_scene_face_normals": (C.c_int, [_V, _V, dptr]),
@@ -426,6 +431,17 @@ class Context:
                                             _d(led), C.byref(h)))
         return Scene(self, h, F.shape[0], len(imgs), W, H)
 
+    def scene_load(self, image_folder, obj_path, cal_path=None, nimg=16):
+        """main.cpp:41-59: LoadModel, LoadImages, SubtractAmbientLight, LoadCameraParameters, InitLEDs -- from the
+        reference's own files.  Returns (Scene, cam16 or None)."""
+        h = C.c_void_p()
+        cam = np.zeros(16)
+        self._ok(lib().brdfgpu_scene_load(self.handle, os.fsencode(image_folder), os.fsencode(obj_path),
+                                          None if cal_path is None else os.fsencode(cal_path), nimg, C.byref(h), _d(cam)))
+        dims = np.zeros(5, dtype=np.int32)
+        self._ok(lib().brdfgpu_scene_dims(h, dims.ctypes.data_as(iptr)))
+        return Scene(self, h, int(dims[1]), int(dims[2]), int(dims[3]), int(dims[4])), (None if cal_path is None else cam)
+
     # ---- multi-GPU ----
     def comm_init(self, unique_id, rank, nranks):
         self._ok(lib().brdfgpu_comm_init(self.handle, unique_id, rank, nranks))
@@ -542,6 +558,38 @@ def solve_equation_single(phi, thetaDash, theta, inten, model=BLINN_PHONG):
     p, info = np.zeros(3), np.zeros(10)
     ret = lib().brdfgpu_solve_equation_single(_d(phi), _d(td), _d(th), _d(inten), phi.size, model, _d(p), _d(info))
     return ret, p, info
+
+
+# ---- the reference's input files (host code) ----
+def read_cal(path):
+    """(cam16, mask of the fields present) -- CBRDFdata::LoadCameraParameters, brdfdata.cpp:149-247"""
+    cam = np.zeros(16)
+    mask = lib().brdfgpu_read_cal(os.fsencode(path), _d(cam))
+    if mask < 0:
+        raise BrdfGpuError(lib().brdfgpu_last_error(None).decode())
+    return cam, mask
+
+
+def read_obj(path):
+    """(V nV x 3 float64, F nF x 3 int32) -- igl::readOBJ as CBRDFdata::LoadModel uses it, brdfdata.cpp:289-312"""
+    nV, nF = C.c_int(0), C.c_int(0)
+    if lib().brdfgpu_read_obj(os.fsencode(path), None, None, C.byref(nV), C.byref(nF)) != 0:
+        raise BrdfGpuError(lib().brdfgpu_last_error(None).decode())
+    V, F = np.empty((nV.value, 3)), np.empty((nF.value, 3), dtype=np.int32)
+    if lib().brdfgpu_read_obj(os.fsencode(path), _d(V), F.ctypes.data_as(iptr), C.byref(nV), C.byref(nF)) != 0:
+        raise BrdfGpuError(lib().brdfgpu_last_error(None).decode())
+    return V, F
+
+
+def read_png(path):
+    """H x W x 3 uint8 BGR -- cv::imread(path, IMREAD_COLOR) for 8-bit PNG files"""
+    W, H = C.c_int(0), C.c_int(0)
+    if lib().brdfgpu_read_png(os.fsencode(path), None, C.byref(W), C.byref(H)) != 0:
+        raise BrdfGpuError(lib().brdfgpu_last_error(None).decode())
+    out = np.empty((H.value, W.value, 3), dtype=np.uint8)
+    if lib().brdfgpu_read_png(os.fsencode(path), out.ctypes.data_as(C.c_void_p), C.byref(W), C.byref(H)) != 0:
+        raise BrdfGpuError(lib().brdfgpu_last_error(None).decode())
+    return out
 
 
 def lm_bc_reduced(jac_cb, cost_cb, p0, n, lb, ub, itmax, opts, dscl=None, want_covar=False):

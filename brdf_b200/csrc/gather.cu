@@ -429,6 +429,12 @@ extern "C" void brdfgpu_scene_free(brdfgpu_ctx* ctx, brdfgpu_scene* sc) {
     delete sc;
 }
 
+extern "C" int brdfgpu_scene_dims(const brdfgpu_scene* sc, int* dims5) {
+    if (!sc || !dims5) return BRDFGPU_LM_ERROR;
+    dims5[0] = sc->nV; dims5[1] = sc->nF; dims5[2] = sc->nimg; dims5[3] = sc->W; dims5[4] = sc->H;
+    return 0;
+}
+
 extern "C" int brdfgpu_scene_face_normals(brdfgpu_ctx* ctx, const brdfgpu_scene* sc, double* FN) {
     ctx = ctx_or_default(ctx);
     if (!ctx || !sc) return BRDFGPU_LM_ERROR;

@@ -218,6 +218,8 @@ int brdfgpu_scene_create(brdfgpu_ctx *ctx, const double *V, int nV, const int *F
                          const unsigned char *const *images, int nimg, int W, int H,
                          const unsigned char *dark, const double *led, brdfgpu_scene **out);
 void brdfgpu_scene_free(brdfgpu_ctx *ctx, brdfgpu_scene *sc);
+/* dims5 = {nV, nF, nimg, W, H} of a scene */
+int brdfgpu_scene_dims(const brdfgpu_scene *sc, int *dims5);
 /* face normals as CalcFaceNormals (brdfdata.cpp:314-330), nF x 3 */
 int brdfgpu_scene_face_normals(brdfgpu_ctx *ctx, const brdfgpu_scene *sc, double *FN);
 /* ambient-subtracted image k back to the host (H*W*3 bytes) */
@@ -255,6 +257,34 @@ long brdfgpu_calc_brdf_equation(brdfgpu_ctx *ctx, const brdfgpu_scene *sc, const
  * ret = 3 levmar return values. */
 long brdfgpu_calc_brdf_equation_single(brdfgpu_ctx *ctx, const brdfgpu_scene *sc, const double *cam,
                                        int model, double *single_brdf, double *info, int *ret);
+
+/* ------------------------------------------------------------------------------------------------
+ * 4b. The reference's input files (host code, usable without a GPU)
+ * ------------------------------------------------------------------------------------------------ */
+
+/* CBRDFdata::LoadCameraParameters + WriteValue (brdfdata.cpp:149-247): the '<name>value</name>' scanner of
+ * the reference, atof() on the value, the 16 fields of BRDFGPU_CAM_SZ kept (kappa1, camera_model and any
+ * other tag ignored, as the reference ignores them).  Returns a bit mask of the fields that were present
+ * (0xffff = all 16; absent fields are 0.0) or BRDFGPU_LM_ERROR when the file cannot be read. */
+int brdfgpu_read_cal(const char *path, double *cam16);
+
+/* CBRDFdata::LoadModel -> igl::readOBJ (brdfdata.cpp:289-312): `v x y z` rows and the vertex index of the
+ * first three corners of every `f` (v, v/vt, v//vn, v/vt/vn; 1-based or negative = relative), 0-based in F.
+ * Two calls: V == NULL returns the counts in *nV / *nF; then V (nV x 3 fp64) and F (nF x 3 int32) sized
+ * accordingly, with *nV / *nF holding those counts.  Returns 0 or BRDFGPU_LM_ERROR. */
+int brdfgpu_read_obj(const char *path, double *V, int *F, int *nV, int *nF);
+
+/* cv::imread(path, IMREAD_COLOR) for 8-bit non-interlaced PNG files (brdfdata.cpp:40, 122): H x W x 3 bytes,
+ * B G R order, alpha dropped, grey replicated.  Two calls: bgr == NULL returns the size in *W / *H. */
+int brdfgpu_read_png(const char *path, unsigned char *bgr, int *W, int *H);
+
+/* The loading sequence of main.cpp:41-59 into a device-resident scene: LoadModel(obj_path),
+ * LoadImages(image_folder) = image_folder + "1.png" .. "<nimg>.png" (the string is a prefix, as in the
+ * reference: end it with '/'), SubtractAmbientLight with image_folder + "dark.png" when that file exists,
+ * LoadCameraParameters(cal_path) into cam16 (cal_path may be NULL), InitLEDs.  PNG only: the reference's
+ * current sources name ".jpeg" files that its repository does not contain. */
+int brdfgpu_scene_load(brdfgpu_ctx *ctx, const char *image_folder, const char *obj_path, const char *cal_path,
+                       int nimg, brdfgpu_scene **out, double *cam16);
 
 /* ------------------------------------------------------------------------------------------------
  * 5. Multi-GPU (one process per GPU).  Global mode only needs it: batched fits and gather views

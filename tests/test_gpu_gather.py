@@ -152,3 +152,41 @@ def test_calc_brdf_equation_drivers(ctx, scene_inputs):
         assert (ret[ch] >= 0) == (w[0] >= 0) and int(info[ch][6]) == int(w[2][6])
         if w[0] >= 0:
             np.testing.assert_allclose(info[ch][1], w[2][1], rtol=1e-6)
+
+
+def test_scene_load_from_files_equals_scene_from_arrays(ctx, scene_inputs, tmp_path):
+    """main.cpp:41-59 from the reference's file formats (brdfgpu_scene_load: .obj, 1..16.png, dark.png, .cal)
+    gives the very scene the array entry point builds: ambient-subtracted photographs, face normals and the
+    pixel map compared as bytes."""
+    cv2 = pytest.importorskip("cv2")
+    V, F, imgs, dark, cams, W, H = scene_inputs
+    folder = str(tmp_path) + "/"
+    with open(folder + "mesh.obj", "w") as f:
+        f.write("# Mesh file written by the test\n")
+        for v in V:
+            f.write("v %r %r %r\n" % tuple(float(x) for x in v))
+        for a, b, c in F:
+            f.write("f %d/%d %d/%d %d/%d\n" % (a + 1, a + 1, b + 1, b + 1, c + 1, c + 1))
+    for k, im in enumerate(imgs):
+        assert cv2.imwrite(folder + "%d.png" % (k + 1), im)
+    assert cv2.imwrite(folder + "dark.png", dark)
+    names = ("cx", "cy", "f", "sx", "nx", "ny", "nz", "ox", "oy", "oz", "ax", "ay", "az", "px", "py", "pz")
+    with open(folder + "cam.cal", "w") as f:
+        f.write("<camera_model>CameraTsai</camera_model>\n")
+        for n, v in zip(names, cams[0]):
+            f.write("<%s>%r</%s>\n" % (n, float(v), n))
+    sc_f, cam = ctx.scene_load(folder, folder + "mesh.obj", folder + "cam.cal")
+    sc_a = ctx.scene(V, F, imgs, dark)
+    assert (sc_f.nF, sc_f.nimg, sc_f.W, sc_f.H) == (sc_a.nF, sc_a.nimg, sc_a.W, sc_a.H)
+    assert cam.tobytes() == np.asarray(cams[0]).tobytes()
+    assert sc_f.face_normals().tobytes() == sc_a.face_normals().tobytes()
+    for k in (0, 7, 15):
+        assert sc_f.image(k).tobytes() == sc_a.image(k).tobytes()
+    assert sc_f.calc_pixel2surface(cam).tobytes() == sc_a.calc_pixel2surface(cams[0]).tobytes()
+    # without a dark frame the reference carries on with the raw photographs (brdfdata.cpp:134-138)
+    import os
+    os.remove(folder + "dark.png")
+    sc_n, _ = ctx.scene_load(folder, folder + "mesh.obj")
+    assert sc_n.image(3).tobytes() == imgs[3].tobytes()
+    for sc in (sc_f, sc_a, sc_n):
+        sc.free()
