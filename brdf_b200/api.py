@@ -99,6 +99,7 @@ SIGNATURES = {
     "brdfgpu_read_png": (C.c_int, [C.c_char_p, _V, iptr, iptr]),
     "brdfgpu_scene_load": (C.c_int, [_V, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(_V), dptr]),
     "brdfgpu_scene_dims": (C.c_int, [_V, iptr]),
+    "brdfgpu_shade_faces": (C.c_int, [_V, _V, dptr, dptr, C.c_int, C.c_int, dptr, C.c_int, dptr]),
     "brdfgpu_scene_create": (C.c_int, [_V, dptr, C.c_int, iptr, C.c_int, C.POINTER(_V), C.c_int, C.c_int, C.c_int, _V, dptr, C.POINTER(_V)]),
     "brdfgpu_scene_free": (None, [_V, _V]),
     "brdfgpu_scene_face_normals": (C.c_int, [_V, _V, dptr]),
@@ -235,6 +236,16 @@ class Scene:
     def image(self, k):
         out = np.empty((self.H, self.W, 3), dtype=np.uint8)
         self.ctx._ok(lib().brdfgpu_scene_image(self.ctx.handle, self.handle, k, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def shade_faces(self, eye, center, brdf, model=BLINN_PHONG, literal_cosln=True):
+        """Per-face (B, G, R) of the BRDF-shaded preview, glutcallbacks.cpp:346-445.  brdf: (3, 3) single or (nF, 3, 3)."""
+        brdf = _arr(brdf)
+        single = brdf.size == 9
+        assert single or brdf.size == 9 * self.nF
+        out = np.empty((self.nF, 3))
+        self.ctx._ok(lib().brdfgpu_shade_faces(self.ctx.handle, self.handle, _d(_arr(eye, 3)), _d(_arr(center, 3)), model,
+                                               int(single), _d(brdf), int(bool(literal_cosln)), _d(out)))
         return out
 
     def calc_pixel2surface(self, cam):

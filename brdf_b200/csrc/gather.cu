@@ -55,6 +55,7 @@ __device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a,
 struct V3 {
     double x, y, z;
 };
+constexpr double kPiShade = 3.1415926535897932384626433832795;  // CV_PI
 __device__ __forceinline__ double dot3(const V3& a, const V3& b) {
     return dadd(dadd(dmul(a.x, b.x), dmul(a.y, b.y)), dmul(a.z, b.z));
 }
@@ -127,6 +128,48 @@ __global__ void k_subtract_ambient(unsigned char* __restrict__ img, const unsign
         v -= d;
         v = v < 0 ? 0 : v;
         img[i] = (unsigned char)v;
+    }
+}
+
+// BRDF-shaded preview, one thread per face (glutcallbacks.cpp:346-445): the light sits at the eye,
+//   lightDir = normalize(eye - centroid), viewDir = normalize(eye - center), h = normalize(lightDir + viewDir)
+//   Blinn-Phong: kd*cosLN + ks*pow(N.h, n)         Phong: kd*cosLN + ks*((n+2)/(2 pi))*pow((float)(viewDir.R), n)
+// per colour channel (B, G, R).  LITERAL keeps the reference's cosLN, which indexes the normal with the
+// truncated dot product -- face_normals(i, (int)(N.lightDir)) -- instead of using the dot product itself.
+// Same single-rounding arithmetic as the gather; only pow() is the device libm's.
+template <bool LITERAL>
+__global__ void k_shade_faces(const double* __restrict__ V, const int* __restrict__ F, const double* __restrict__ FN, int nF,
+                              V3 eye, V3 center, int model, int single, const double* __restrict__ brdf,
+                              double* __restrict__ bgr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nF) return;
+    const V3 c = centroid_of(V, F, i);
+    const V3 N = load3(FN + 3l * i);
+    const V3 l = normalized(V3{dsub(eye.x, c.x), dsub(eye.y, c.y), dsub(eye.z, c.z)});
+    const V3 v = normalized(V3{dsub(eye.x, center.x), dsub(eye.y, center.y), dsub(eye.z, center.z)});
+    const double nl = dot3(N, l);
+    double cosLN = nl;
+    if (LITERAL) {
+        int col = (int)nl;  // |N.l| < 1 -> 0: the x component of the normal
+        col = col < 0 ? 0 : (col > 2 ? 2 : col);
+        cosLN = col == 0 ? N.x : (col == 1 ? N.y : N.z);
+    }
+    double t;  // the cosine under the power
+    if (model == 1) {
+        const V3 h = normalized(V3{dadd(l.x, v.x), dadd(l.y, v.y), dadd(l.z, v.z)});
+        t = dot3(N, h);
+    } else {
+        const double sf = -nl;  // P = -scale_factor * N, R = lightDir - 2*P
+        const V3 R{dsub(l.x, dmul(2.0, dmul(sf, N.x))), dsub(l.y, dmul(2.0, dmul(sf, N.y))), dsub(l.z, dmul(2.0, dmul(sf, N.z)))};
+        t = (double)(float)dot3(v, R);  // `float cosRV`, glutcallbacks.cpp:420
+    }
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const double* q = brdf + (single ? 3l * ch : 9l * i + 3l * ch);
+        const double kd = q[0], ks = q[1], n = q[2];
+        const double pw = pow(t, n);
+        const double spec = model == 1 ? dmul(ks, pw) : dmul(dmul(ks, ddiv(dadd(n, 2.0), dmul(2.0, kPiShade))), pw);
+        bgr[3l * i + ch] = dadd(dmul(kd, cosLN), spec);
     }
 }
 
@@ -427,6 +470,34 @@ extern "C" void brdfgpu_scene_free(brdfgpu_ctx* ctx, brdfgpu_scene* sc) {
     if (!sc) return;
     cudaFree(sc->V); cudaFree(sc->F); cudaFree(sc->FN); cudaFree(sc->img); cudaFree(sc->led);
     delete sc;
+}
+
+extern "C" int brdfgpu_shade_faces(brdfgpu_ctx* ctx, const brdfgpu_scene* sc, const double* eye, const double* center, int model,
+                                   int single, const double* brdf, int literal_cosln, double* bgr_out) {
+    ctx = ctx_or_default(ctx);
+    if (!ctx || !sc || !eye || !center || !brdf || !bgr_out || (model != 0 && model != 1)) return BRDFGPU_LM_ERROR;
+    const size_t nb = sizeof(double) * (single ? 9 : 9 * (size_t)sc->nF), no = sizeof(double) * 3 * (size_t)sc->nF;
+    double *d_brdf = nullptr, *d_out = nullptr;
+    BG_CUDA_OK(ctx, cudaMalloc(&d_brdf, nb));
+    cudaError_t e = cudaMalloc(&d_out, no);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_brdf, brdf, nb, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        const V3 ey{eye[0], eye[1], eye[2]}, ce{center[0], center[1], center[2]};
+        const int blocks = (sc->nF + 255) / 256;
+        if (literal_cosln) k_shade_faces<true><<<blocks, 256, 0, ctx->stream>>>(sc->V, sc->F, sc->FN, sc->nF, ey, ce, model, single, d_brdf, d_out);
+        else k_shade_faces<false><<<blocks, 256, 0, ctx->stream>>>(sc->V, sc->F, sc->FN, sc->nF, ey, ce, model, single, d_brdf, d_out);
+        ++ctx->launches;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(bgr_out, d_out, no, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_brdf);
+    cudaFree(d_out);
+    if (e != cudaSuccess) {
+        set_error(ctx, std::string("shade_faces: ") + cudaGetErrorString(e));
+        return BRDFGPU_LM_ERROR;
+    }
+    return 0;
 }
 
 extern "C" int brdfgpu_scene_dims(const brdfgpu_scene* sc, int* dims5) {

@@ -258,6 +258,18 @@ long brdfgpu_calc_brdf_equation(brdfgpu_ctx *ctx, const brdfgpu_scene *sc, const
 long brdfgpu_calc_brdf_equation_single(brdfgpu_ctx *ctx, const brdfgpu_scene *sc, const double *cam,
                                        int model, double *single_brdf, double *info, int *ret);
 
+/* The consumer of the fitted parameters: per-face colour of the BRDF-shaded preview
+ * (glutcallbacks.cpp:346-445, the loop its own comment wants moved "auf grafikkarte").  The light sits at
+ * the eye: lightDir = normalize(eye - centroid), viewDir = normalize(eye - center), h their normalised
+ * sum; Blinn-Phong kd*cosLN + ks*pow(N.h, n), Phong kd*cosLN + ks*((n+2)/(2 pi))*pow((float)(viewDir.R), n).
+ * brdf: single != 0 -> 3 channels x {kd, ks, n} (single_brdf), else nF x 3 x 3 (brdf_surfaces as
+ * brdfgpu_calc_brdf_equation writes them).  literal_cosln != 0 keeps the reference's cosLN =
+ * face_normals(i, (int)(N.lightDir)) (glutcallbacks.cpp:385: the dot product is used as a COLUMN INDEX, so
+ * cosLN is the normal's x component whenever |N.lightDir| < 1; indices are clamped to 0..2); 0 uses the dot
+ * product itself.  bgr_out: nF x 3 (B, G, R) fp64, the values the reference hands to glColor4d. */
+int brdfgpu_shade_faces(brdfgpu_ctx *ctx, const brdfgpu_scene *sc, const double *eye, const double *center,
+                        int model, int single, const double *brdf, int literal_cosln, double *bgr_out);
+
 /* ------------------------------------------------------------------------------------------------
  * 4b. The reference's input files (host code, usable without a GPU)
  * ------------------------------------------------------------------------------------------------ */

@@ -232,3 +232,49 @@ int oracle_gather(const double *V, const int *F, int nF, const double *cam, cons
     free(FN);
     return nfit;
 }
+
+/* glutcallbacks.cpp:346-445: the "show shaded BRDF" loop, one colour per face; the light source is the
+ * eye (:352-353).  Operation order as written there: centroid by three additions and a division
+ * (:356-366), lightDir / viewDir / h through Eigen's normalize() (:369-380), cwiseProduct().sum() dots,
+ * `float cosRV` (:420), colour = kd*cosLN + ks*[coef*]pow(t, n) with coef = (n+2)/(2*CV_PI) for Phong
+ * (:426-435 -- NOT the ((n+2)/2*pi) of BRDFFunc).  The literal cosLN of :385 passes the dot product as the
+ * column argument of face_normals(i, .): it truncates to 0 for every |dot| < 1. */
+void oracle_shade_faces(const double *V, const int *F, const double *FN, int nF, const double *eye,
+                        const double *center, int model, int single, const double *brdf, int literal,
+                        double *bgr)
+{
+    const double pi = 3.1415926535897932384626433832795;
+    int i, k, ch;
+    for (i = 0; i < nF; ++i) {
+        const double *N = FN + (size_t)i * 3;
+        double c[3], l[3], v[3], h[3], nl, cosLN, t;
+        centroid(V, F, i, c);
+        for (k = 0; k < 3; ++k) { l[k] = eye[k] - c[k]; v[k] = eye[k] - center[k]; }
+        normalize3(l);
+        normalize3(v);
+        nl = dot3(N, l);
+        cosLN = nl;
+        if (literal) {
+            int col = (int)nl;
+            if (col < 0) col = 0;
+            if (col > 2) col = 2;
+            cosLN = N[col];
+        }
+        if (model == 1) {
+            for (k = 0; k < 3; ++k) h[k] = l[k] + v[k];
+            normalize3(h);
+            t = dot3(N, h);
+        } else {
+            const double sf = -nl;
+            double R[3];
+            for (k = 0; k < 3; ++k) R[k] = l[k] - 2.0 * (sf * N[k]);
+            t = (double)(float)dot3(v, R);
+        }
+        for (ch = 0; ch < 3; ++ch) {
+            const double *q = brdf + (single ? (size_t)3 * ch : (size_t)9 * i + 3 * ch);
+            const double pw = pow(t, q[2]);
+            const double spec = (model == 1) ? q[1] * pw : (q[1] * ((q[2] + 2.0) / (2.0 * pi))) * pw;
+            bgr[(size_t)i * 3 + ch] = q[0] * cosLN + spec;
+        }
+    }
+}

@@ -92,6 +92,12 @@ int  oracle_gather(const double *V, const int *F, int nF, const double *cam, con
                    int *map, int *fit_face, int *fit_pixel,
                    double *phi, double *thetaDash, double *theta, double *I /* [3][nfit*nimg] */);
 
+/* BRDF-shaded preview colours per face, (B, G, R) x nF (glutcallbacks.cpp:346-445).  literal != 0 keeps the
+ * reference's cosLN = face_normals(i, (int)(N.lightDir)) (column index clamped to 0..2). */
+void oracle_shade_faces(const double *V, const int *F, const double *FN, int nF, const double *eye,
+                        const double *center, int model, int single, const double *brdf, int literal,
+                        double *bgr);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,3 +78,18 @@ def paint_model_radiance(images, gathered, params_bgr=((0.55, 0.30, 8.0), (0.45,
             q = np.clip(np.floor(255.0 * val + rng.uniform(-1, 1, val.shape)), 0, 255).astype(np.uint8)
             out[k][rows, cols, ch] = q
     return out
+
+
+def oracle_shade_faces(V, F, eye, center, brdf, model=1, literal=True):
+    lib = O.oracle()
+    nF = F.shape[0]
+    FN = np.empty((nF, 3))
+    lib.oracle_face_normals(O.as_d(V), O.as_i(F), nF, O.as_d(FN))
+    brdf = np.ascontiguousarray(brdf, dtype=np.float64)
+    out = np.empty((nF, 3))
+    eye, center = np.ascontiguousarray(eye, dtype=np.float64), np.ascontiguousarray(center, dtype=np.float64)
+    lib.oracle_shade_faces.restype = None
+    lib.oracle_shade_faces.argtypes = [O.dptr, O.iptr, O.dptr, C.c_int, O.dptr, O.dptr, C.c_int, C.c_int, O.dptr, C.c_int, O.dptr]
+    lib.oracle_shade_faces(O.as_d(V), O.as_i(F), O.as_d(FN), nF, O.as_d(eye), O.as_d(center), model, int(brdf.size == 9),
+                           O.as_d(brdf), int(bool(literal)), O.as_d(out))
+    return out

@@ -190,3 +190,23 @@ def test_scene_load_from_files_equals_scene_from_arrays(ctx, scene_inputs, tmp_p
     assert sc_n.image(3).tobytes() == imgs[3].tobytes()
     for sc in (sc_f, sc_a, sc_n):
         sc.free()
+
+
+@pytest.mark.parametrize("model", [A.BLINN_PHONG, A.PHONG])
+@pytest.mark.parametrize("literal", [True, False])
+def test_shade_faces_matches_oracle(ctx, scene_inputs, model, literal):
+    """BRDF-shaded preview colours (glutcallbacks.cpp:346-445): everything but pow() is the oracle's single
+    roundings, so the colours agree to a few ulp of the power (1e-12 relative), NaNs in the same places."""
+    V, F, imgs, dark, cams, W, H = scene_inputs
+    sc = ctx.scene(V, F, imgs, dark)
+    rng = np.random.default_rng(21)
+    eye, center = np.array([60.0, 40.0, 260.0]), np.array([0.0, 0.0, 0.0])
+    per_face = np.stack([rng.uniform(0, 1, (F.shape[0], 3)), rng.uniform(0, 1, (F.shape[0], 3)),
+                         rng.uniform(0.5, 40, (F.shape[0], 3))], axis=2)
+    for brdf in (np.array([[0.55, 0.30, 8.0], [0.45, 0.35, 14.0], [0.35, 0.25, 20.5]]), per_face):
+        got = sc.shade_faces(eye, center, brdf, model, literal)
+        want = S.oracle_shade_faces(V, F, eye, center, brdf, model, literal)
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        ok = ~np.isnan(want)
+        np.testing.assert_allclose(got[ok], want[ok], rtol=1e-12, atol=1e-300)
+    sc.free()
