@@ -253,15 +253,15 @@ def run_gpu_arm(args):
         kern_ms, launches_per_step, algo_bytes = e0.elapsed_time(e1) / reps, None, 24.0 * n
     achieved = algo_bytes / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": 38.2e6 if drive == A.DRIVE_PERSISTENT else None,
-                "traffic_source": "ncu --set full, profiles/r01_ncu_tables.md (dram read + write of one k_persistent_fit launch)",
+                "traffic": 40.98e6 if drive == A.DRIVE_PERSISTENT else None,
+                "traffic_source": "ncu --set full, profiles/r01_ncu_tables.md r01_persist_spec (dram read + write of one k_persistent_fit launch)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": kern_ms,
                 "sweeps_per_launch": passes / args.steps, "evaluations_per_launch": ref_passes / args.steps,
                 "swept_bytes_per_launch": 24.0 * n * passes / args.steps,
                 "note": "algorithmic bytes = 24 B/sample x the evaluations levmar counts for this trajectory (1 per fused "
                         "Jacobian, 1 per cost evaluation; SURVEY.md 8d).  At 10^6 samples/GPU the shard is held in shared "
                         "memory for the whole fit and the projected-gradient walk evaluates up to 8 trial points per sweep, "
-                        "so almost none of these bytes move through HBM (ncu: 38 MB of DRAM traffic per launch) and "
+                        "so almost none of these bytes move through HBM (ncu: 41 MB of DRAM traffic per launch) and "
                         "'achieved' is an algorithmic rate, not HBM utilisation; the kernel is bound by the FP64 pipe and "
                         "the per-evaluation exchange latency.  roofline_hbm is the HBM-resident regime (10^8 samples).  "
                         "Speculative Jacobians (fit_stats.spec_jac_*) answer some cost evaluations with a Jacobian sweep "
