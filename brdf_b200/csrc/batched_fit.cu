@@ -45,12 +45,24 @@ struct GroupEval {
 #ifndef BG_BATCH_LANE_WALK
 #define BG_BATCH_LANE_WALK 0
 #endif
-    // projected-gradient walk with BG_BATCH_LANE_WALK candidates per round, one per lane of the group
-    // (0 = the sequential walk of lm_engine.cuh); needs the samples in registers.  Bit-identical results
-    // (checked on the GPU), but measured slower for 65 536 x 64: 0 -> 16.8 ms, 2 -> 17.9, 4 -> 19.0,
-    // 8 -> 23.9: most walks of a small fit stop at their first candidates, the rest is wasted work.
-    static constexpr int kWalk = (S > 0) ? BG_BATCH_LANE_WALK : 0;
+    // Opt-in projected-gradient walk with one candidate per LANE of the group and a batch width that
+    // doubles 1, 2, 4, ... up to min(BG_BATCH_LANE_WALK, G) (0 = the sequential walk of lm_engine.cuh, the
+    // default); needs the samples in registers.  Motivation: 94 % of the cost evaluations of a batch are
+    // walk candidates (9.6 walks per fit, median length 3, but 2/3 of the candidates sit in walks longer
+    // than 100 -- levmar tries t, 0.9 t, ... down to 1e-18, 393 evaluations, when nothing is to be found).
+    // A round evaluates its candidates BG_BATCH_WALK_CHUNK at a time with the control code of the round spread
+    // over the lanes.  Bit-identical to the sequential walk (checked on the GPU for 64 / 40 / 16 samples per
+    // fit).  Measured on B200, 65 536 x 64 (profiles/r01_summary.md): warp instructions 9.7e9 -> 6.2e9, but
+    // the issue rate falls from 0.56 to 0.35 per cycle (the longer register-hungry rounds cost occupancy or
+    // spill: chunk 4 @ 80 regs 22.4 ms, chunk 4 @ 128 regs 21.8 ms, chunk 2 @ 80 regs 16.7 ms, chunk 2 @ 128
+    // regs 16.2 ms) against 16.5 ms sequential -- no gain worth a second code path, hence off by default.
+    // (A fixed width of 2 / 4 / 8 from the first round on: 17.9 / 19.0 / 23.9 ms.)
+    static constexpr int kWalk = (S > 0) ? ((BG_BATCH_LANE_WALK) < G ? (BG_BATCH_LANE_WALK) : G) : 0;
     static constexpr bool kLanePgWalk = kWalk > 0;
+#ifndef BG_BATCH_WALK_CHUNK
+#define BG_BATCH_WALK_CHUNK 2
+#endif
+    static constexpr int kWalkChunk = BG_BATCH_WALK_CHUNK;  // candidates evaluated together (2 x this many exp chains per lane)
     static constexpr int KB = kCostBatch;
     static constexpr int SR = S > 0 ? S : 1;
     double* s_pts;   // shared memory of this lane group: KB x 3 candidate points
@@ -122,12 +134,63 @@ struct GroupEval {
         return esq;
     }
 
-    // levmar's projected-gradient walk (lmbc_core.c:885-934), kWalk candidates per round: lane c of the
-    // group builds and projects candidate c and later applies levmar's tests to it; the evaluation of
-    // the round is one pass over the lane's samples for all candidates (kWalk x S independent exp
-    // chains); the first lane with an event, in levmar's order of checks, decides.  Same candidates and
-    // same arithmetic per candidate as the sequential walk; candidates past the deciding one are
-    // discarded and not counted.  Returns 0 = nothing found, 1 = found (pDp), 2 = non-finite residuals.
+    // residuals-squared sums of CH candidates (lanes c0 .. c0+CH-1 of the group hold them in my_q) over this
+    // lane's samples, reduced over the group; per candidate exactly the arithmetic of cost()
+    template <int CH>
+    __device__ __forceinline__ void walk_chunk(const CostPoint& my_q, int c0, int nc, double& e, bool& bad) const {
+        CostPoint q[CH];
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+            q[k].kd = __shfl_sync(mask, my_q.kd, c0 + k, G);
+            q[k].cks = __shfl_sync(mask, my_q.cks, c0 + k, G);
+            q[k].n = __shfl_sync(mask, my_q.n, c0 + k, G);
+        }
+        double esq[CH], nbad[CH];
+#pragma unroll
+        for (int k = 0; k < CH; ++k) esq[k] = nbad[k] = 0.0;
+#pragma unroll
+        for (int s = 0; s < SR; ++s) {
+            const int idx = s * G + lane;
+            if (idx < nper) {
+                double y[CH], pw[CH];
+                bool slow = false;
+#pragma unroll
+                for (int k = 0; k < CH; ++k) {
+                    y[k] = q[k].n * L[s];
+                    slow |= (c0 + k < nc) && needs_care(y[k]);
+                }
+                exp_core_n<CH>(y, pw);
+#pragma unroll
+                for (int k = 0; k < CH; ++k) {
+                    double r = x[s] - __fma_rn(q[k].kd, c[s], q[k].cks * pw[k]);
+                    if (slow && c0 + k < nc && needs_care(y[k])) r = residual_careful(q[k], c[s], traw[idx], x[s]);
+                    esq[k] = __fma_rn(r, r, esq[k]);
+                    nbad[k] += lm_finite(r) ? 0.0 : 1.0;
+                }
+            }
+        }
+#pragma unroll
+        for (int off = G / 2; off; off >>= 1) {
+#pragma unroll
+            for (int k = 0; k < CH; ++k) esq[k] += __shfl_xor_sync(mask, esq[k], off, G);
+        }
+        bool any_nonfinite = false;
+#pragma unroll
+        for (int k = 0; k < CH; ++k) any_nonfinite |= (c0 + k < nc) && !lm_finite(esq[k]);
+        if (any_nonfinite) {  // uniform within the group
+#pragma unroll
+            for (int k = 0; k < CH; ++k) nbad[k] = group_sum(nbad[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < CH; ++k)
+            if (lane == c0 + k) { e = esq[k]; bad = any_nonfinite && nbad[k] != 0.0; }
+    }
+
+    // levmar's projected-gradient walk (lmbc_core.c:885-934) with one candidate per lane of the group:
+    // lane c of a round builds and projects candidate c and later applies levmar's tests to it; the first
+    // lane with an event, in levmar's order of checks, decides.  Same candidates and same arithmetic per
+    // candidate as the sequential walk; candidates past the deciding one are discarded and not counted.
+    // Returns 0 = nothing found, 1 = found (pDp), 2 = non-finite residuals.
     __device__ __forceinline__ int pg_walk(const double* p, const double* g, double e_cur, const double* lb, const double* ub,
                                            double& t, double t0, int& gprevtaken, double* pDp, double* Dp, double& Dp_L2,
                                            double& e_new, int& nfev) const {
@@ -149,54 +212,15 @@ struct GroupEval {
                 box_project<3>(cand, box, 3);
                 my_q = make_cost_point(cand, model);
             }
-            CostPoint q[W];
-#pragma unroll
-            for (int k = 0; k < W; ++k) {
-                q[k].kd = __shfl_sync(mask, my_q.kd, k, G);
-                q[k].cks = __shfl_sync(mask, my_q.cks, k, G);
-                q[k].n = __shfl_sync(mask, my_q.n, k, G);
-            }
-            double esq[W], nbad[W];
-#pragma unroll
-            for (int k = 0; k < W; ++k) esq[k] = nbad[k] = 0.0;
-#pragma unroll
-            for (int s = 0; s < SR; ++s) {
-                const int idx = s * G + lane;
-                if (idx < nper) {
-                    double y[W], pw[W];
-                    bool slow = false;
-#pragma unroll
-                    for (int k = 0; k < W; ++k) {
-                        y[k] = q[k].n * L[s];
-                        slow |= (k < nc) && needs_care(y[k]);
-                    }
-                    exp_core_n<W>(y, pw);
-#pragma unroll
-                    for (int k = 0; k < W; ++k) {
-                        double e = x[s] - __fma_rn(q[k].kd, c[s], q[k].cks * pw[k]);
-                        if (slow && k < nc && needs_care(y[k])) e = residual_careful(q[k], c[s], traw[idx], x[s]);
-                        esq[k] = __fma_rn(e, e, esq[k]);
-                        nbad[k] += lm_finite(e) ? 0.0 : 1.0;
-                    }
-                }
-            }
-#pragma unroll
-            for (int off = G / 2; off; off >>= 1) {
-#pragma unroll
-                for (int k = 0; k < W; ++k) esq[k] += __shfl_xor_sync(mask, esq[k], off, G);
-            }
-            bool any_nonfinite = false;
-#pragma unroll
-            for (int k = 0; k < W; ++k) any_nonfinite |= (k < nc) && !lm_finite(esq[k]);
-            if (any_nonfinite) {  // uniform within the group
-#pragma unroll
-                for (int k = 0; k < W; ++k) nbad[k] = group_sum(nbad[k]);
-            }
             double e = 0.0;
             bool bad = false;
-#pragma unroll
-            for (int k = 0; k < W; ++k)
-                if (lane == k) { e = esq[k]; bad = nbad[k] != 0.0; }
+            if (nc == 1) {
+                walk_chunk<1>(my_q, 0, 1, e, bad);
+            } else if (nc == 2) {
+                walk_chunk<2>(my_q, 0, 2, e, bad);
+            } else {
+                for (int c0 = 0; c0 < nc; c0 += kWalkChunk) walk_chunk<kWalkChunk>(my_q, c0, nc, e, bad);
+            }
             double d[3], dl2 = 0.0, gTd = 0.0;
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
@@ -208,7 +232,7 @@ struct GroupEval {
             const bool fatal = mine && !lm_finite(e) && bad;
             const bool restart = mine && !fatal && gprevtaken && e <= e_cur + 2.0 * 0.99999 * gTd;
             const bool found = mine && !fatal && !restart && e <= e_cur + 2.0 * alpha * gTd;
-            const unsigned events = __ballot_sync(mask, fatal || restart || found) >> shift;
+            const unsigned events = (__ballot_sync(mask, fatal || restart || found) & mask) >> shift;
             const int src = events ? __ffs(events) - 1 : nc - 1;
             nfev += src + 1;
 #pragma unroll
