@@ -556,28 +556,76 @@ int model_jacobian(brdfgpu_ctx* ctx, const double* p, const double* angles_host,
 struct HostEval {
     static constexpr int kCostBatch = 1;
     static constexpr bool kLanePgWalk = false;
+    // Speculative Jacobians as in the persistent kernel (lm_engine.cuh "sites"): a K2 pass costs ~15 % more
+    // than a K3 pass and saves a whole pass (plus its launch and ticket round trip) when the point is taken.
+    // K2 and K3 sum ||e||^2 in different orders, so here the value may differ from K3's in the last bits.
+    static constexpr bool kSpecJac = true;
     brdfgpu_ctx* ctx;
     const brdfgpu_samples* s;
     double delta;
     int jkind;
     bool failed;
+    bool spec_on = true, memo_valid = false, sp_trial = false, sp_pg = false;
+    int sp_ls = 0;
+    double memo_p[3] = {0, 0, 0}, memo[NACC] = {0};
+    unsigned long long spec_issued = 0, spec_hits = 0, jac_launched = 0, cost_launched = 0;
 
-    void jac(const double* p, double* JtJ, double* Jte) {
+    bool run_jac(const double* p) {
         const bool pub = ctx->nranks == 1;
-        if (failed || launch_normal_eq(ctx, s, p, delta, jkind, pub) != 0 || fetch_result(ctx, NACC, pub) != 0) {
-            failed = true;
-            for (int i = 0; i < 9; ++i) JtJ[i] = NAN;
-            for (int i = 0; i < 3; ++i) Jte[i] = NAN;
-            return;
-        }
-        const double* r = ctx->h_result;
+        ++jac_launched;
+        if (failed || launch_normal_eq(ctx, s, p, delta, jkind, pub) != 0 || fetch_result(ctx, NACC, pub) != 0) failed = true;
+        return !failed;
+    }
+    static void unpack(const double* r, double* JtJ, double* Jte) {
         JtJ[0] = r[A00]; JtJ[1] = r[A01]; JtJ[2] = r[A02];
         JtJ[3] = r[A01]; JtJ[4] = r[A11]; JtJ[5] = r[A12];
         JtJ[6] = r[A02]; JtJ[7] = r[A12]; JtJ[8] = r[A22];
         Jte[0] = r[G0]; Jte[1] = r[G1]; Jte[2] = r[G2];
     }
+    void jac(const double* p, double* JtJ, double* Jte) {
+        if (memo_valid && memcmp(p, memo_p, sizeof(memo_p)) == 0) {
+            memo_valid = false;
+            ++spec_hits;
+            unpack(memo, JtJ, Jte);
+            return;
+        }
+        memo_valid = false;
+        if (!run_jac(p)) {
+            for (int i = 0; i < 9; ++i) JtJ[i] = NAN;
+            for (int i = 0; i < 3; ++i) Jte[i] = NAN;
+            return;
+        }
+        unpack(ctx->h_result, JtJ, Jte);
+    }
+    double cost_site(int site, const double* p, bool& bad) {
+        const bool spec = spec_on && (site == kSiteTrial ? sp_trial : site == kSitePgFirst ? sp_pg : site == sp_ls);
+        if (!spec) return cost(p, bad);
+        memo_valid = false;
+        if (!run_jac(p)) {
+            bad = true;
+            return NAN;
+        }
+        ++spec_issued;
+        for (int k = 0; k < NACC; ++k) memo[k] = ctx->h_result[k];
+        for (int i = 0; i < 3; ++i) memo_p[i] = p[i];
+        memo_valid = true;
+        const double esq = memo[ESQ];
+        bad = false;
+        if (!lm_finite(esq)) {
+            double cnt = 0.0;
+            if (count_bad(ctx, s, p, &cnt) != 0) failed = true;
+            bad = failed || cnt != 0.0;
+        }
+        return esq;
+    }
+    void trial_outcome(bool accepted) { sp_trial = accepted; }
+    void ls_outcome(int accepted_probe) { sp_ls = accepted_probe; }
+    void pg_outcome(bool took_first) { sp_pg = took_first; }
+    void ls_fallback(const double*, const double*, double, const double*, const double*) {}
+
     double cost(const double* p, bool& bad) {
         const bool pub = ctx->nranks == 1;
+        ++cost_launched;
         if (failed || launch_cost(ctx, s, p, pub) != 0 || fetch_result(ctx, 1, pub) != 0) {
             failed = true;
             bad = true;
@@ -1164,7 +1212,7 @@ struct GridEval {
 
     // lm_engine.cuh sites: 0 = the LM trial point, k >= 1 = line-search probe number k
     __device__ __forceinline__ double cost_site(int site, const double* p, bool& bad) {
-        const bool spec = spec_on && (site == kSiteTrial ? sp_trial : site == sp_ls);
+        const bool spec = spec_on && (site == kSiteTrial ? sp_trial : site == kSitePgFirst ? sp_pg : site == sp_ls);
         const bool fallback = hint_valid && !spec;
         hint_valid = false;
         if (spec) return cost_with_jac(p, bad);
@@ -1173,6 +1221,7 @@ struct GridEval {
     }
     __device__ __forceinline__ void trial_outcome(bool accepted) { sp_trial = accepted; }
     __device__ __forceinline__ void ls_outcome(int accepted_probe) { sp_ls = accepted_probe; }
+    __device__ __forceinline__ void pg_outcome(bool took_first) { sp_pg = took_first; }  // sequential form of the walk only
 
     __device__ __forceinline__ double count_bad(int k) {
         if (threadIdx.x == 0) s_req.cnt = k;
@@ -1580,11 +1629,17 @@ int global_fit(brdfgpu_ctx* ctx, const brdfgpu_samples* s, double* p, int m, con
         for (int i = 0; i < 9; ++i) JtJ[i] = h->JtJ[i];
     } else {
         HostEval ev{ctx, s, delta, jkind, false};
+        {
+            const char* sj = getenv("BRDFGPU_SPEC_JAC");
+            ev.spec_on = sj ? (atoi(sj) & 1) != 0 : true;
+        }
         if (unconstrained) ret = lm_der<3>(ev, 3, p, o, fit_info, JtJ);
         else ret = lm_bc_der<3>(ev, 3, p, lb ? lbs : nullptr, ub ? ubs : nullptr, dscl, o, fit_info, JtJ);
         if (ev.failed) return BRDFGPU_LM_ERROR;
-        ctx->fit_stats[0] = (unsigned long long)fit_info[8]; ctx->fit_stats[1] = (unsigned long long)fit_info[7];
-        ctx->fit_stats[2] = (unsigned long long)fit_info[7]; ctx->fit_stats[3] = ctx->fit_stats[4] = ctx->fit_stats[5] = ctx->fit_stats[6] = ctx->fit_stats[7] = 0;
+        ctx->fit_stats[0] = ev.jac_launched; ctx->fit_stats[1] = ev.cost_launched;  // passes over the samples
+        ctx->fit_stats[2] = ev.cost_launched;
+        for (int i = 3; i < 19; ++i) ctx->fit_stats[i] = 0;
+        ctx->fit_stats[19] = ev.spec_issued; ctx->fit_stats[20] = ev.spec_hits;
     }
     finish_info(info, fit_info, m, jkind, jac_mode == BRDFGPU_JAC_FD);
     if (covar) {  // lmbc_core.c:994-1002

@@ -231,6 +231,7 @@ struct LmCounters {
 
 // evaluation sites named to evaluators with kSpecJac: the LM trial point, or line-search probe k >= 2
 constexpr int kSiteTrial = 0;
+constexpr int kSitePgFirst = -1;  // first candidate of a projected-gradient walk (sequential form of the walk)
 template <class E, class = void>
 struct SpecJac : std::false_type {};
 template <class E>
@@ -244,6 +245,10 @@ BG_HDI double eval_cost_site(Eval& ev, int site, const double* p, bool& bad) {
 template <class Eval>
 BG_HDI void note_trial_outcome(Eval& ev, bool accepted) {
     if constexpr (SpecJac<Eval>::value) ev.trial_outcome(accepted);
+}
+template <class Eval>
+BG_HDI void note_pg_outcome(Eval& ev, bool took_first_candidate) {
+    if constexpr (SpecJac<Eval>::value) ev.pg_outcome(took_first_candidate);
 }
 template <class Eval>
 BG_HDI void note_ls_outcome(Eval& ev, int accepted_probe /* 0: the search failed */) {
@@ -305,14 +310,22 @@ struct PgBatch {
     double pts[MM], e;
     bool b;
     BG_HDI double* points(Eval&) { return pts; }
-    BG_HDI void run(Eval& ev, int, const double* dscl, int m) { e = eval_cost_scaled<MM>(ev, pts, dscl, m, b); }
+    BG_HDI void run(Eval& ev, int, const double* dscl, int m, bool first = false) {
+        if constexpr (SpecJac<Eval>::value) {  // (evaluators without speculation keep ONE inlined copy of cost())
+            if (first && !dscl) {
+                e = eval_cost_site(ev, kSitePgFirst, pts, b);
+                return;
+            }
+        }
+        e = eval_cost_scaled<MM>(ev, pts, dscl, m, b);
+    }
     BG_HDI double cost(Eval&, int) const { return e; }
     BG_HDI bool bad(Eval&, int) const { return b; }
 };
 template <int MM, class Eval>
 struct PgBatch<MM, Eval, true> {
     BG_HDI double* points(Eval& ev) { return ev.batch_points(); }
-    BG_HDI void run(Eval& ev, int cnt, const double* dscl, int m) { ev.cost_many(cnt, dscl, m); }
+    BG_HDI void run(Eval& ev, int cnt, const double* dscl, int m, bool = false) { ev.cost_many(cnt, dscl, m); }
     BG_HDI double cost(Eval& ev, int c) const { return ev.batch_cost(c); }
     BG_HDI bool bad(Eval& ev, int c) const { return ev.batch_bad(c); }
 };
@@ -589,6 +602,8 @@ BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double*
                 if (!pg_done) {
                 PgBatch<MM, Eval> batch;
                 double* pts = batch.points(ev);
+                constexpr bool kSites = SpecJac<Eval>::value;
+                [[maybe_unused]] bool first_round = true, took_first = false;
                 while (t > tming && !pg_done) {
                     int nc = 0;
                     double tt = t;
@@ -600,7 +615,7 @@ BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double*
                         ++nc;
                         tt *= beta;
                     }
-                    batch.run(ev, nc, dscl, m);
+                    batch.run(ev, nc, dscl, m, kSites && first_round);
                     bool restarted = false;
                     double tc = t;  // the same recurrence reproduces every candidate's t
                     for (int c = 0; c < nc; ++c, tc *= beta) {
@@ -624,11 +639,18 @@ BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double*
                             restarted = true;
                             break;
                         }
-                        if (e_new <= e_cur + 2.0 * alpha * gTd) { found = true; pg_done = true; break; }
+                        if (e_new <= e_cur + 2.0 * alpha * gTd) {
+                            found = true;
+                            pg_done = true;
+                            if constexpr (kSites) took_first = first_round && c == 0;
+                            break;
+                        }
                     }
+                    if constexpr (kSites) first_round = false;
                     if (!pg_done && !restarted) t = tt;
                     width = (2 * width < KB) ? 2 * width : KB;
                 }
+                if constexpr (kSites) note_pg_outcome(ev, took_first);
                 }
                 if (fatal) goto done;
                 if (!found) { gprevtaken = 0; break; }
