@@ -78,7 +78,56 @@ def main():
                       (name, preset_name, world, n_total, info[5], info[7], p, info[1], dt * 1e3), flush=True)
         s1.free()
         single.close()
+
+    # ---- the two modes that shard with NO data-path collective ----
+    # gather: views are independent units -> rank r takes views r, r+world, ...; the concatenation in view order
+    # must be the single-GPU gather of all views, byte for byte (results travel through the launcher only)
+    import scene_lib as S
+    W, H = 320, 240
+    V, F = S.height_field(40, 30, seed=5)
+    imgs, dark = S.random_images(16, W, H, seed=6)
+    cams = np.array([S.look_at_camera((40.0 * np.cos(a), 30.0 * np.sin(a), 250.0), (0.0, 0.0, 0.0), f=400.0, cx=160.0, cy=120.0)
+                     for a in np.linspace(0.0, 3.0, 2 * world + 1)])
+    sc = ctx.scene(V, F, imgs, dark)
+    mine = list(range(rank, len(cams), world))
+    g = sc.gather(cams[mine])
+    off = np.concatenate([[0], np.cumsum(g["nfit_cam"])])
+    parts = {v: {k: np.ascontiguousarray(g[k][off[j]:off[j + 1]]).tobytes() for k in ("fit_face", "fit_pixel", "phi", "thetaDash", "theta")}
+             for j, v in enumerate(mine)}
+    for j, v in enumerate(mine):
+        parts[v]["map"] = g["maps"][j].tobytes()
+        parts[v]["I"] = np.ascontiguousarray(g["I"][:, off[j]:off[j + 1]]).tobytes()
+    all_parts = [None] * world
+    dist.all_gather_object(all_parts, parts)
+    # batched fits: fit ids [lo, hi) per rank; the union must be the single-GPU batch
+    nfit = 1000 * world + 7
+    blo, bhi = rank * nfit // world, (rank + 1) * nfit // world
+    b = ctx.batch_synth(bhi - blo, 16, seed=9, first_fit=blo)
+    b.fit(A.REF_PERFACE)
+    bp, binfo, bret = b.results()
+    all_b = [None] * world
+    dist.all_gather_object(all_b, (bp.tobytes(), binfo.tobytes(), bret.tobytes()))
+    if rank == 0:
+        merged = {}
+        for d in all_parts:
+            merged.update(d)
+        gg = sc.gather(cams)
+        o = np.concatenate([[0], np.cumsum(gg["nfit_cam"])])
+        for v in range(len(cams)):
+            for k in ("fit_face", "fit_pixel", "phi", "thetaDash", "theta"):
+                assert merged[v][k] == np.ascontiguousarray(gg[k][o[v]:o[v + 1]]).tobytes(), (v, k)
+            assert merged[v]["map"] == gg["maps"][v].tobytes() and merged[v]["I"] == np.ascontiguousarray(gg["I"][:, o[v]:o[v + 1]]).tobytes()
+        print("gather sharded by view: %d views over %d ranks, %d fits, byte-identical to one GPU" % (len(cams), world, int(o[-1])), flush=True)
+        b1 = ctx.batch_synth(nfit, 16, seed=9)
+        b1.fit(A.REF_PERFACE)
+        p1, i1, r1 = b1.results()
+        assert b"".join(x[0] for x in all_b) == p1.tobytes() and b"".join(x[1] for x in all_b) == i1.tobytes()
+        assert b"".join(x[2] for x in all_b) == r1.tobytes()
+        print("batched fits sharded by fit id: %d fits over %d ranks, byte-identical to one GPU" % (nfit, world), flush=True)
+        b1.free()
         print("MULTI_GPU_OK world=%d" % world, flush=True)
+    b.free()
+    sc.free()
     dist.barrier()
     s.free()
     ctx.close()
