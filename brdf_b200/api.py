@@ -99,6 +99,8 @@ SIGNATURES = {
     "brdfgpu_read_png": (C.c_int, [C.c_char_p, _V, iptr, iptr]),
     "brdfgpu_scene_load": (C.c_int, [_V, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(_V), dptr]),
     "brdfgpu_scene_dims": (C.c_int, [_V, iptr]),
+    "brdfgpu_scene_set_gather_options": (C.c_int, [_V, _V, C.c_int, dptr, C.c_int]),
+    "brdfgpu_read_cal_kappa1": (C.c_int, [C.c_char_p, dptr]),
     "brdfgpu_shade_faces": (C.c_int, [_V, _V, dptr, dptr, C.c_int, C.c_int, dptr, C.c_int, dptr]),
     "brdfgpu_scene_create": (C.c_int, [_V, dptr, C.c_int, iptr, C.c_int, C.POINTER(_V), C.c_int, C.c_int, C.c_int, _V, dptr, C.POINTER(_V)]),
     "brdfgpu_scene_free": (None, [_V, _V]),
@@ -237,6 +239,11 @@ class Scene:
         out = np.empty((self.H, self.W, 3), dtype=np.uint8)
         self.ctx._ok(lib().brdfgpu_scene_image(self.ctx.handle, self.handle, k, out.ctypes.data_as(C.c_void_p)))
         return out
+
+    def set_gather_options(self, flags, kappa1=None):
+        """Options beyond the reference for later gathers: GATHER_DEPTH_TEST | GATHER_CULL_BACKFACES | GATHER_KAPPA1."""
+        k = _arr(kappa1)
+        self.ctx._ok(lib().brdfgpu_scene_set_gather_options(self.ctx.handle, self.handle, int(flags), _d(k), 0 if k is None else k.size))
 
     def shade_faces(self, eye, center, brdf, model=BLINN_PHONG, literal_cosln=True):
         """Per-face (B, G, R) of the BRDF-shaded preview, glutcallbacks.cpp:346-445.  brdf: (3, 3) single or (nF, 3, 3)."""
@@ -571,7 +578,18 @@ def solve_equation_single(phi, thetaDash, theta, inten, model=BLINN_PHONG):
     return ret, p, info
 
 
+GATHER_DEPTH_TEST, GATHER_CULL_BACKFACES, GATHER_KAPPA1 = 1, 2, 4
+
+
 # ---- the reference's input files (host code) ----
+def read_cal_kappa1(path):
+    k = C.c_double(0.0)
+    has = lib().brdfgpu_read_cal_kappa1(os.fsencode(path), C.byref(k))
+    if has < 0:
+        raise BrdfGpuError(lib().brdfgpu_last_error(None).decode())
+    return (k.value if has else None)
+
+
 def read_cal(path):
     """(cam16, mask of the fields present) -- CBRDFdata::LoadCameraParameters, brdfdata.cpp:149-247"""
     cam = np.zeros(16)

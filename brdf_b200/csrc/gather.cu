@@ -38,6 +38,8 @@ struct Trace {
 
 struct brdfgpu_scene {
     int nV = 0, nF = 0, nimg = 0, W = 0, H = 0;
+    int gather_flags = 0;          // BRDFGPU_GATHER_* (0 = the reference's behaviour)
+    std::vector<double> kappa1;    // per camera of the next gather calls (BRDFGPU_GATHER_KAPPA1)
     double* V = nullptr;           // nV x 3
     int* F = nullptr;              // nF x 3
     double* FN = nullptr;          // nF x 3
@@ -174,6 +176,70 @@ __global__ void k_shade_faces(const double* __restrict__ V, const int* __restric
 }
 
 __global__ void k_fill_int(int* p, long n, int value) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) p[i] = value;
+}
+
+// Projection with the options beyond the reference (the oracle's project_opts): back-face
+// culling N.(p - C) > 0, Tsai's radial distortion by five fixed-point steps, depth returned for the z-test.
+__device__ __forceinline__ int project_opts(const V3& c, const V3& N, const Camera& cam, double kappa1, int flags, int W, int H,
+                                            double* depth) {
+    const V3 d{dsub(c.x, cam.p.x), dsub(c.y, cam.p.y), dsub(c.z, cam.p.z)};
+    const double xc = dot3(d, cam.n), yc = dot3(d, cam.o), zc = dot3(d, cam.a);
+    if (!(zc > 0.0)) return -1;
+    if (flags & BRDFGPU_GATHER_CULL_BACKFACES) {
+        const V3 toward{-d.x, -d.y, -d.z};
+        if (!(dot3(N, toward) > 0.0)) return -1;
+    }
+    double u, v;
+    if (flags & BRDFGPU_GATHER_KAPPA1) {
+        const double xu = ddiv(dmul(cam.f, xc), zc), yu = ddiv(dmul(cam.f, yc), zc);
+        double xd = xu, yd = yu;
+#pragma unroll 1
+        for (int it = 0; it < 5; ++it) {
+            const double s = dadd(1.0, dmul(kappa1, dadd(dmul(xd, xd), dmul(yd, yd))));
+            xd = ddiv(xu, s);
+            yd = ddiv(yu, s);
+        }
+        u = dadd(cam.cx, dmul(cam.sx, xd));
+        v = dadd(cam.cy, yd);
+    } else {
+        u = dadd(cam.cx, ddiv(dmul(dmul(cam.sx, cam.f), xc), zc));
+        v = dadd(cam.cy, ddiv(dmul(cam.f, yc), zc));
+    }
+    if (!(u >= 0.0 && v >= 0.0 && u < (double)W && v < (double)H)) return -1;
+    *depth = zc;
+    return (int)v * W + (int)u;
+}
+
+// one thread per (view, face) with options: pass 0 records the pixel and (depth test) the nearest depth per pixel
+// (zc > 0, so the bits of the double order like the value); pass 1 lets the faces at that depth claim the pixel
+__global__ void k_project_opts(const double* __restrict__ V, const int* __restrict__ F, const double* __restrict__ FN, int nF,
+                               const double* __restrict__ cams, const double* __restrict__ kappa1, int flags, int ncam, int W,
+                               int H, int pass, int* __restrict__ pix, unsigned long long* __restrict__ zbits,
+                               unsigned long long* __restrict__ depth, int* __restrict__ maps) {
+    const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long)ncam * nF) return;
+    const int v = (int)(e / nF), face = (int)(e % nF);
+    if (pass == 0) {
+        const Camera cam = load_camera(cams + 16l * v);
+        double z = 0.0;
+        const int px = project_opts(centroid_of(V, F, face), load3(FN + 3l * face), cam, kappa1 ? kappa1[v] : 0.0, flags, W, H, &z);
+        pix[e] = px;
+        if (px < 0) return;
+        if (flags & BRDFGPU_GATHER_DEPTH_TEST) {
+            const unsigned long long zb = (unsigned long long)__double_as_longlong(z);
+            zbits[e] = zb;
+            atomicMin(depth + (long)v * W * H + px, zb);
+        } else {
+            atomicMax(maps + (long)v * W * H + px, face);
+        }
+    } else {
+        const int px = pix[e];
+        if (px >= 0 && zbits[e] == depth[(long)v * W * H + px]) atomicMax(maps + (long)v * W * H + px, face);
+    }
+}
+
+__global__ void k_fill_u64(unsigned long long* p, long n, unsigned long long value) {
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) p[i] = value;
 }
 
@@ -352,8 +418,39 @@ static int gather_device(brdfgpu_ctx* ctx, const brdfgpu_scene* sc, const double
     tr.mark("8 cudaMalloc + H2D of the cameras");
 
     k_fill_int<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(g->maps, npix, -1);
-    k_project<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(sc->V, sc->F, sc->nF, g->cams, ncam, sc->W, sc->H,
-                                                                        g->pix, g->maps);
+    if (sc->gather_flags == 0) {
+        k_project<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(sc->V, sc->F, sc->nF, g->cams, ncam, sc->W, sc->H,
+                                                                            g->pix, g->maps);
+    } else {
+        const int flags = sc->gather_flags;
+        double* d_kappa = nullptr;
+        unsigned long long *d_zbits = nullptr, *d_depth = nullptr;
+        if (flags & BRDFGPU_GATHER_KAPPA1) {
+            if ((int)sc->kappa1.size() != ncam) {
+                set_error(ctx, "gather: BRDFGPU_GATHER_KAPPA1 needs one kappa1 per camera (brdfgpu_scene_set_gather_options)");
+                return BRDFGPU_LM_ERROR;
+            }
+            BG_CUDA_OK(ctx, cudaMalloc(&d_kappa, sizeof(double) * ncam));
+            BG_CUDA_OK(ctx, cudaMemcpyAsync(d_kappa, sc->kappa1.data(), sizeof(double) * ncam, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        if (flags & BRDFGPU_GATHER_DEPTH_TEST) {
+            BG_CUDA_OK(ctx, cudaMalloc(&d_zbits, sizeof(unsigned long long) * total));
+            BG_CUDA_OK(ctx, cudaMalloc(&d_depth, sizeof(unsigned long long) * npix));
+            k_fill_u64<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_depth, npix, ~0ull);
+            ++ctx->launches;
+        }
+        const unsigned blocks = (unsigned)((total + 255) / 256);
+        k_project_opts<<<blocks, 256, 0, ctx->stream>>>(sc->V, sc->F, sc->FN, sc->nF, g->cams, d_kappa, flags, ncam, sc->W, sc->H, 0,
+                                                        g->pix, d_zbits, d_depth, g->maps);
+        if (flags & BRDFGPU_GATHER_DEPTH_TEST) {
+            k_project_opts<<<blocks, 256, 0, ctx->stream>>>(sc->V, sc->F, sc->FN, sc->nF, g->cams, d_kappa, flags, ncam, sc->W, sc->H, 1,
+                                                            g->pix, d_zbits, d_depth, g->maps);
+            ++ctx->launches;
+        }
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        cudaFree(d_kappa); cudaFree(d_zbits); cudaFree(d_depth);
+        BG_CUDA_OK(ctx, e);
+    }
     k_owner_count<<<nblocks, kScanThreads, 0, ctx->stream>>>(g->pix, g->maps, sc->nF, sc->W, sc->H, total, g->block_sums);
     k_scan_block_sums<<<1, kScanThreads, 0, ctx->stream>>>(g->block_sums, nblocks);
     k_owner_scatter<<<nblocks, kScanThreads, 0, ctx->stream>>>(g->pix, g->maps, sc->nF, sc->W, sc->H, total, g->block_sums,
@@ -497,6 +594,24 @@ extern "C" int brdfgpu_shade_faces(brdfgpu_ctx* ctx, const brdfgpu_scene* sc, co
         set_error(ctx, std::string("shade_faces: ") + cudaGetErrorString(e));
         return BRDFGPU_LM_ERROR;
     }
+    return 0;
+}
+
+extern "C" int brdfgpu_scene_set_gather_options(brdfgpu_ctx* ctx, brdfgpu_scene* sc, int flags, const double* kappa1, int ncam) {
+    ctx = ctx_or_default(ctx);
+    if (!ctx || !sc) return BRDFGPU_LM_ERROR;
+    const int known = BRDFGPU_GATHER_DEPTH_TEST | BRDFGPU_GATHER_CULL_BACKFACES | BRDFGPU_GATHER_KAPPA1;
+    if (flags & ~known) {
+        set_error(ctx, "scene_set_gather_options: unknown flag");
+        return BRDFGPU_LM_ERROR;
+    }
+    if ((flags & BRDFGPU_GATHER_KAPPA1) && (!kappa1 || ncam < 1)) {
+        set_error(ctx, "scene_set_gather_options: BRDFGPU_GATHER_KAPPA1 needs kappa1[ncam]");
+        return BRDFGPU_LM_ERROR;
+    }
+    sc->gather_flags = flags;
+    sc->kappa1.clear();
+    if (flags & BRDFGPU_GATHER_KAPPA1) sc->kappa1.assign(kappa1, kappa1 + ncam);
     return 0;
 }
 

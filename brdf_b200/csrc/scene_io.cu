@@ -45,9 +45,11 @@ static bool read_whole_file(const char* path, std::vector<unsigned char>* out, b
 static const char* const kCalFields[BRDFGPU_CAM_SZ] = {"cx", "cy", "f",  "sx", "nx", "ny", "nz", "ox",
                                                        "oy", "oz", "ax", "ay", "az", "px", "py", "pz"};
 
-static int parse_cal(const std::vector<unsigned char>& buf, double* cam) {
+static int parse_cal(const std::vector<unsigned char>& buf, double* cam, double* kappa1 = nullptr, int* has_kappa1 = nullptr) {
     int seen = 0;
     for (int i = 0; i < BRDFGPU_CAM_SZ; ++i) cam[i] = 0.0;
+    if (kappa1) *kappa1 = 0.0;
+    if (has_kappa1) *has_kappa1 = 0;
     const size_t n = buf.size();
     size_t it = 0;
     while (it < n && buf[it] != 0) {
@@ -58,6 +60,10 @@ static int parse_cal(const std::vector<unsigned char>& buf, double* cam) {
             if (it < n && buf[it] == '>') ++it;
             for (; it < n && buf[it] != '<'; ++it) value += (char)buf[it];
             if (it < n && buf[it] == '<') ++it;
+            if (kappa1 && name == "kappa1") {
+                *kappa1 = atof(value.c_str());
+                if (has_kappa1) *has_kappa1 = 1;
+            }
             for (int k = 0; k < BRDFGPU_CAM_SZ; ++k)
                 if (name == kCalFields[k]) {
                     cam[k] = atof(value.c_str());  // brdfdata.cpp:197
@@ -271,6 +277,16 @@ extern "C" int brdfgpu_read_cal(const char* path, double* cam16) {
     std::vector<unsigned char> buf;
     if (!cam16 || !read_whole_file(path, &buf, ctx)) return BRDFGPU_LM_ERROR;
     return parse_cal(buf, cam16);
+}
+
+extern "C" int brdfgpu_read_cal_kappa1(const char* path, double* kappa1) {
+    brdfgpu_ctx* ctx = nullptr;
+    std::vector<unsigned char> buf;
+    if (!kappa1 || !read_whole_file(path, &buf, ctx)) return BRDFGPU_LM_ERROR;
+    double cam[BRDFGPU_CAM_SZ];
+    int has = 0;
+    parse_cal(buf, cam, kappa1, &has);
+    return has;
 }
 
 extern "C" int brdfgpu_read_obj(const char* path, double* V, int* F, int* nV, int* nF) {

@@ -242,6 +242,19 @@ long brdfgpu_gather(brdfgpu_ctx *ctx, const brdfgpu_scene *sc, const double *cam
                     long capacity, int *maps, long *nfit_cam, int *fit_face, int *fit_pixel,
                     double *phi, double *thetaDash, double *theta, double *I);
 
+/* Options BEYOND the reference for every later gather / pixel-map call on this scene.
+ * The reference maps a pixel to the LAST face whose centroid lands there, whether or not that face is
+ * visible (no depth test, brdfdata.cpp:676-677), and never reads kappa1 (brdfdata.cpp:195-247); flags = 0
+ * (the default) keeps exactly that.
+ *   DEPTH_TEST      the pixel goes to the face whose centroid is nearest to the camera (equal depth: last face)
+ *   CULL_BACKFACES  faces seen from behind (N.(p_cam - centroid) <= 0) are not mapped
+ *   KAPPA1          Tsai's radial distortion Xu = Xd (1 + kappa1 r^2), one kappa1 per camera of the gather call
+ *                   (the <kappa1> tag of the .cal files: brdfgpu_read_cal_kappa1), five fixed-point steps */
+#define BRDFGPU_GATHER_DEPTH_TEST 1
+#define BRDFGPU_GATHER_CULL_BACKFACES 2
+#define BRDFGPU_GATHER_KAPPA1 4
+int brdfgpu_scene_set_gather_options(brdfgpu_ctx *ctx, brdfgpu_scene *sc, int flags, const double *kappa1, int ncam);
+
 /* Gather that stays on the device and hands the samples straight to the fit stages. */
 int brdfgpu_gather_resident(brdfgpu_ctx *ctx, const brdfgpu_scene *sc, const double *cams, int ncam,
                             int model, int channel, brdfgpu_samples **global_out,
@@ -279,6 +292,10 @@ int brdfgpu_shade_faces(brdfgpu_ctx *ctx, const brdfgpu_scene *sc, const double 
  * other tag ignored, as the reference ignores them).  Returns a bit mask of the fields that were present
  * (0xffff = all 16; absent fields are 0.0) or BRDFGPU_LM_ERROR when the file cannot be read. */
 int brdfgpu_read_cal(const char *path, double *cam16);
+
+/* The <kappa1> value of a .cal file, which the reference never reads (for BRDFGPU_GATHER_KAPPA1).
+ * Returns 1 when the tag is present (else 0 and *kappa1 = 0) or BRDFGPU_LM_ERROR. */
+int brdfgpu_read_cal_kappa1(const char *path, double *kappa1);
 
 /* CBRDFdata::LoadModel -> igl::readOBJ (brdfdata.cpp:289-312): `v x y z` rows and the vertex index of the
  * first three corners of every `f` (v, v/vt, v//vn, v/vt/vn; 1-based or negative = relative), 0-based in F.

@@ -112,6 +112,80 @@ static int project_tsai(const double *c, const double *cam, int W, int H, int *c
     return 1;
 }
 
+/* ---- options beyond the reference; flags == 0 is the reference's behaviour ----
+ *   ORACLE_GATHER_DEPTH_TEST      a pixel goes to the face whose centroid is nearest to the camera (smallest
+ *                                 zc = (C - p).a; equal depths: the later face), not simply to the last face
+ *   ORACLE_GATHER_CULL_BACKFACES  faces seen from behind, N.(p - C) <= 0, are not mapped
+ *   ORACLE_GATHER_KAPPA1          Tsai's radial lens distortion: the undistorted sensor point (Xu, Yu) =
+ *                                 (f xc/zc, f yc/zc) is pulled to (Xd, Yd) with Xu = Xd (1 + kappa1 r^2),
+ *                                 r^2 = Xd^2 + Yd^2, by FIVE fixed-point steps from (Xu, Yu); pixel =
+ *                                 (cx + sx Xd, cy + Yd)
+ * Returns 1, the pixel and the depth when the face is mapped. */
+static int project_opts(const double *c, const double *N, const double *cam, double kappa1, int flags,
+                        int W, int H, int *col, int *row, double *depth)
+{
+    double d[3], xc, yc, zc, u, v;
+    d[0] = c[0] - cam[CAM_P + 0];
+    d[1] = c[1] - cam[CAM_P + 1];
+    d[2] = c[2] - cam[CAM_P + 2];
+    xc = dot3(d, cam + CAM_N);
+    yc = dot3(d, cam + CAM_O);
+    zc = dot3(d, cam + CAM_A);
+    if (!(zc > 0.0)) return 0;
+    if (flags & ORACLE_GATHER_CULL_BACKFACES) {
+        double toward[3];
+        toward[0] = -d[0]; toward[1] = -d[1]; toward[2] = -d[2];
+        if (!(dot3(N, toward) > 0.0)) return 0;
+    }
+    if (flags & ORACLE_GATHER_KAPPA1) {
+        const double xu = (cam[CAM_F] * xc) / zc, yu = (cam[CAM_F] * yc) / zc;
+        double xd = xu, yd = yu;
+        int it;
+        for (it = 0; it < 5; ++it) {
+            const double s = 1.0 + kappa1 * (xd * xd + yd * yd);
+            xd = xu / s;
+            yd = yu / s;
+        }
+        u = cam[CAM_CX] + cam[CAM_SX] * xd;
+        v = cam[CAM_CY] + yd;
+    } else {
+        u = cam[CAM_CX] + ((cam[CAM_SX] * cam[CAM_F]) * xc) / zc;
+        v = cam[CAM_CY] + (cam[CAM_F] * yc) / zc;
+    }
+    if (!(u >= 0.0 && v >= 0.0 && u < (double)W && v < (double)H)) return 0;
+    *col = (int)u;
+    *row = (int)v;
+    *depth = zc;
+    return 1;
+}
+
+int oracle_calc_pixel2surface_opts(const double *V, const int *F, const double *FN, int nF, const double *cam,
+                                   double kappa1, int flags, int W, int H, int *map)
+{
+    int i, hits = 0;
+    double *zbuf = NULL;
+    for (i = 0; i < W * H; ++i) map[i] = -1;
+    if (flags & ORACLE_GATHER_DEPTH_TEST) {
+        zbuf = (double *)malloc((size_t)W * H * sizeof(double));
+        if (!zbuf) return -1;
+    }
+    for (i = 0; i < nF; ++i) {
+        double c[3], z;
+        int col, row;
+        centroid(V, F, i, c);
+        if (!project_opts(c, FN + (size_t)i * 3, cam, kappa1, flags, W, H, &col, &row, &z)) continue;
+        ++hits;
+        if (zbuf) {
+            const int px = row * W + col;
+            if (map[px] >= 0 && zbuf[px] < z) continue; /* something nearer is already there */
+            zbuf[px] = z;
+        }
+        map[row * W + col] = i;
+    }
+    free(zbuf);
+    return hits;
+}
+
 /* brdfdata.cpp:629-681: faces in index order, last writer wins, map starts at -1.
  * Returns the number of faces that landed inside the image. */
 int oracle_calc_pixel2surface(const double *V, const int *F, int nF, const double *cam,
@@ -277,4 +351,38 @@ void oracle_shade_faces(const double *V, const int *F, const double *FN, int nF,
             bgr[(size_t)i * 3 + ch] = q[0] * cosLN + spec;
         }
     }
+}
+
+/* oracle_gather with the options of oracle_calc_pixel2surface_opts */
+int oracle_gather_opts(const double *V, const int *F, int nF, const double *cam, double kappa1, int flags,
+                       const double *led, const unsigned char *const *images, int nimg, int W, int H,
+                       int *map, int *fit_face, int *fit_pixel,
+                       double *phi, double *thetaDash, double *theta, double *I)
+{
+    double *FN;
+    int i, ch, nfit = 0;
+
+    FN = (double *)malloc((size_t)nF * 3 * sizeof(double));
+    if (!FN) return -1;
+    oracle_face_normals(V, F, nF, FN);
+    if (oracle_calc_pixel2surface_opts(V, F, FN, nF, cam, kappa1, flags, W, H, map) < 0) { free(FN); return -1; }
+
+    for (i = 0; i < nF; ++i) {
+        double c[3], z;
+        int col, row;
+        centroid(V, F, i, c);
+        if (!project_opts(c, FN + (size_t)i * 3, cam, kappa1, flags, W, H, &col, &row, &z)) continue;
+        if (map[row * W + col] != i) continue;
+        fit_face[nfit] = i;
+        fit_pixel[nfit] = row * W + col;
+        oracle_cos_ln(V, F, FN, led, nimg, i, phi + (size_t)nfit * nimg);
+        oracle_cos_nh(V, F, FN, led, nimg, cam, i, thetaDash + (size_t)nfit * nimg);
+        oracle_cos_rv(V, F, FN, led, nimg, cam, i, theta + (size_t)nfit * nimg);
+        for (ch = 0; ch < 3; ++ch)
+            oracle_intensities_from_pixel(images, nimg, W, H, col, row, ch,
+                                          I + (size_t)ch * nF * nimg + (size_t)nfit * nimg);
+        ++nfit;
+    }
+    free(FN);
+    return nfit;
 }

@@ -92,6 +92,17 @@ int  oracle_gather(const double *V, const int *F, int nF, const double *cam, con
                    int *map, int *fit_face, int *fit_pixel,
                    double *phi, double *thetaDash, double *theta, double *I /* [3][nfit*nimg] */);
 
+/* Options beyond the reference (depth test, back-face culling, Tsai kappa1); flags 0 == the functions above */
+#define ORACLE_GATHER_DEPTH_TEST 1
+#define ORACLE_GATHER_CULL_BACKFACES 2
+#define ORACLE_GATHER_KAPPA1 4
+int  oracle_calc_pixel2surface_opts(const double *V, const int *F, const double *FN, int nF, const double *cam,
+                                    double kappa1, int flags, int W, int H, int *map);
+int  oracle_gather_opts(const double *V, const int *F, int nF, const double *cam, double kappa1, int flags,
+                        const double *led, const unsigned char *const *images, int nimg, int W, int H,
+                        int *map, int *fit_face, int *fit_pixel,
+                        double *phi, double *thetaDash, double *theta, double *I);
+
 /* BRDF-shaded preview colours per face, (B, G, R) x nF (glutcallbacks.cpp:346-445).  literal != 0 keeps the
  * reference's cosLN = face_normals(i, (int)(N.lightDir)) (column index clamped to 0..2). */
 void oracle_shade_faces(const double *V, const int *F, const double *FN, int nF, const double *eye,

@@ -93,3 +93,26 @@ def oracle_shade_faces(V, F, eye, center, brdf, model=1, literal=True):
     lib.oracle_shade_faces(O.as_d(V), O.as_i(F), O.as_d(FN), nF, O.as_d(eye), O.as_d(center), model, int(brdf.size == 9),
                            O.as_d(brdf), int(bool(literal)), O.as_d(out))
     return out
+
+
+DEPTH_TEST, CULL_BACKFACES, KAPPA1 = 1, 2, 4
+
+
+def oracle_gather_opts(V, F, cam, led, images, W, H, flags, kappa1=0.0):
+    """oracle_gather with the options beyond the reference (depth test / back-face culling / Tsai kappa1)."""
+    lib = O.oracle()
+    nF, nimg = F.shape[0], len(images)
+    ptrs = (C.c_void_p * nimg)(*[im.ctypes.data for im in images])
+    m = np.empty((H, W), dtype=np.int32)
+    fit_face, fit_pixel = np.empty(nF, dtype=np.int32), np.empty(nF, dtype=np.int32)
+    phi, td, th = (np.empty((nF, nimg)) for _ in range(3))
+    inten = np.empty((3, nF, nimg))
+    cam = np.ascontiguousarray(cam, dtype=np.float64)
+    led = np.ascontiguousarray(led, dtype=np.float64)
+    lib.oracle_gather_opts.restype = C.c_int
+    lib.oracle_gather_opts.argtypes = [O.dptr, O.iptr, C.c_int, O.dptr, C.c_double, C.c_int, O.dptr, C.POINTER(C.c_void_p), C.c_int,
+                                       C.c_int, C.c_int, O.iptr, O.iptr, O.iptr, O.dptr, O.dptr, O.dptr, O.dptr]
+    n = lib.oracle_gather_opts(O.as_d(V), O.as_i(F), nF, O.as_d(cam), float(kappa1), int(flags), O.as_d(led), ptrs, nimg, W, H,
+                               O.as_i(m), O.as_i(fit_face), O.as_i(fit_pixel), O.as_d(phi), O.as_d(td), O.as_d(th), O.as_d(inten))
+    return dict(nfit=n, map=m, fit_face=fit_face[:n], fit_pixel=fit_pixel[:n], phi=phi[:n], thetaDash=td[:n],
+                theta=th[:n], I=inten[:, :n])

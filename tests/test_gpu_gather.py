@@ -210,3 +210,38 @@ def test_shade_faces_matches_oracle(ctx, scene_inputs, model, literal):
         ok = ~np.isnan(want)
         np.testing.assert_allclose(got[ok], want[ok], rtol=1e-12, atol=1e-300)
     sc.free()
+
+
+@pytest.mark.parametrize("flags", [1, 2, 3, 4, 7])
+def test_gather_options_bit_exact(ctx, flags):
+    """Options beyond the reference (depth test, back-face culling, Tsai kappa1) against the
+    oracle's statement of the same rules: pixel maps, owners, cosines and intensities as bytes.  A scene with a
+    hidden second sheet, so the depth test has something to decide; flags = 0 afterwards is the reference again."""
+    W, H = 320, 240
+    V, F = S.height_field(40, 30, seed=3)
+    V2, F2 = S.height_field(40, 30, seed=4, z0=-40.0)
+    F = np.ascontiguousarray(np.concatenate([F, F2 + V.shape[0]]).astype(np.int32))
+    V = np.ascontiguousarray(np.concatenate([V, V2]))
+    imgs, dark = S.random_images(16, W, H, seed=5)
+    cams = np.array([S.look_at_camera((30.0, 20.0, 260.0), (0.0, 0.0, 0.0), f=400.0, cx=160.0, cy=120.0),
+                     S.look_at_camera((-60.0, 10.0, 240.0), (5.0, -5.0, 0.0), f=380.0, cx=150.0, cy=125.0)])
+    kappa = np.array([2.5e-6, -1.0e-6])
+    sc = ctx.scene(V, F, imgs)
+    sc.set_gather_options(flags, kappa if flags & A.GATHER_KAPPA1 else None)
+    g = sc.gather(cams)
+    off = np.concatenate([[0], np.cumsum(g["nfit_cam"])])
+    for v in range(2):
+        w = S.oracle_gather_opts(V, F, cams[v], S.led_table(), imgs, W, H, flags, kappa[v])
+        assert int(g["nfit_cam"][v]) == w["nfit"]
+        assert g["maps"][v].tobytes() == w["map"].tobytes()
+        sl = slice(off[v], off[v + 1])
+        for k in ("fit_face", "fit_pixel", "phi", "thetaDash", "theta"):
+            assert np.ascontiguousarray(g[k][sl]).tobytes() == w[k].tobytes(), (v, k)
+        assert np.ascontiguousarray(g["I"][:, sl]).tobytes() == np.ascontiguousarray(w["I"]).tobytes()
+        assert sc.calc_pixel2surface(cams[v]).tobytes() == w["map"].tobytes() if not (flags & A.GATHER_KAPPA1) else True
+    sc.set_gather_options(0)
+    w0 = S.oracle_gather(V, F, cams[0], S.led_table(), imgs, W, H)
+    assert sc.calc_pixel2surface(cams[0]).tobytes() == w0["map"].tobytes()
+    with pytest.raises(A.BrdfGpuError):
+        sc.set_gather_options(A.GATHER_KAPPA1)          # kappa1 values missing
+    sc.free()
