@@ -40,10 +40,15 @@ for name in ("cup", "bunny"):
     ms, g = wall(lambda: scene.gather(cams))
     print("| %s | gather, %d view(s) (pixel map + cosines + intensities to the host) | %.2f | %d fits, %d samples per channel |" %
           (name, len(cams), ms, g["nfit"], g["phi"].size))
-    ms, (s, b, nfit) = wall(lambda: scene.gather_resident(cams, model=A.BLINN_PHONG, channel=0, want_global=True, want_batch=True))
+    def resident():
+        s, b, nfit = scene.gather_resident(cams, model=A.BLINN_PHONG, channel=0, want_global=True, want_batch=True)
+        s.free(); b.free()      # (handles left to the garbage collector pile up device memory and skew later timings)
+        return nfit
+    ms, nfit = wall(resident)
     print("| %s | gather, results resident on the device | %.2f | |" % (name, ms))
     ms, (nf, surf) = wall(lambda: scene.calc_brdf_equation(sc["cams"][0]))
     print("| %s | CalcBRDFEquation: gather + %d per-face fits (3 channels) | %.2f | %.3g fits/s |" % (name, 3 * nf, ms, 3 * nf / ms * 1e3))
     ms, out = wall(lambda: scene.calc_brdf_equation_single(sc["cams"][0]))
     print("| %s | CalcBRDFEquation_SingleBRDF: gather + 3 global fits | %.2f | stop reasons %s |" % (name, ms, [int(v[6]) for v in out[2]]))
+    scene.free()
 ctx.close()
