@@ -665,7 +665,7 @@ constexpr int kPersistThreads = BG_PERSIST_THREADS;  // 512: 16 warps, <= 128 re
 constexpr int kMaxPersistBlocks = 160;  // >= SM count (148 on B200)
 constexpr int kGridCostBatch = 8;       // trial points per cost_many() sweep (<= NACC)
 constexpr int NSUM = NACC + 1;          // sums of the widest sweep: a Jacobian at one point + the cost at another
-constexpr long long kSpinCycles = 6000000000LL;  // ~3 s at 2 GHz, then the fit is abandoned
+constexpr long long kSpinCycles = 20000000000LL;  // ~10 s at 2 GHz, then the fit is abandoned (ranks may enter seconds apart on a cold box)
 
 // A cell is two 64-bit words {value.lo | tag << 32, value.hi | tag << 32}; each word is one scalar
 // access, so a reader that finds the current tag in both has the whole double -- the data is its own
