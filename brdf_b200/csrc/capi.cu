@@ -60,6 +60,16 @@ extern "C" int brdfgpu_create(int device, brdfgpu_ctx** out) {
         if (!(flags & cudaDeviceLmemResizeToMax) && cudaSetDeviceFlags(flags | cudaDeviceLmemResizeToMax) != cudaSuccess)
             cudaGetLastError();  // an application that fixed its flags earlier keeps them
     }
+    if (e == cudaSuccess) {
+        // the gather allocates its temporaries with cudaMallocAsync: let the device's default pool keep them
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+            unsigned long long keep = ~0ull;
+            if (cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) != cudaSuccess) cudaGetLastError();
+        } else {
+            cudaGetLastError();
+        }
+    }
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->coop, cudaDevAttrCooperativeLaunch, device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);

@@ -3,6 +3,7 @@
     python profiles/prof_kernels.py fit 1000000       the persistent global fit
     python profiles/prof_kernels.py batch 65536 64    the batched per-face fits
     python profiles/prof_kernels.py gather            the gather on a synthetic scene
+    python profiles/prof_kernels.py gather_scene      the gather on the reference's bunny scene (13 views), tests/_scenes
 """
 import os
 import sys
@@ -76,4 +77,12 @@ elif what == "gather":
     for _ in range(2):
         g = sc.gather(cams)
     print(g["nfit"])
+elif what == "gather_scene":
+    import real_scenes as R
+    sc = R.load("bunny")
+    scene = ctx.scene(sc["V"], sc["F"], sc["imgs"], dark=sc["dark"])
+    for _ in range(2):
+        s, b, nfit = scene.gather_resident(sc["cams"], want_global=True, want_batch=False)
+        s.free()
+    print(nfit)
 ctx.close()
