@@ -133,7 +133,7 @@ struct GlobalFitOut {
     int ret;
     unsigned peer_epoch;  // exchange tag after the fit (all ranks advance in lock step)
     int aborted;          // an exchange partner never delivered: the fit was abandoned
-    unsigned jac_passes, cost_passes, cost_points, spec_issued, spec_hits;
+    unsigned jac_passes, cost_passes, cost_points, spec_issued, spec_hits, creep_fused;
     long long cyc_sweep, cyc_exchange, cyc_total;  // SM cycles of CTA 0 / thread 0
     long long cyc_x[4];
     long long cyc_ctl[7];  // control-code cycles by the kind of sweep they led to (SweepKind)

@@ -622,6 +622,7 @@ struct HostEval {
     void ls_outcome(int accepted_probe) { sp_ls = accepted_probe; }
     void pg_outcome(bool took_first) { sp_pg = took_first; }
     void ls_fallback(const double*, const double*, double, const double*, const double*) {}
+    void iteration_hint(const double*, const double*, const double*, double, const double*, const double*) {}
 
     double cost(const double* p, bool& bad) {
         const bool pub = ctx->nranks == 1;
@@ -664,7 +665,7 @@ struct HostEval {
 constexpr int kPersistThreads = BG_PERSIST_THREADS;  // 512: 16 warps, <= 128 registers per thread
 constexpr int kMaxPersistBlocks = 160;  // >= SM count (148 on B200)
 constexpr int kGridCostBatch = 8;       // trial points per cost_many() sweep (<= NACC)
-constexpr int NSUM = NACC + 1;          // sums of the widest sweep: a Jacobian at one point + the cost at another
+constexpr int NSUM = NACC + 2;          // sums of the widest sweep: a Jacobian at one point + the cost at two others
 constexpr long long kSpinCycles = 20000000000LL;  // ~10 s at 2 GHz, then the fit is abandoned (ranks may enter seconds apart on a cold box)
 
 // A cell is two 64-bit words {value.lo | tag << 32, value.hi | tag << 32}; each word is one scalar
@@ -712,7 +713,7 @@ __device__ __forceinline__ unsigned next_tag(unsigned e) { return e + 1u ? e + 1
 enum SweepKind { kQuit = 0, kSweepJacForward, kSweepJacCentral, kSweepJacAnalytic, kSweepCost, kSweepMany, kSweepBad };
 struct SweepRequest {
     int kind, cnt;  // cnt: trial points of kSweepMany / index of the point of kSweepBad
-    int extra;      // Jacobian sweeps: also ||x - f||^2 at pts[0] (sum number NACC)
+    int extra;      // Jacobian sweeps: also ||x - f||^2 at pts[0] (.. pts[extra-1]), sums number NACC (, NACC+1)
     PassParams q;   // Jacobian sweeps
     CostPoint pts[kGridCostBatch];
 };
@@ -745,6 +746,8 @@ __shared__ double s_cand_cost[kGridCostBatch];
 __shared__ int s_cand_bad[kGridCostBatch];
 __shared__ double s_memo[3 + NACC];  // speculative Jacobian: the point, then A00..A22, G0..G2, ||e||^2 (GridEval::cost_site)
 __shared__ double s_hint[3];         // first projected-gradient candidate announced by the line search (GridEval::ls_fallback)
+__shared__ double s_ahead[6 + 4];    // announced before the trial: the lambda = 0.1 probe, the walk's first candidate;
+                                     // then the probe's evaluated point and ||e||^2 (GridEval::iteration_hint)
 __shared__ long long s_cyc[6];  // thread 0: cycles in sweeps, exchanges, and the 4 exchange phases
 __shared__ long long s_ctl[8];  // thread 0: control-code cycles by the kind of request they led to; [7] = time of the last exchange end
 // TMA ring of the streamed part (sample sets beyond on-chip residency): 3 stages x 48 KB
@@ -858,14 +861,14 @@ __device__ __forceinline__ void all_reduce(const double* acc, long long t_sweep_
 // ||e||^2 of a Jacobian sweep is accumulated in exactly the order the cost sweeps use (two running sums
 // over alternate pairs, resident part first, then the streamed part), so a trial point evaluated by a
 // Jacobian sweep (speculation, GridEval::cost_site) gets the very bits a cost sweep would give it.
-// EXTRA: the same sweep also sums ||x - f||^2 at the trial point s_req.pts[0] (sum number NACC), again
-// in the order of the cost sweeps.
-template <int JAC, bool EXTRA>
+// EXTRA (0, 1, 2): the same sweep also sums ||x - f||^2 at the trial points s_req.pts[0 .. EXTRA-1] (sums number
+// NACC, NACC+1), again in the order of the cost sweeps.
+template <int JAC, int EXTRA>
 __device__ __noinline__ void jac_sweep() {
     const long long t0 = clock64();
     const PassParams q = s_req.q;
-    const CostPoint xq = s_req.pts[0];
-    double xa = 0.0, xb = 0.0;
+    const CostPoint xq = s_req.pts[0], zq = s_req.pts[EXTRA > 1 ? 1 : 0];
+    double xa = 0.0, xb = 0.0, za = 0.0, zb = 0.0;
     const unsigned sc = s_ctx.sc, sl = s_ctx.sl, sx = s_ctx.sx;
     const int res_pairs = s_ctx.res_pairs;
     const long res_first = s_ctx.res_first;
@@ -885,21 +888,23 @@ __device__ __noinline__ void jac_sweep() {
         acc[ESQ] = esq_b;
         accumulate_jac_pair<JAC>(q, s_req.q, d, m, y, traw, 2 * (res_first + i2), acc);
         esq_b = acc[ESQ];
-        if (EXTRA) accumulate_cost_2pairs(xq, c, l, x, 2 * (res_first + i), d, m, y, 2 * (res_first + i2), traw, &xa, &xb);
+        if (EXTRA >= 1) accumulate_cost_2pairs(xq, c, l, x, 2 * (res_first + i), d, m, y, 2 * (res_first + i2), traw, &xa, &xb);
+        if (EXTRA >= 2) accumulate_cost_2pairs(zq, c, l, x, 2 * (res_first + i), d, m, y, 2 * (res_first + i2), traw, &za, &zb);
     }
     if (i < res_pairs) {
         const double2 c = lds_pair(sc, i), l = lds_pair(sl, i), x = lds_pair(sx, i);
         acc[ESQ] = esq_a;
         accumulate_jac_pair<JAC>(q, s_req.q, c, l, x, traw, 2 * (res_first + i), acc);
         esq_a = acc[ESQ];
-        if (EXTRA) accumulate_cost_pair(xq, c, l, x, traw, 2 * (res_first + i), &xa);
+        if (EXTRA >= 1) accumulate_cost_pair(xq, c, l, x, traw, 2 * (res_first + i), &xa);
+        if (EXTRA >= 2) accumulate_cost_pair(zq, c, l, x, traw, 2 * (res_first + i), &za);
     }
     acc[ESQ] = esq_a + esq_b;
-    double extra[1] = {xa + xb};
+    double extra[2] = {xa + xb, za + zb};
     if (s_ctx.stream_first < (s_ctx.v.n >> 1)) {
         const SampleView v = s_ctx.v;
         const double esq_res = acc[ESQ];
-        double sa = 0.0, sb = 0.0, ya = 0.0, yb = 0.0;
+        double sa = 0.0, sb = 0.0, ya = 0.0, yb = 0.0, wa = 0.0, wb = 0.0;
         const long seq = s_ring.stream(v, s_ctx.stream_first, s_ring_seq,
             [&](double2 c0, double2 l0, double2 x0, long i0, double2 c1, double2 l1, double2 x1, long i1, int valid) {
                 if (valid >= 1) {
@@ -912,27 +917,34 @@ __device__ __noinline__ void jac_sweep() {
                     accumulate_jac_pair<JAC>(q, s_req.q, c1, l1, x1, v.traw, i1, acc);
                     sb = acc[ESQ];
                 }
-                if (EXTRA) {
+                if (EXTRA >= 1) {
                     if (valid == 2) accumulate_cost_2pairs(xq, c0, l0, x0, i0, c1, l1, x1, i1, v.traw, &ya, &yb);
                     else if (valid == 1) accumulate_cost_pair(xq, c0, l0, x0, v.traw, i0, &ya);
+                }
+                if (EXTRA >= 2) {
+                    if (valid == 2) accumulate_cost_2pairs(zq, c0, l0, x0, i0, c1, l1, x1, i1, v.traw, &wa, &wb);
+                    else if (valid == 1) accumulate_cost_pair(zq, c0, l0, x0, v.traw, i0, &wa);
                 }
             });
         acc[ESQ] = esq_res + (sa + sb);
         extra[0] += ya + yb;
+        extra[1] += wa + wb;
         __syncthreads();  // everybody has read s_ring_seq
         if (threadIdx.x == 0) s_ring_seq = seq;
     }
     if ((s_ctx.v.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
         const long j = s_ctx.v.n - 1;
         accumulate_jac<JAC>(s_req.q, s_ctx.v.c[j], s_ctx.v.L[j], s_ctx.v.x[j], traw, j, acc);
-        if (EXTRA) accumulate_cost(xq, s_ctx.v.c[j], s_ctx.v.L[j], s_ctx.v.x[j], traw, j, extra);
+        if (EXTRA >= 1) accumulate_cost(xq, s_ctx.v.c[j], s_ctx.v.L[j], s_ctx.v.x[j], traw, j, &extra[0]);
+        if (EXTRA >= 2) accumulate_cost(zq, s_ctx.v.c[j], s_ctx.v.L[j], s_ctx.v.x[j], traw, j, &extra[1]);
     }
-    if (EXTRA) {
-        double all[NSUM];
+    if (EXTRA >= 1) {
+        double all[NACC + EXTRA];
 #pragma unroll
         for (int k = 0; k < NACC; ++k) all[k] = acc[k];
         all[NACC] = extra[0];
-        all_reduce<NSUM>(all, t0);
+        if (EXTRA >= 2) all[NACC + EXTRA - 1] = extra[1];
+        all_reduce<NACC + EXTRA>(all, t0);
     } else {
         all_reduce<NACC>(acc, t0);
     }
@@ -1074,9 +1086,15 @@ __device__ __noinline__ void many_sweep() {
 
 __device__ __forceinline__ void run_sweep(int kind) {
     switch (kind) {
-        case kSweepJacForward: if (s_req.extra) jac_sweep<kJacForward, true>(); else jac_sweep<kJacForward, false>(); break;
-        case kSweepJacCentral: if (s_req.extra) jac_sweep<kJacCentral, true>(); else jac_sweep<kJacCentral, false>(); break;
-        case kSweepJacAnalytic: if (s_req.extra) jac_sweep<kJacAnalytic, true>(); else jac_sweep<kJacAnalytic, false>(); break;
+        case kSweepJacForward:
+            if (s_req.extra == 2) jac_sweep<kJacForward, 2>(); else if (s_req.extra) jac_sweep<kJacForward, 1>(); else jac_sweep<kJacForward, 0>();
+            break;
+        case kSweepJacCentral:
+            if (s_req.extra == 2) jac_sweep<kJacCentral, 2>(); else if (s_req.extra) jac_sweep<kJacCentral, 1>(); else jac_sweep<kJacCentral, 0>();
+            break;
+        case kSweepJacAnalytic:
+            if (s_req.extra == 2) jac_sweep<kJacAnalytic, 2>(); else if (s_req.extra) jac_sweep<kJacAnalytic, 1>(); else jac_sweep<kJacAnalytic, 0>();
+            break;
         case kSweepCost: cost_sweep(); break;
         case kSweepMany: many_sweep(); break;
         default: bad_sweep(); break;
@@ -1112,7 +1130,8 @@ struct GridEval {
     int model, jkind;
     double delta;
     unsigned jac_passes, cost_passes, cost_points, spec_issued, spec_hits;
-    bool spec_on, fuse_on, width_on, memo_valid, sp_trial, sp_pg, hint_valid;
+    bool spec_on, fuse_on, width_on, memo_valid, sp_trial, sp_pg, hint_valid, ahead_valid, probe_known, sp_clip;
+    unsigned creep_fused;
     int sp_ls;    // probe number the last line search accepted (0: it failed)
     int pg_last;  // candidates the last projected-gradient walk consumed
 
@@ -1180,10 +1199,9 @@ struct GridEval {
         return esq;
     }
 
-    // ||x - f(p)||^2 and, in the same sweep, the Jacobian (and cost) at the announced first candidate of the
+    // ||x - f(p)||^2 and, in the same sweep, the Jacobian (and cost) at the announced first candidate h of the
     // projected-gradient walk that follows if this last line-search probe is not accepted
-    __device__ __forceinline__ double cost_and_fallback_jac(const double* p, bool& bad) {
-        const double h[3] = {s_hint[0], s_hint[1], s_hint[2]};
+    __device__ __forceinline__ double cost_and_jac_at(const double* p, const double* h, bool& bad) {
         if (threadIdx.x == 0) s_req.pts[0] = make_cost_point(p, model);
         post_jac(make_pass_params(h, model, delta, jkind), 1);
         const double esq = s_res[NACC];
@@ -1210,13 +1228,69 @@ struct GridEval {
         hint_valid = true;
     }
 
+    // Before every trial evaluation the engine announces what the iteration would evaluate next if the trial is
+    // rejected: the line search's probe at lambda = 0.1 and the first candidate p - t g of the projected-gradient
+    // walk (g = -J^T e).  A fit that creeps repeats one pattern -- LM step rejected, first backtrack clipped to
+    // lambda = 0.1, that probe already below the minimum step and not accepted, first candidate of the walk
+    // taken -- and all three points of it are known here, so ONE sweep evaluates the costs of the trial point
+    // and of the probe and the Jacobian (and cost) of the candidate: the iteration needs no second sweep.
+    __device__ __forceinline__ void iteration_hint(const double* probe, const double* p, const double* Jte, double t,
+                                                   const double* lb, const double* ub) {
+        const double g[3] = {-Jte[0], -Jte[1], -Jte[2]};
+        double cand[3];
+        pg_candidate(p, g, t, Box{lb, ub}, cand);
+        __syncwarp();
+        if (threadIdx.x == 0) {
+            s_ahead[0] = probe[0]; s_ahead[1] = probe[1]; s_ahead[2] = probe[2];
+            s_ahead[3] = cand[0]; s_ahead[4] = cand[1]; s_ahead[5] = cand[2];
+        }
+        __syncwarp();
+        ahead_valid = true;
+    }
+
+    // costs at the trial point p and at the announced probe, Jacobian (and cost) at the announced candidate
+    __device__ __forceinline__ double cost_probe_and_candidate(const double* p, bool& bad) {
+        const double probe[3] = {s_ahead[0], s_ahead[1], s_ahead[2]}, cand[3] = {s_ahead[3], s_ahead[4], s_ahead[5]};
+        if (threadIdx.x == 0) {
+            s_req.pts[0] = make_cost_point(p, model);
+            s_req.pts[1] = make_cost_point(probe, model);
+        }
+        post_jac(make_pass_params(cand, model, delta, jkind), 2);
+        const double esq = s_res[NACC], esq_probe = s_res[NACC + 1];
+        keep_jac(cand);
+        __syncwarp();
+        if (threadIdx.x == 0) { s_ahead[6] = probe[0]; s_ahead[7] = probe[1]; s_ahead[8] = probe[2]; s_ahead[9] = esq_probe; }
+        __syncwarp();
+        probe_known = lm_finite(esq_probe);
+        ++creep_fused;
+        bad = false;
+        if (!lm_finite(esq)) bad = count_bad(0) != 0.0;
+        return esq;
+    }
+
     // lm_engine.cuh sites: 0 = the LM trial point, k >= 1 = line-search probe number k
     __device__ __forceinline__ double cost_site(int site, const double* p, bool& bad) {
         const bool spec = spec_on && (site == kSiteTrial ? sp_trial : site == kSitePgFirst ? sp_pg : site == sp_ls);
         const bool fallback = hint_valid && !spec;
         hint_valid = false;
+        if (site == kSiteTrial) {
+            probe_known = false;
+            // the last iteration crept (search failed at its lambda = 0.1 probe, walk took its first candidate)
+            if (fuse_on && !spec && ahead_valid && sp_ls == 0 && sp_pg && sp_clip) return cost_probe_and_candidate(p, bad);
+        } else if (site == 2) {
+            sp_clip = ahead_valid && same_bits(p[0], s_ahead[0]) && same_bits(p[1], s_ahead[1]) && same_bits(p[2], s_ahead[2]);
+            ahead_valid = false;
+            if (probe_known && same_bits(p[0], s_ahead[6]) && same_bits(p[1], s_ahead[7]) && same_bits(p[2], s_ahead[8])) {
+                probe_known = false;  // evaluated together with the trial point
+                bad = false;
+                return s_ahead[9];
+            }
+        }
         if (spec) return cost_with_jac(p, bad);
-        if (fallback) return cost_and_fallback_jac(p, bad);
+        if (fallback && !memo_is(s_hint)) {
+            const double h[3] = {s_hint[0], s_hint[1], s_hint[2]};
+            return cost_and_jac_at(p, h, bad);
+        }
         return cost(p, bad);
     }
     __device__ __forceinline__ void trial_outcome(bool accepted) { sp_trial = accepted; }
@@ -1422,7 +1496,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_persistent_fit(SampleVie
     ev.spec_on = (spec.spec_jac & 1) != 0;
     ev.fuse_on = (spec.spec_jac & 2) != 0;
     ev.width_on = (spec.spec_jac & 4) != 0;
-    ev.memo_valid = ev.sp_trial = ev.sp_pg = ev.hint_valid = false;
+    ev.memo_valid = ev.sp_trial = ev.sp_pg = ev.hint_valid = ev.ahead_valid = ev.probe_known = ev.sp_clip = false;
+    ev.creep_fused = 0u;
     ev.sp_ls = ev.pg_last = 0;
     double p[3], info[10], JtJ[9];
     for (int i = 0; i < 3; ++i) p[i] = spec.p[i];
@@ -1441,6 +1516,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_persistent_fit(SampleVie
         out->cost_points = ev.cost_points;
         out->spec_issued = ev.spec_issued;
         out->spec_hits = ev.spec_hits;
+        out->creep_fused = ev.creep_fused;
         out->cyc_sweep = s_cyc[0];
         out->cyc_exchange = s_cyc[1];
         out->cyc_total = clock64() - t_start;
@@ -1622,7 +1698,7 @@ int global_fit(brdfgpu_ctx* ctx, const brdfgpu_samples* s, double* p, int m, con
         ctx->fit_stats[7] = (unsigned long long)h->cyc_total;
         for (int i = 0; i < 4; ++i) ctx->fit_stats[8 + i] = (unsigned long long)h->cyc_x[i];
         for (int i = 0; i < 7; ++i) ctx->fit_stats[12 + i] = (unsigned long long)h->cyc_ctl[i];
-        ctx->fit_stats[19] = h->spec_issued; ctx->fit_stats[20] = h->spec_hits;
+        ctx->fit_stats[19] = h->spec_issued; ctx->fit_stats[20] = h->spec_hits; ctx->fit_stats[21] = h->creep_fused;
         ret = h->ret;
         for (int i = 0; i < 3; ++i) p[i] = h->p[i];
         for (int i = 0; i < 10; ++i) fit_info[i] = h->info[i];

@@ -56,6 +56,15 @@ constexpr int kLmError = -1;
 // misc.h:68 (not fabs: identical -0.0 / NaN behaviour)
 BG_HDI double lm_abs(double v) { return (v >= 0.0) ? v : -v; }
 BG_HDI bool lm_finite(double v) { return (v - v) == 0.0; }  // false for NaN and +-Inf
+// y + a*x with ONE spelling per target (device: fused; host: levmar's two roundings), for points that are formed
+// at two places and compared bit for bit (the line-search probe and its announcement)
+BG_HDI double lm_axpy(double a, double x, double y) {
+#ifdef __CUDA_ARCH__
+    return __fma_rn(a, x, y);
+#else
+    return y + a * x;
+#endif
+}
 
 struct LmOptions {
     double tau, eps1, eps2, eps2_sq, eps3;
@@ -254,6 +263,14 @@ template <class Eval>
 BG_HDI void note_ls_outcome(Eval& ev, int accepted_probe /* 0: the search failed */) {
     if constexpr (SpecJac<Eval>::value) ev.ls_outcome(accepted_probe);
 }
+// Before the LM trial point is evaluated: what the iteration evaluates next if the trial is rejected -- the line
+// search's probe at lambda = 0.1 (its first backtrack when the step was far too long) and, from p, J^T e and the
+// step length t, the first candidate of the projected-gradient walk.
+template <class Eval>
+BG_HDI void note_iteration_hint(Eval& ev, const double* probe, const double* p, const double* Jte, double t,
+                                const double* lb, const double* ub) {
+    if constexpr (SpecJac<Eval>::value) ev.iteration_hint(probe, p, Jte, t, lb, ub);
+}
 // The line search is about to evaluate its LAST probe (lambda is already below the minimum step): if
 // that probe is not accepted the search fails and the projected-gradient walk starts from p with
 // gradient g at step length t -- its first candidate is known now, so the evaluator may evaluate it
@@ -374,7 +391,7 @@ BG_HDI int lm_line_search(Eval& ev, int m, const double* xc, double fc, const do
     lambda = 1.0;
 
     for (int it = kLsItMax; it-- > 0;) {
-        LM_FOR_REV(i) xnew[i] = xc[i] + lambda * step[i];
+        LM_FOR_REV(i) xnew[i] = lm_axpy(lambda, step[i], xc[i]);
         box_project<MM>(xnew, box, m);
 
         // levmar's first probe (lambda = 1) is usually the very point whose rejection started this
@@ -524,6 +541,23 @@ BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double*
             if (Dp_L2 <= o.eps2_sq * p_L2) { stop = 2; break; }
             if (Dp_L2 >= (p_L2 + o.eps2) / (kEpsilon * kEpsilon)) { stop = 4; break; }
 
+            bool t0_known = false;
+            if constexpr (SpecJac<Eval>::value) {
+                if (!dscl) {
+                    // first step length of a projected-gradient walk from here (:876-879), needed early for the hint
+                    tmp = 0.0;
+                    LM_FOR(i) tmp += Jte[i] * Jte[i];
+                    tmp = sqrt(tmp);
+                    tmp = 100.0 / (1.0 + tmp);
+                    t0 = (tmp <= tini) ? tmp : tini;
+                    t0_known = true;
+                    const double lambda01 = 1.0 * 0.1;  // the line search's lambda after one clipped backtrack
+                    double probe[MM];
+                    LM_FOR_REV(i) probe[i] = lm_axpy(lambda01, Dp[i], p[i]);
+                    box_project<MM>(probe, box, m);
+                    note_iteration_hint(ev, probe, p, Jte, gprevtaken ? t : t0, lb, ub);
+                }
+            }
             e_new = eval_trial_scaled<MM>(ev, pDp, dscl, m, bad);
             ++cnt.nfev;
             // :748 -- overflow of the sum alone is tolerated, non-finite residuals are not
@@ -555,12 +589,13 @@ BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double*
                 Jte[i] = -Jte[i];
                 gTd += Jte[i] * Dp[i];
             }
-            // first step length of a projected-gradient walk from here (:876-879)
-            tmp = 0.0;
-            LM_FOR(i) tmp += Jte[i] * Jte[i];
-            tmp = sqrt(tmp);
-            tmp = 100.0 / (1.0 + tmp);
-            t0 = (tmp <= tini) ? tmp : tini;
+            if (!t0_known) {  // first step length of a projected-gradient walk from here (:876-879)
+                tmp = 0.0;
+                LM_FOR(i) tmp += Jte[i] * Jte[i];
+                tmp = sqrt(tmp);
+                tmp = 100.0 / (1.0 + tmp);
+                t0 = (tmp <= tini) ? tmp : tini;
+            }
             if (gTd <= -rho * pow(Dp_L2, kPow / 2.0)) {
                 const double steptl = 1e3 * sqrt(DBL_EPSILON);
                 tmp = sqrt(p_L2);

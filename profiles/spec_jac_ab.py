@@ -52,9 +52,9 @@ for name, n, start, preset, kw in cases:
         assert m[2].tobytes() == a[2].tobytes() and m[3].tobytes() == a[3].tobytes(), mode
     same = a[2].tobytes() == b[2].tobytes() and a[3].tobytes() == b[3].tobytes() and a[1] == b[1]
     sa, sb = a[4], b[4]
-    print("%-28s off %.3f ms (%d jac + %d cost sweeps) | on %.3f ms (%d jac + %d cost sweeps, %d speculated, %d hits) | it %d nfev %d stop %d | identical=%s"
+    print("%-28s off %.3f ms (%d jac + %d cost sweeps) | on %.3f ms (%d jac + %d cost sweeps, %d speculated, %d hits, %d creep-fused) | it %d nfev %d stop %d | identical=%s"
           % (name, a[0], sa["jac_passes"], sa["cost_passes"], b[0], sb["jac_passes"], sb["cost_passes"], sb["spec_jac_issued"],
-             sb["spec_jac_hits"], b[3][5], b[3][7], b[3][6], same))
+             sb["spec_jac_hits"], sb["creep_fused"], b[3][5], b[3][7], b[3][6], same))
     if not same:
         print("   off:", a[2], a[3]); print("   on: ", b[2], b[3])
     s.free()
