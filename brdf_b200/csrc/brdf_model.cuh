@@ -63,7 +63,7 @@ BG_HDI PassParams make_pass_params(const double* p, int model, double delta, int
         dj = lm_abs(dj);
         if (dj < delta) dj = delta;
         d[j] = dj;
-        q.inv[j] = half / dj;
+        q.inv[j] = (dj == 1.0) ? half : half / dj;  // (delta = 1, the reference's global preset: no fp64 division on the control path)
     }
     q.kd_hi = p[0] + d[0]; q.ks_hi = p[1] + d[1]; q.n_hi = p[2] + d[2];
     q.kd_lo = p[0] - d[0]; q.ks_lo = p[1] - d[1]; q.n_lo = p[2] - d[2];

@@ -622,7 +622,9 @@ struct HostEval {
     void ls_outcome(int accepted_probe) { sp_ls = accepted_probe; }
     void pg_outcome(bool took_first) { sp_pg = took_first; }
     void ls_fallback(const double*, const double*, double, const double*, const double*) {}
-    void iteration_hint(const double*, const double*, const double*, double, const double*, const double*) {}
+    void probe_hint(const double*) {}
+    bool wants_candidate_hint() const { return false; }
+    void candidate_hint(const double*, const double*, double, const double*, const double*) {}
 
     double cost(const double* p, bool& bad) {
         const bool pub = ctx->nranks == 1;
@@ -747,7 +749,7 @@ __shared__ int s_cand_bad[kGridCostBatch];
 __shared__ double s_memo[3 + NACC];  // speculative Jacobian: the point, then A00..A22, G0..G2, ||e||^2 (GridEval::cost_site)
 __shared__ double s_hint[3];         // first projected-gradient candidate announced by the line search (GridEval::ls_fallback)
 __shared__ double s_ahead[6 + 4];    // announced before the trial: the lambda = 0.1 probe, the walk's first candidate;
-                                     // then the probe's evaluated point and ||e||^2 (GridEval::iteration_hint)
+                                     // then the probe's evaluated point and ||e||^2 (GridEval::probe_hint, candidate_hint)
 __shared__ long long s_cyc[6];  // thread 0: cycles in sweeps, exchanges, and the 4 exchange phases
 __shared__ long long s_ctl[8];  // thread 0: control-code cycles by the kind of request they led to; [7] = time of the last exchange end
 // TMA ring of the streamed part (sample sets beyond on-chip residency): 3 stages x 48 KB
@@ -1130,7 +1132,7 @@ struct GridEval {
     int model, jkind;
     double delta;
     unsigned jac_passes, cost_passes, cost_points, spec_issued, spec_hits;
-    bool spec_on, fuse_on, width_on, memo_valid, sp_trial, sp_pg, hint_valid, ahead_valid, probe_known, sp_clip;
+    bool spec_on, fuse_on, width_on, memo_valid, sp_trial, sp_pg, hint_valid, ahead_valid, cand_valid, probe_known, sp_clip;
     unsigned creep_fused;
     int sp_ls;    // probe number the last line search accepted (0: it failed)
     int pg_last;  // candidates the last projected-gradient walk consumed
@@ -1234,18 +1236,23 @@ struct GridEval {
     // lambda = 0.1, that probe already below the minimum step and not accepted, first candidate of the walk
     // taken -- and all three points of it are known here, so ONE sweep evaluates the costs of the trial point
     // and of the probe and the Jacobian (and cost) of the candidate: the iteration needs no second sweep.
-    __device__ __forceinline__ void iteration_hint(const double* probe, const double* p, const double* Jte, double t,
-                                                   const double* lb, const double* ub) {
+    __device__ __forceinline__ void probe_hint(const double* probe) {
+        __syncwarp();
+        if (threadIdx.x == 0) { s_ahead[0] = probe[0]; s_ahead[1] = probe[1]; s_ahead[2] = probe[2]; }
+        __syncwarp();
+        ahead_valid = true;
+        cand_valid = false;
+    }
+    // the pattern held last time: the candidate is worth the square root and the division its step length costs
+    __device__ __forceinline__ bool wants_candidate_hint() const { return fuse_on && sp_ls == 0 && sp_pg && sp_clip && !(spec_on && sp_trial); }
+    __device__ __forceinline__ void candidate_hint(const double* p, const double* Jte, double t, const double* lb, const double* ub) {
         const double g[3] = {-Jte[0], -Jte[1], -Jte[2]};
         double cand[3];
         pg_candidate(p, g, t, Box{lb, ub}, cand);
         __syncwarp();
-        if (threadIdx.x == 0) {
-            s_ahead[0] = probe[0]; s_ahead[1] = probe[1]; s_ahead[2] = probe[2];
-            s_ahead[3] = cand[0]; s_ahead[4] = cand[1]; s_ahead[5] = cand[2];
-        }
+        if (threadIdx.x == 0) { s_ahead[3] = cand[0]; s_ahead[4] = cand[1]; s_ahead[5] = cand[2]; }
         __syncwarp();
-        ahead_valid = true;
+        cand_valid = true;
     }
 
     // costs at the trial point p and at the announced probe, Jacobian (and cost) at the announced candidate
@@ -1276,7 +1283,7 @@ struct GridEval {
         if (site == kSiteTrial) {
             probe_known = false;
             // the last iteration crept (search failed at its lambda = 0.1 probe, walk took its first candidate)
-            if (fuse_on && !spec && ahead_valid && sp_ls == 0 && sp_pg && sp_clip) return cost_probe_and_candidate(p, bad);
+            if (!spec && ahead_valid && cand_valid) return cost_probe_and_candidate(p, bad);
         } else if (site == 2) {
             sp_clip = ahead_valid && same_bits(p[0], s_ahead[0]) && same_bits(p[1], s_ahead[1]) && same_bits(p[2], s_ahead[2]);
             ahead_valid = false;
@@ -1496,7 +1503,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_persistent_fit(SampleVie
     ev.spec_on = (spec.spec_jac & 1) != 0;
     ev.fuse_on = (spec.spec_jac & 2) != 0;
     ev.width_on = (spec.spec_jac & 4) != 0;
-    ev.memo_valid = ev.sp_trial = ev.sp_pg = ev.hint_valid = ev.ahead_valid = ev.probe_known = ev.sp_clip = false;
+    ev.memo_valid = ev.sp_trial = ev.sp_pg = ev.hint_valid = ev.ahead_valid = ev.cand_valid = ev.probe_known = ev.sp_clip = false;
     ev.creep_fused = 0u;
     ev.sp_ls = ev.pg_last = 0;
     double p[3], info[10], JtJ[9];

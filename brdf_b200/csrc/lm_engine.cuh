@@ -264,12 +264,21 @@ BG_HDI void note_ls_outcome(Eval& ev, int accepted_probe /* 0: the search failed
     if constexpr (SpecJac<Eval>::value) ev.ls_outcome(accepted_probe);
 }
 // Before the LM trial point is evaluated: what the iteration evaluates next if the trial is rejected -- the line
-// search's probe at lambda = 0.1 (its first backtrack when the step was far too long) and, from p, J^T e and the
-// step length t, the first candidate of the projected-gradient walk.
+// search's probe at lambda = 0.1 (its first backtrack when the step was far too long), announced every time,
+// and, only when the evaluator asks for it, the first candidate of the projected-gradient walk (from p, J^T e and
+// the step length t, which costs a square root and a division to know this early).
 template <class Eval>
-BG_HDI void note_iteration_hint(Eval& ev, const double* probe, const double* p, const double* Jte, double t,
-                                const double* lb, const double* ub) {
-    if constexpr (SpecJac<Eval>::value) ev.iteration_hint(probe, p, Jte, t, lb, ub);
+BG_HDI void note_probe_hint(Eval& ev, const double* probe) {
+    if constexpr (SpecJac<Eval>::value) ev.probe_hint(probe);
+}
+template <class Eval>
+BG_HDI bool wants_candidate_hint(Eval& ev) {
+    if constexpr (SpecJac<Eval>::value) return ev.wants_candidate_hint();
+    else return false;
+}
+template <class Eval>
+BG_HDI void note_candidate_hint(Eval& ev, const double* p, const double* Jte, double t, const double* lb, const double* ub) {
+    if constexpr (SpecJac<Eval>::value) ev.candidate_hint(p, Jte, t, lb, ub);
 }
 // The line search is about to evaluate its LAST probe (lambda is already below the minimum step): if
 // that probe is not accepted the search fails and the projected-gradient walk starts from p with
@@ -544,18 +553,21 @@ BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double*
             bool t0_known = false;
             if constexpr (SpecJac<Eval>::value) {
                 if (!dscl) {
-                    // first step length of a projected-gradient walk from here (:876-879), needed early for the hint
-                    tmp = 0.0;
-                    LM_FOR(i) tmp += Jte[i] * Jte[i];
-                    tmp = sqrt(tmp);
-                    tmp = 100.0 / (1.0 + tmp);
-                    t0 = (tmp <= tini) ? tmp : tini;
-                    t0_known = true;
                     const double lambda01 = 1.0 * 0.1;  // the line search's lambda after one clipped backtrack
                     double probe[MM];
                     LM_FOR_REV(i) probe[i] = lm_axpy(lambda01, Dp[i], p[i]);
                     box_project<MM>(probe, box, m);
-                    note_iteration_hint(ev, probe, p, Jte, gprevtaken ? t : t0, lb, ub);
+                    note_probe_hint(ev, probe);
+                    if (wants_candidate_hint(ev)) {
+                        // first step length of a projected-gradient walk from here (:876-879), needed early
+                        tmp = 0.0;
+                        LM_FOR(i) tmp += Jte[i] * Jte[i];
+                        tmp = sqrt(tmp);
+                        tmp = 100.0 / (1.0 + tmp);
+                        t0 = (tmp <= tini) ? tmp : tini;
+                        t0_known = true;
+                        note_candidate_hint(ev, p, Jte, gprevtaken ? t : t0, lb, ub);
+                    }
                 }
             }
             e_new = eval_trial_scaled<MM>(ev, pDp, dscl, m, bad);
