@@ -905,10 +905,12 @@ __device__ __noinline__ void jac_sweep() {
     double extra[2] = {xa + xb, za + zb};
     if (s_ctx.stream_first < (s_ctx.v.n >> 1)) {
         const SampleView v = s_ctx.v;
-        const double esq_res = acc[ESQ];
-        double sa = 0.0, sb = 0.0, ya = 0.0, yb = 0.0, wa = 0.0, wb = 0.0;
+        // streamed part: every group of two pairs adds (pair 0 + pair 1) to the running sums -- the order of
+        // many_sweep and cost_sweep, so a point gets the same ||e||^2 bits from any kind of sweep
+        double esq_run = acc[ESQ], x_run = extra[0], z_run = extra[1];
         const long seq = s_ring.stream(v, s_ctx.stream_first, s_ring_seq,
             [&](double2 c0, double2 l0, double2 x0, long i0, double2 c1, double2 l1, double2 x1, long i1, int valid) {
+                double sa = 0.0, sb = 0.0;
                 if (valid >= 1) {
                     acc[ESQ] = sa;
                     accumulate_jac_pair<JAC>(q, s_req.q, c0, l0, x0, v.traw, i0, acc);
@@ -919,18 +921,23 @@ __device__ __noinline__ void jac_sweep() {
                     accumulate_jac_pair<JAC>(q, s_req.q, c1, l1, x1, v.traw, i1, acc);
                     sb = acc[ESQ];
                 }
+                esq_run += sa + sb;
                 if (EXTRA >= 1) {
+                    double ya = 0.0, yb = 0.0;
                     if (valid == 2) accumulate_cost_2pairs(xq, c0, l0, x0, i0, c1, l1, x1, i1, v.traw, &ya, &yb);
                     else if (valid == 1) accumulate_cost_pair(xq, c0, l0, x0, v.traw, i0, &ya);
+                    x_run += ya + yb;
                 }
                 if (EXTRA >= 2) {
+                    double wa = 0.0, wb = 0.0;
                     if (valid == 2) accumulate_cost_2pairs(zq, c0, l0, x0, i0, c1, l1, x1, i1, v.traw, &wa, &wb);
                     else if (valid == 1) accumulate_cost_pair(zq, c0, l0, x0, v.traw, i0, &wa);
+                    z_run += wa + wb;
                 }
             });
-        acc[ESQ] = esq_res + (sa + sb);
-        extra[0] += ya + yb;
-        extra[1] += wa + wb;
+        acc[ESQ] = esq_run;
+        extra[0] = x_run;
+        extra[1] = z_run;
         __syncthreads();  // everybody has read s_ring_seq
         if (threadIdx.x == 0) s_ring_seq = seq;
     }
@@ -1006,13 +1013,15 @@ __device__ __noinline__ void cost_sweep() {
     acc[0] = resident_cost(q, s_ctx.sc, s_ctx.sl, s_ctx.sx, s_ctx.res_pairs, s_ctx.res_first, s_ctx.v.traw);
     if (s_ctx.stream_first < (s_ctx.v.n >> 1)) {
         const SampleView v = s_ctx.v;
-        double a0 = 0.0, a1 = 0.0;
+        double run = acc[0];  // (same order as many_sweep and jac_sweep: pair 0 + pair 1 of every group, in sequence)
         const long seq = s_ring.stream(v, s_ctx.stream_first, s_ring_seq,
             [&](double2 c0, double2 l0, double2 x0, long i0, double2 c1, double2 l1, double2 x1, long i1, int valid) {
+                double a0 = 0.0, a1 = 0.0;
                 if (valid == 2) accumulate_cost_2pairs(q, c0, l0, x0, i0, c1, l1, x1, i1, v.traw, &a0, &a1);
                 else if (valid == 1) accumulate_cost_pair(q, c0, l0, x0, v.traw, i0, &a0);
+                run += a0 + a1;
             });
-        acc[0] += a0 + a1;
+        acc[0] = run;
         __syncthreads();
         if (threadIdx.x == 0) s_ring_seq = seq;
     }
@@ -1509,7 +1518,25 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_persistent_fit(SampleVie
     double p[3], info[10], JtJ[9];
     for (int i = 0; i < 3; ++i) p[i] = spec.p[i];
     int ret;
-    if (spec.unconstrained)
+    if (spec.spec_jac & 8) {
+        // self-check (BRDFGPU_SPEC_JAC=8, tests only): ||x - f(p)||^2 at the start point from a cost sweep, from a
+        // Jacobian sweep, from a fused Jacobian-at-p + cost-at-p sweep and from a batch of two identical points --
+        // the speculation relies on all of them having the same bits
+        bool bad;
+        for (int i = 0; i < 10; ++i) info[i] = 0.0;
+        for (int i = 0; i < 9; ++i) JtJ[i] = 0.0;
+        info[0] = ev.cost(p, bad);
+        info[1] = ev.cost_with_jac(p, bad);
+        info[2] = ev.cost_and_jac_at(p, p, bad);
+        info[3] = s_memo[3 + ESQ];
+        __syncwarp();
+        if (threadIdx.x < 6) s_cand[threadIdx.x] = p[threadIdx.x % 3];
+        __syncwarp();
+        ev.cost_many(2, nullptr, 3);
+        info[4] = ev.batch_cost(0);
+        info[5] = ev.batch_cost(1);
+        ret = 0;
+    } else if (spec.unconstrained)
         ret = lm_der<3>(ev, 3, p, spec.opt, info, JtJ);
     else
         ret = lm_bc_der<3>(ev, 3, p, spec.has_lb ? spec.lb : nullptr, spec.has_ub ? spec.ub : nullptr,
