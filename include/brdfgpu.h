@@ -98,7 +98,9 @@ unsigned long long brdfgpu_launch_count(brdfgpu_ctx *ctx);
  * candidates per sweep and the unused ones are discarded), out[3] samples held in shared memory for
  * the whole fit, out[4] CTAs of the persistent kernel (0 = host-driven fit), out[5..7] SM clock cycles CTA 0 spent
  * sweeping samples / in the grid-wide exchange / in the kernel altogether, out[8..11] the exchange by
- * phase, out[12..18] control-code cycles by the kind of sweep they led to (up to 20 values). */
+ * phase, out[12..18] control-code cycles by the kind of sweep they led to, out[19] cost evaluations answered
+ * by a Jacobian sweep (speculative Jacobians), out[20] Jacobians that were then obtained without a
+ * sweep, out[21] iterations done in a single fused sweep (up to 24 values). */
 int brdfgpu_fit_stats(brdfgpu_ctx *ctx, unsigned long long *out, int count);
 /* CUDA stream (cudaStream_t) the context launches on, for timing with CUDA events */
 void *brdfgpu_stream(brdfgpu_ctx *ctx);
