@@ -337,6 +337,7 @@ extern "C" int brdfgpu_read_png(const char* path, unsigned char* bgr, int* W, in
 
 extern "C" int brdfgpu_scene_load(brdfgpu_ctx* ctx, const char* image_folder, const char* obj_path, const char* cal_path,
                                   int nimg, brdfgpu_scene** out, double* cam16) {
+    if (!ctx) ctx = default_ctx();  // NULL = the process-wide context, as everywhere in this API
     if (!ctx || !image_folder || !obj_path || !out || nimg < 1) return BRDFGPU_LM_ERROR;
     // LoadModel (main.cpp:41)
     std::vector<unsigned char> buf;

@@ -14,12 +14,73 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "examples", "solve_equation_c.c")
 
 
-def build(tmp_path):
-    exe = str(tmp_path / "solve_equation_c")
+def build(tmp_path, src=SRC):
+    exe = str(tmp_path / os.path.splitext(os.path.basename(src))[0])
     lib_dir = os.path.join(ROOT, "brdf_b200")
-    subprocess.check_call(["gcc", "-O2", "-Wall", "-Werror", "-std=c99", "-I" + os.path.join(ROOT, "include"), SRC, "-L" + lib_dir,
+    subprocess.check_call(["gcc", "-O2", "-Wall", "-Werror", "-std=c99", "-I" + os.path.join(ROOT, "include"), src, "-L" + lib_dir,
                            "-lbrdfgpu", "-Wl,-rpath," + lib_dir, "-lm", "-o", exe])
     return exe
+
+
+PIPELINE = os.path.join(ROOT, "examples", "scene_pipeline_c.c")
+
+
+def test_scene_pipeline_compiles_as_c99_and_checks_its_arguments(tmp_path):
+    """no GPU needed: main.cpp's flow in plain C links, and without arguments it answers as the reference does"""
+    exe = build(tmp_path, PIPELINE)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode != 0 and "required command line arguments" in out.stdout
+
+
+@pytest.mark.gpu
+def test_scene_pipeline_matches_python_mirror(tmp_path):
+    """examples/scene_pipeline_c.c on a scene written in the reference's file formats (.obj, 1..16.png, dark.png,
+    .cal) against the same calls through the ctypes mirror on the in-memory arrays."""
+    cv2 = pytest.importorskip("cv2")
+    import scene_lib as S
+    from brdf_b200 import api as A
+    W, H = 320, 240
+    V, F = S.height_field(40, 30, seed=3)
+    imgs, dark = S.random_images(16, W, H, seed=4)
+    cam = S.look_at_camera((30.0, 20.0, 260.0), (0.0, 0.0, 0.0), f=400.0, cx=160.0, cy=120.0)
+    g = S.oracle_gather(V, F, cam, S.led_table(), imgs, W, H)
+    imgs = S.paint_model_radiance(imgs, g)          # so that the fits are well posed
+    dark = np.zeros_like(dark)
+    folder = str(tmp_path) + "/"
+    with open(folder + "m.obj", "w") as f:
+        for v in V:
+            f.write("v %r %r %r\n" % tuple(float(x) for x in v))
+        for a, b, c in F:
+            f.write("f %d %d %d\n" % (a + 1, b + 1, c + 1))
+    for k, im in enumerate(imgs):
+        assert cv2.imwrite(folder + "%d.png" % (k + 1), im)
+    assert cv2.imwrite(folder + "dark.png", dark)
+    names = ("cx", "cy", "f", "sx", "nx", "ny", "nz", "ox", "oy", "oz", "ax", "ay", "az", "px", "py", "pz")
+    with open(folder + "c.cal", "w") as f:
+        for n, v in zip(names, cam):
+            f.write("<%s>%r</%s>\n" % (n, float(v), n))
+    out = subprocess.run([build(tmp_path, PIPELINE), folder, folder + "m.obj", folder + "c.cal"], capture_output=True, text=True,
+                         timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    ctx = A.Context()
+    sc = ctx.scene(V, F, imgs, dark)
+    nfit, surf = sc.calc_brdf_equation(cam)
+    surf = np.nan_to_num(surf, nan=0.0)     # the C program starts from zeros where no pixel maps to the face
+    n1, single, info, ret = sc.calc_brdf_equation_single(cam)
+    eye = cam[13:16]
+    bgr = sc.shade_faces(eye, eye + cam[10:13], surf, A.BLINN_PHONG, True)
+    text = out.stdout
+    assert "per-face: %d faces fitted" % nfit in text
+    for ch in range(3):
+        m = re.search(r"single\[%d\]: ret=(-?\d+) p=(\S+) (\S+) (\S+) reason=(\d+)" % ch, text)
+        assert int(m.group(1)) == int(ret[ch]) and int(m.group(5)) == int(info[ch][6])
+        assert [float(m.group(i)) for i in (2, 3, 4)] == [float(v) for v in single[ch]]
+    m = re.search(r"shaded: (\d+) finite colour values, sum=(\S+)", text)
+    ok = np.isfinite(bgr)
+    assert int(m.group(1)) == int(ok.sum())
+    np.testing.assert_allclose(float(m.group(2)), bgr[ok].sum(), rtol=1e-9)
+    sc.free()
+    ctx.close()
 
 
 def test_c_example_compiles_as_c99(tmp_path):
