@@ -747,6 +747,15 @@ __shared__ double s_cand[kGridCostBatch * 3];  // candidate points of the projec
 __shared__ double s_cand_cost[kGridCostBatch];
 __shared__ int s_cand_bad[kGridCostBatch];
 __shared__ double s_memo[3 + NACC];  // speculative Jacobian: the point, then A00..A22, G0..G2, ||e||^2 (GridEval::cost_site)
+#ifdef BG_CTL_TICKS
+// debug variant (make VARIANT=_ticks EXTRA=-DBG_CTL_TICKS): control-code cycles between the evaluator's hooks, sweeps
+// and exchanges excluded, printed by CTA 0 at the end of the fit
+__shared__ long long s_tick[12], s_tick_last, s_tick_busy;
+__shared__ int s_tick_prev;
+#define BG_TICK(id) tick(id)
+#else
+#define BG_TICK(id) ((void)0)
+#endif
 __shared__ double s_hint[3];         // first projected-gradient candidate announced by the line search (GridEval::ls_fallback)
 __shared__ double s_ahead[6 + 4];    // announced before the trial: the lambda = 0.1 probe, the walk's first candidate;
                                      // then the probe's evaluated point and ||e||^2 (GridEval::probe_hint, candidate_hint)
@@ -1146,6 +1155,20 @@ struct GridEval {
     int sp_ls;    // probe number the last line search accepted (0: it failed)
     int pg_last;  // candidates the last projected-gradient walk consumed
 
+#ifdef BG_CTL_TICKS
+    // segment ids: the hook that ENDS the segment -- 0 jac() entry (end of iteration + loop head), 1 probe_hint
+    // (after the Jacobian: gradient tests, LU solve, projection, probe), 2 trial cost_site (candidate hint, set-up),
+    // 3 trial_outcome, 4 line-search probe cost_site (rejection algebra, pow, search set-up, first backtrack),
+    // 5 ls_outcome, 6 pg_walk entry, 7 pg_walk exit (walk control without its sweeps), 8 other cost_site
+    __device__ __forceinline__ void tick(int id) {
+        if (threadIdx.x == 0) {
+            const long long now = clock64(), busy = s_cyc[0] + s_cyc[1];
+            s_tick[id] += (now - s_tick_last) - (busy - s_tick_busy);
+            s_tick_last = now;
+            s_tick_busy = busy;
+        }
+    }
+#endif
     __device__ __forceinline__ void post(int kind) {
         if (threadIdx.x == 0) {
             s_req.kind = kind;
@@ -1185,6 +1208,7 @@ struct GridEval {
     }
 
     __device__ __forceinline__ void jac(const double* p, double* JtJ, double* Jte) {
+        BG_TICK(0);
         const double* r = s_res;
         if (memo_is(p)) {
             ++spec_hits;  // the sums of this very point are already here
@@ -1246,6 +1270,7 @@ struct GridEval {
     // taken -- and all three points of it are known here, so ONE sweep evaluates the costs of the trial point
     // and of the probe and the Jacobian (and cost) of the candidate: the iteration needs no second sweep.
     __device__ __forceinline__ void probe_hint(const double* probe) {
+        BG_TICK(1);
         __syncwarp();
         if (threadIdx.x == 0) { s_ahead[0] = probe[0]; s_ahead[1] = probe[1]; s_ahead[2] = probe[2]; }
         __syncwarp();
@@ -1286,6 +1311,7 @@ struct GridEval {
 
     // lm_engine.cuh sites: 0 = the LM trial point, k >= 1 = line-search probe number k
     __device__ __forceinline__ double cost_site(int site, const double* p, bool& bad) {
+        BG_TICK(site == kSiteTrial ? 2 : site >= 1 ? 4 : 8);
         const bool spec = spec_on && (site == kSiteTrial ? sp_trial : site == kSitePgFirst ? sp_pg : site == sp_ls);
         const bool fallback = hint_valid && !spec;
         hint_valid = false;
@@ -1309,8 +1335,8 @@ struct GridEval {
         }
         return cost(p, bad);
     }
-    __device__ __forceinline__ void trial_outcome(bool accepted) { sp_trial = accepted; }
-    __device__ __forceinline__ void ls_outcome(int accepted_probe) { sp_ls = accepted_probe; }
+    __device__ __forceinline__ void trial_outcome(bool accepted) { BG_TICK(3); sp_trial = accepted; }
+    __device__ __forceinline__ void ls_outcome(int accepted_probe) { BG_TICK(5); sp_ls = accepted_probe; }
     __device__ __forceinline__ void pg_outcome(bool took_first) { sp_pg = took_first; }  // sequential form of the walk only
 
     __device__ __forceinline__ double count_bad(int k) {
@@ -1375,6 +1401,7 @@ struct GridEval {
         const double alpha = 1e-4, beta = 0.9, tming = 1e-18;
         const int lane = threadIdx.x;  // control warp: 0..31
         const Box box{lb, ub};
+        BG_TICK(6);
         // walks tend to repeat: start with the batch width the last walk needed (1, 2, 4 or 8 candidates)
         int width = 1;
         if (width_on) while (width < pg_last && width < kGridCostBatch) width *= 2;
@@ -1449,8 +1476,8 @@ struct GridEval {
             if (events) {
                 const int kind = __shfl_sync(0xffffffffu, fatal ? 2 : (restart ? 3 : 1), src);
                 consumed += src + 1;
-                if (kind == 2) { t = t_src; sp_pg = false; return 2; }
-                if (kind == 1) { t = t_src; sp_pg = first_batch && src == 0; pg_last = consumed; return 1; }
+                if (kind == 2) { t = t_src; sp_pg = false; BG_TICK(7); return 2; }
+                if (kind == 1) { t = t_src; sp_pg = first_batch && src == 0; pg_last = consumed; BG_TICK(7); return 1; }
                 t = t0 * beta;  // restart: t = t0, then the loop increment still applies (:926-930)
                 gprevtaken = 0;
             } else {
@@ -1462,6 +1489,7 @@ struct GridEval {
         }
         sp_pg = false;
         pg_last = consumed;
+        BG_TICK(7);
         return 0;
     }
 };
@@ -1498,6 +1526,11 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_persistent_fit(SampleVie
         for (int i = 0; i < 6; ++i) s_cyc[i] = 0;
         for (int i = 0; i < 7; ++i) s_ctl[i] = 0;
         s_ctl[7] = clock64();
+#ifdef BG_CTL_TICKS
+        for (int i = 0; i < 12; ++i) s_tick[i] = 0;
+        s_tick_last = clock64();
+        s_tick_busy = 0;
+#endif
     }
     __syncthreads();
 
@@ -1542,6 +1575,11 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_persistent_fit(SampleVie
         ret = lm_bc_der<3>(ev, 3, p, spec.has_lb ? spec.lb : nullptr, spec.has_ub ? spec.ub : nullptr,
                            spec.has_dscl ? spec.dscl : nullptr, spec.opt, info, JtJ);
     ev.post(kQuit);
+#ifdef BG_CTL_TICKS
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        printf("ticks: iter-end %lld | post-jac+LU+probe %lld | cand-hint %lld | trial-test %lld | reject+LS-setup %lld | LS-tests %lld | to-PG %lld | PG-control %lld | other %lld  (iterations %d)\n",
+               s_tick[0], s_tick[1], s_tick[2], s_tick[3], s_tick[4], s_tick[5], s_tick[6], s_tick[7], s_tick[8], (int)info[5]);
+#endif
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         out->ret = ret;
         out->peer_epoch = s_peer_epoch;

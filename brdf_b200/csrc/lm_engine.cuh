@@ -393,7 +393,7 @@ BG_HDI int lm_line_search(Eval& ev, int m, const double* xc, double fc, const do
     LM_FOR_REV(i) {
         slp += g[i] * step[i];
         const double a = (lm_abs(xc[i]) >= 1.0) ? lm_abs(xc[i]) : 1.0;
-        const double b = lm_abs(step[i]) / a;
+        const double b = (a == 1.0) ? lm_abs(step[i]) : lm_abs(step[i]) / a;  // x / 1.0 == x: no division needed
         if (rln < b) rln = b;
     }
     rmnlmb = steptl / rln;
@@ -608,7 +608,18 @@ BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double*
                 tmp = 100.0 / (1.0 + tmp);
                 t0 = (tmp <= tini) ? tmp : tini;
             }
-            if (gTd <= -rho * pow(Dp_L2, kPow / 2.0)) {
+            // levmar: gTd <= -rho * pow(Dp_L2, kPow/2) (:816).  D**1.05 lies between D and D*D, so the power (a
+            // ~2000-cycle libm call on the control warp) is only needed when gTd falls between the two bounds --
+            // it practically never does (rho = 1e-8); the decision is levmar's in every case, NaN and Inf included
+            bool descent;
+            {
+                const double dd = Dp_L2 * Dp_L2;
+                const double hi = (Dp_L2 >= dd) ? Dp_L2 : dd, lo = (Dp_L2 >= dd) ? dd : Dp_L2;
+                if (gTd <= -rho * hi * 1.000001) descent = true;
+                else if (gTd > -rho * lo * 0.999999) descent = false;
+                else descent = gTd <= -rho * pow(Dp_L2, kPow / 2.0);
+            }
+            if (descent) {
                 const double steptl = 1e3 * sqrt(DBL_EPSILON);
                 tmp = sqrt(p_L2);
                 const double stepmx = 1e3 * ((tmp >= 1.0) ? tmp : 1.0);
