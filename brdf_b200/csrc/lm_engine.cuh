@@ -463,6 +463,21 @@ BG_HDI int lm_line_search(Eval& ev, int m, const double* xc, double fc, const do
     return 1;
 }
 
+// First step length of a projected-gradient walk, t0 = min(100 / (1 + ||g||), tini) (lmbc_core.c:876-879).
+// 100 / (1 + ||g||) exceeds tini = 1 whenever ||g||^2 < 9000 (then 1 + ||g|| < 96), so the square root and the
+// division -- ~600 cycles on the control warp -- are only paid for large gradients; same value in every case.
+template <int MM>
+struct MMTag {};
+template <int MM>
+BG_HDI double lm_pg_first_step(const double* g, int m, double tini, MMTag<MM>) {
+    double tmp = 0.0;
+    LM_FOR(i) tmp += g[i] * g[i];
+    if (tmp < 9000.0 && tini == 1.0) return tini;  // (NaN falls through to the literal formula)
+    tmp = sqrt(tmp);
+    tmp = 100.0 / (1.0 + tmp);
+    return (tmp <= tini) ? tmp : tini;
+}
+
 // =============================================================================================
 // Box-constrained LM (projected LM step / line search / projected gradient), lmbc_core.c:369-1022.
 // p: in/out (m).  lb/ub/dscl may be nullptr.  JtJ_out (m*m, may be nullptr) receives the
@@ -560,11 +575,7 @@ BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double*
                     note_probe_hint(ev, probe);
                     if (wants_candidate_hint(ev)) {
                         // first step length of a projected-gradient walk from here (:876-879), needed early
-                        tmp = 0.0;
-                        LM_FOR(i) tmp += Jte[i] * Jte[i];
-                        tmp = sqrt(tmp);
-                        tmp = 100.0 / (1.0 + tmp);
-                        t0 = (tmp <= tini) ? tmp : tini;
+                        t0 = lm_pg_first_step(Jte, m, tini, MMTag<MM>());
                         t0_known = true;
                         note_candidate_hint(ev, p, Jte, gprevtaken ? t : t0, lb, ub);
                     }
@@ -602,11 +613,7 @@ BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double*
                 gTd += Jte[i] * Dp[i];
             }
             if (!t0_known) {  // first step length of a projected-gradient walk from here (:876-879)
-                tmp = 0.0;
-                LM_FOR(i) tmp += Jte[i] * Jte[i];
-                tmp = sqrt(tmp);
-                tmp = 100.0 / (1.0 + tmp);
-                t0 = (tmp <= tini) ? tmp : tini;
+                t0 = lm_pg_first_step(Jte, m, tini, MMTag<MM>());
             }
             // levmar: gTd <= -rho * pow(Dp_L2, kPow/2) (:816).  D**1.05 lies between D and D*D, so the power (a
             // ~2000-cycle libm call on the control warp) is only needed when gTd falls between the two bounds --
