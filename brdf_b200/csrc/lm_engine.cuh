@@ -563,7 +563,9 @@ BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double*
                 Dp_L2 += tmp * tmp;
             }
             if (Dp_L2 <= o.eps2_sq * p_L2) { stop = 2; break; }
-            if (Dp_L2 >= (p_L2 + o.eps2) / (kEpsilon * kEpsilon)) { stop = 4; break; }
+            // almost singular (:726-730): (p_L2 + eps2) / 1e-24; the division is only made when the cheap lower bound of
+            // that threshold is reached (same decision: x * 9.9e23 < x / 1e-24 for every x >= 0)
+            if (Dp_L2 >= (p_L2 + o.eps2) * 9.9e23 && Dp_L2 >= (p_L2 + o.eps2) / (kEpsilon * kEpsilon)) { stop = 4; break; }
 
             bool t0_known = false;
             if constexpr (SpecJac<Eval>::value) {
@@ -795,7 +797,9 @@ BG_HDI int lm_der(Eval& ev, int m, double* p, const LmOptions& o, double* info, 
                     Dp_L2 += tmp * tmp;
                 }
                 if (Dp_L2 <= o.eps2_sq * p_L2) { stop = 2; break; }
-                if (Dp_L2 >= (p_L2 + o.eps2) / (kEpsilon * kEpsilon)) { stop = 4; break; }
+                // almost singular (:726-730): (p_L2 + eps2) / 1e-24; the division is only made when the cheap lower bound of
+            // that threshold is reached (same decision: x * 9.9e23 < x / 1e-24 for every x >= 0)
+            if (Dp_L2 >= (p_L2 + o.eps2) * 9.9e23 && Dp_L2 >= (p_L2 + o.eps2) / (kEpsilon * kEpsilon)) { stop = 4; break; }
 
                 e_new = eval_cost_site(ev, kSiteTrial, pDp, bad);
                 ++cnt.nfev;
