@@ -16,8 +16,10 @@
 //   host       : one kernel per evaluation, the last CTA publishes the sums straight into mapped
 //                pinned memory and the host spins on a ticket (no stream synchronise per pass);
 //                with a communicator the sums are all-reduced across ranks first.
-//   persistent : the whole fit in ONE cooperative kernel -- every thread runs the same control
-//                code on the same grid-reduced sums, a grid barrier per evaluation.
+//   persistent : the whole fit in ONE cooperative kernel -- the control warp of every CTA runs the same
+//                control code on the same grid-reduced sums; one flagged-cell exchange per sweep (the data
+//                is the barrier), samples resident in shared memory, speculative Jacobians and fused
+//                sweeps (GridEval) so that an iteration needs one or two sweeps.
 #include <cooperative_groups.h>
 
 #include <cstdlib>
