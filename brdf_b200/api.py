@@ -19,6 +19,7 @@ PHONG, BLINN_PHONG = 0, 1
 DRIVE_HOST, DRIVE_PERSISTENT = 0, 1
 JAC_FD, JAC_ANALYTIC = 0, 1
 LM_ERROR = -1
+IPC_HANDLE_BYTES = 72   # BRDFGPU_IPC_HANDLE_BYTES
 
 # the reference's two option presets (brdfdata.cpp:1002,1046-1058 and :1085,1107-1119)
 REF_GLOBAL = dict(p0=(0.0, 0.0, 0.0), itmax=2000, opts=(1e-3, 1e-15, 1e-10, 1e-50, 1.0),
@@ -241,7 +242,8 @@ class Scene:
         return out
 
     def set_gather_options(self, flags, kappa1=None):
-        """Options beyond the reference for later gathers: GATHER_DEPTH_TEST | GATHER_CULL_BACKFACES | GATHER_KAPPA1."""
+        """Options for later gathers: GATHER_DEPTH_TEST | GATHER_CULL_BACKFACES | GATHER_KAPPA1 (beyond the reference),
+        GATHER_SEQ_DOT (left-to-right dot products in GetCosLN / GetCosNH instead of Eigen 3.3's order)."""
         k = _arr(kappa1)
         self.ctx._ok(lib().brdfgpu_scene_set_gather_options(self.ctx.handle, self.handle, int(flags), _d(k), 0 if k is None else k.size))
 
@@ -465,13 +467,18 @@ class Context:
         self._ok(lib().brdfgpu_comm_init(self.handle, unique_id, rank, nranks))
 
     def peer_export(self):
-        buf = C.create_string_buffer(64)
+        """This rank's 72-byte export record (CUDA-IPC handle + the exchange tag reached); export again before every
+        (re-)attach"""
+        buf = C.create_string_buffer(IPC_HANDLE_BYTES)
         self._ok(lib().brdfgpu_peer_export(self.handle, buf))
         return buf.raw
 
     def peer_attach(self, handles, rank, nranks):
-        """handles: the 64-byte exports of all ranks in rank order"""
+        """handles: the export records of all ranks in rank order"""
         self._ok(lib().brdfgpu_peer_attach(self.handle, b"".join(handles), rank, nranks))
+
+    def peer_detach(self):
+        lib().brdfgpu_peer_detach(self.handle)
 
     def allreduce(self, values):
         buf = _arr(values).copy()
@@ -578,7 +585,7 @@ def solve_equation_single(phi, thetaDash, theta, inten, model=BLINN_PHONG):
     return ret, p, info
 
 
-GATHER_DEPTH_TEST, GATHER_CULL_BACKFACES, GATHER_KAPPA1 = 1, 2, 4
+GATHER_DEPTH_TEST, GATHER_CULL_BACKFACES, GATHER_KAPPA1, GATHER_SEQ_DOT = 1, 2, 4, 8
 
 
 # ---- the reference's input files (host code) ----

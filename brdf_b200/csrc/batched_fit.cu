@@ -528,21 +528,22 @@ int batch_alloc(brdfgpu_ctx* ctx, long nfit, int nper, int model, brdfgpu_batch*
         return BRDFGPU_LM_ERROR;
     }
     brdfgpu_batch* b = new brdfgpu_batch;
-    b->nfit = nfit; b->nper = nper; b->model = model;
-    const size_t nb = sizeof(double) * (size_t)(nfit > 0 ? nfit * nper : 1);
-    cudaError_t e = cudaMalloc(&b->c, nb);
-    if (e == cudaSuccess) e = cudaMalloc(&b->L, nb);
-    if (e == cudaSuccess) e = cudaMalloc(&b->x, nb);
-    if (e == cudaSuccess) e = cudaMalloc(&b->traw, nb);
-    if (e == cudaSuccess) e = cudaMalloc(&b->p, sizeof(double) * 3 * (size_t)(nfit > 0 ? nfit : 1));
-    if (e == cudaSuccess) e = cudaMalloc(&b->info, sizeof(double) * 10 * (size_t)(nfit > 0 ? nfit : 1));
-    if (e == cudaSuccess) e = cudaMalloc(&b->ret, sizeof(int) * (size_t)(nfit > 0 ? nfit : 1));
+    b->nfit = nfit; b->capacity = nfit; b->nper = nper; b->model = model;
+    b->stream = ctx->stream;
+    // one stream-ordered allocation, every array on a 256-byte boundary
+    const size_t nf = (size_t)(nfit > 0 ? nfit : 1);
+    const size_t na = (sizeof(double) * nf * nper + 255) & ~(size_t)255, np = (sizeof(double) * 3 * nf + 255) & ~(size_t)255,
+                 ni = (sizeof(double) * 10 * nf + 255) & ~(size_t)255, nr = (sizeof(int) * nf + 255) & ~(size_t)255;
+    cudaError_t e = cudaMallocAsync(&b->block, 4 * na + np + ni + nr, ctx->stream);
     if (e != cudaSuccess) {
-        cudaFree(b->c); cudaFree(b->L); cudaFree(b->x); cudaFree(b->traw); cudaFree(b->p); cudaFree(b->info); cudaFree(b->ret);
         delete b;
-        set_error(ctx, std::string("batch: cudaMalloc: ") + cudaGetErrorString(e));
+        set_error(ctx, std::string("batch: cudaMallocAsync: ") + cudaGetErrorString(e));
         return BRDFGPU_LM_ERROR;
     }
+    char* q = static_cast<char*>(b->block);
+    b->c = reinterpret_cast<double*>(q); b->L = reinterpret_cast<double*>(q + na); b->x = reinterpret_cast<double*>(q + 2 * na);
+    b->traw = reinterpret_cast<double*>(q + 3 * na); b->p = reinterpret_cast<double*>(q + 4 * na);
+    b->info = reinterpret_cast<double*>(q + 4 * na + np); b->ret = reinterpret_cast<int*>(q + 4 * na + np + ni);
     *out = b;
     return 0;
 }

@@ -87,6 +87,7 @@ extern "C" int brdfgpu_create(int device, brdfgpu_ctx** out) {
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_cells, sizeof(uint4) * 2 * 160 * 16);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_fitio, sizeof(GlobalFitOut));
     if (e == cudaSuccess) e = cudaHostAlloc(&ctx->h_fitio, sizeof(GlobalFitOut), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->h_counts, sizeof(int) * kCountStagingInts, cudaHostAllocDefault);
     if (e != cudaSuccess) {
         set_error(nullptr, std::string("context creation failed: ") + cudaGetErrorString(e));
         brdfgpu_destroy(ctx);
@@ -113,6 +114,7 @@ extern "C" void brdfgpu_destroy(brdfgpu_ctx* ctx) {
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     if (ctx->h_seq) cudaFreeHost((void*)ctx->h_seq);
     if (ctx->h_fitio) cudaFreeHost(ctx->h_fitio);
+    if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -260,7 +262,8 @@ extern "C" void brdfgpu_samples_free(brdfgpu_ctx* ctx, brdfgpu_samples* s) {
         if (ctx && ctx->pooled == s) ctx->pooled_busy = false;
         return;
     }
-    cudaFree(s->c); cudaFree(s->L); cudaFree(s->x); cudaFree(s->traw); cudaFree(s->jac);
+    free_block(ctx, s->block, s->stream);
+    cudaFree(s->jac);
     delete s;
 }
 
@@ -341,6 +344,11 @@ static int levmar_entry(const char* name, brdfgpu_func_t func, brdfgpu_jacf_t ja
     if (func != brdfgpu_BRDFFunc || (need_jacf && jacf != brdfgpu_BRDFJac)) {
         fprintf(stderr, "%s: only the brdfgpu_BRDFFunc / brdfgpu_BRDFJac callbacks are supported (GPU path, no CPU fallback)\n",
                 name);
+        return BRDFGPU_LM_ERROR;
+    }
+    if (m != BRDFGPU_NUM_PARAMS) {  // levmar is generic in m (levmar.h:124-127); BRDFFunc is not (brdfdata.cpp:980-986)
+        set_error(nullptr, std::string(name) + ": the BRDF models have exactly 3 parameters (kd, ks, n); m = " + std::to_string(m) +
+                               " is not supported");
         return BRDFGPU_LM_ERROR;
     }
     const brdfgpu_extraData* d = static_cast<const brdfgpu_extraData*>(adata);
@@ -507,9 +515,8 @@ extern "C" int brdfgpu_batch_results(brdfgpu_ctx* ctx, const brdfgpu_batch* b, d
 extern "C" long brdfgpu_batch_count(const brdfgpu_batch* b) { return b ? b->nfit : 0; }
 
 extern "C" void brdfgpu_batch_free(brdfgpu_ctx* ctx, brdfgpu_batch* b) {
-    (void)ctx;
     if (!b) return;
-    cudaFree(b->c); cudaFree(b->L); cudaFree(b->x); cudaFree(b->traw); cudaFree(b->p); cudaFree(b->info); cudaFree(b->ret);
+    free_block(ctx, b->block, b->stream);
     delete b;
 }
 

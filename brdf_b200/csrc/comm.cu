@@ -138,10 +138,12 @@ extern "C" int brdfgpu_comm_allreduce(brdfgpu_ctx* ctx, double* buf, int count) 
 // ------------------------------------------------------------------------------------------------
 static size_t peer_buffer_bytes() { return sizeof(uint4) * 2 * kMaxRanks * kPeerCellsPerRank; }
 
+// exported record: the IPC handle, then the exchange tag this rank's session has reached
+static_assert(sizeof(cudaIpcMemHandle_t) + 8 == BRDFGPU_IPC_HANDLE_BYTES, "export record = cudaIpcMemHandle_t + 8 bytes");
+
 extern "C" int brdfgpu_peer_export(brdfgpu_ctx* ctx, char* handle64) {
     if (!ctx) ctx = default_ctx();
     if (!ctx || !handle64) return BRDFGPU_LM_ERROR;
-    static_assert(sizeof(cudaIpcMemHandle_t) == BRDFGPU_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
     BG_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     if (!ctx->peer_local) {
         BG_CUDA_OK(ctx, cudaMalloc(&ctx->peer_local, peer_buffer_bytes()));
@@ -150,6 +152,8 @@ extern "C" int brdfgpu_peer_export(brdfgpu_ctx* ctx, char* handle64) {
     cudaIpcMemHandle_t h;
     BG_CUDA_OK(ctx, cudaIpcGetMemHandle(&h, ctx->peer_local));
     memcpy(handle64, &h, sizeof(h));
+    const unsigned long long reached = ctx->peer_epoch;
+    memcpy(handle64 + sizeof(h), &reached, sizeof(reached));
     return 0;
 }
 
@@ -169,20 +173,30 @@ extern "C" int brdfgpu_peer_attach(brdfgpu_ctx* ctx, const char* handles, int ra
         return BRDFGPU_LM_ERROR;
     }
     BG_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    brdfgpu_peer_detach(ctx);  // mappings of an earlier session
+    // The buffers are zeroed once, at allocation; cells of an earlier session stay in them.  Tags therefore never
+    // go back: the new session starts above the highest tag any rank has reached (every rank computes the same
+    // number from the same records), so a stale cell {value | tag} can never satisfy a wait of this session.
+    unsigned long long reached = ctx->peer_epoch;
+    for (int r = 0; r < nranks; ++r) {
+        unsigned long long e = 0;
+        memcpy(&e, handles + (size_t)r * BRDFGPU_IPC_HANDLE_BYTES + sizeof(cudaIpcMemHandle_t), sizeof(e));
+        if (e > reached) reached = e;
+    }
     for (int r = 0; r < nranks; ++r) {
         if (r == rank) {
             ctx->peer_remote[r] = ctx->peer_local;
             continue;
         }
         cudaIpcMemHandle_t h;
-        memcpy(&h, handles + (size_t)r * sizeof(h), sizeof(h));
+        memcpy(&h, handles + (size_t)r * BRDFGPU_IPC_HANDLE_BYTES, sizeof(h));
         void* ptr = nullptr;
         BG_CUDA_OK(ctx, cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
         ctx->peer_remote[r] = static_cast<uint4*>(ptr);
     }
     ctx->rank = rank;
     ctx->nranks = nranks;
-    ctx->peer_epoch = 0;
+    ctx->peer_epoch = (unsigned)((reached + 4) & 0xfffffffeull);  // (even; 32-bit tags wrap after 2^32 exchanges, next_tag skips 0)
     ctx->peer_attached = nranks > 1;
     return 0;
 }

@@ -17,6 +17,7 @@ constexpr int kMaxPassBlocks = 2048; // upper bound on CTAs of one pass (partial
 constexpr int kResultDoubles = 16;   // >= NACC
 constexpr int kMaxRanks = 8;         // GPUs of one NVSwitch domain
 constexpr int kPeerCellsPerRank = 16;  // >= NACC flagged cells per (parity, rank)
+constexpr int kCountStagingInts = 1024;  // pinned staging for the per-view fit counts of a gather
 
 // Exchange buffer of the fused in-kernel all-reduce: [2 parities][kMaxRanks][kPeerCellsPerRank]
 // 16-byte cells {value.lo, tag, value.hi, tag}.  Every 8-byte half is written atomically, so a
@@ -51,6 +52,7 @@ struct brdfgpu_ctx {
     // persistent-fit in/out block
     void* d_fitio = nullptr;
     void* h_fitio = nullptr;  // pinned
+    int* h_counts = nullptr;      // pinned, kCountStagingInts: per-view fit counts of the running gather
     uint4* d_cells = nullptr;     // flagged exchange cells of the persistent fit: 2 x kMaxPersistBlocks x 16
     int tma_mode = 0;             // 0: not probed, 1: automatic, 2: never, 3: always (BRDFGPU_TMA)
     long persist_smem_max = 0;    // dynamic shared memory one CTA of the persistent fit may use (0: not probed, <0: unusable)
@@ -77,7 +79,12 @@ struct brdfgpu_ctx {
 
 struct brdfgpu_samples {
     long n = 0;
+    long capacity = 0;  // samples the arrays were allocated for (>= n)
     int model = 1;
+    // c, L, x, traw are carved from ONE stream-ordered allocation (cudaMallocAsync on the context's stream);
+    // block == nullptr: a view onto arrays somebody else owns (the three channel sets of one gather)
+    void* block = nullptr;
+    cudaStream_t stream = nullptr;
     double* c = nullptr;     // cosphi
     double* L = nullptr;     // log(t), NaN = take the pow() path
     double* x = nullptr;     // measurements
@@ -90,8 +97,11 @@ struct brdfgpu_samples {
 
 struct brdfgpu_batch {
     long nfit = 0;
+    long capacity = 0;  // fits the arrays were allocated for (>= nfit)
     int nper = 0;
     int model = 1;
+    void* block = nullptr;  // one stream-ordered allocation behind all seven arrays
+    cudaStream_t stream = nullptr;
     double *c = nullptr, *L = nullptr, *x = nullptr, *traw = nullptr;  // nfit x nper each
     double* p = nullptr;     // nfit x 3
     double* info = nullptr;  // nfit x 10
@@ -125,6 +135,7 @@ inline int pass_blocks(const brdfgpu_ctx* ctx, long n, int ctas_per_sm) {
 // ---- global_fit.cu ----
 struct GlobalFitSpec {
     int m, itmax, jac_mode, has_lb, has_ub, has_dscl, unconstrained, spec_jac;
+    int want_n_all;  // several ranks + covariance: sum the ranks' sample counts through the kernel's exchange
     double delta;  // |opts[4]|
     double p[kMaxM], lb[kMaxM], ub[kMaxM], dscl[kMaxM];
     LmOptions opt;
@@ -140,9 +151,11 @@ struct GlobalFitOut {
     double p[kMaxM];
     double info[10];
     double JtJ[kMaxM * kMaxM];
+    double n_all;  // samples of all ranks (GlobalFitSpec::want_n_all)
 };
 
 int samples_alloc(brdfgpu_ctx* ctx, long n, int model, brdfgpu_samples** out);
+void free_block(brdfgpu_ctx* ctx, void* block, cudaStream_t stream);  // stream-ordered when ctx still owns `stream`
 int samples_prepare(brdfgpu_ctx* ctx, brdfgpu_samples* s);  // L from traw
 int global_normal_eq(brdfgpu_ctx* ctx, const brdfgpu_samples* s, const double* p, double delta, int jac_mode,
                      double* out11);

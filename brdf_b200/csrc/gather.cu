@@ -8,14 +8,20 @@
 //
 // Bit-exactness contract (oracle/gather_oracle.c is the definition): every arithmetic step is one
 // IEEE-754 double operation issued through the round-to-nearest intrinsics below, so no FMA
-// contraction can occur whatever flags this file is compiled with; 3-term sums associate left to
-// right; double -> int truncates.  "Last face wins" is atomicMax(face id): the reference walks
-// faces in ascending order, so the survivor is the largest id.
+// contraction can occur whatever flags this file is compiled with; 3-term sums associate the way
+// Eigen 3.3 evaluates the reference's expressions (oracle/gather_oracle.c has the derivation): left to
+// right everywhere except the final dot products of GetCosLN / GetCosNH, a0*b0 + (a1*b1 + a2*b2)
+// (BRDFGPU_GATHER_SEQ_DOT restores left to right there); double -> int truncates.  "Last face wins"
+// is atomicMax(face id): the reference walks faces in ascending order, so the survivor is the largest id.
 //
 // Work decomposition: one thread per (view, face) for the projection, one thread per
 // (fit, LED) for the sample rows, so the 16 LEDs of a fit write 16 consecutive doubles.
+// Face centroids and normals are per-scene constants (computed once by k_face_geometry); the sample
+// kernel writes straight into the arrays of the fit stage (cosphi, model cosine, its log, the channel's
+// intensities), so a resident gather needs no device-to-device hand-over and one synchronisation.
 #include <vector>
 
+#include "brdf_model.cuh"
 #include "common.cuh"
 
 // BRDFGPU_TRACE=1: wall-clock milestones of the scene drivers on stderr (host-side diagnosis)
@@ -43,6 +49,7 @@ struct brdfgpu_scene {
     double* V = nullptr;           // nV x 3
     int* F = nullptr;              // nF x 3
     double* FN = nullptr;          // nF x 3
+    double* FC = nullptr;          // nF x 3 face centroids, brdfdata.cpp:653-660 (the same for every view and LED)
     unsigned char* img = nullptr;  // nimg x H x W x 3 (BGR), ambient already removed
     double* led = nullptr;         // nimg x 3
 };
@@ -60,6 +67,11 @@ struct V3 {
 constexpr double kPiShade = 3.1415926535897932384626433832795;  // CV_PI
 __device__ __forceinline__ double dot3(const V3& a, const V3& b) {
     return dadd(dadd(dmul(a.x, b.x), dmul(a.y, b.y)), dmul(a.z, b.z));
+}
+// fixed-size vector .cwiseProduct(row of a column-major MatrixXd).sum() in Eigen 3.3 (brdfdata.cpp:893, 937):
+// the unrolled scalar reduction splits 3 terms as 1 + 2
+__device__ __forceinline__ double dot3_row(const V3& a, const V3& b) {
+    return dadd(dmul(a.x, b.x), dadd(dmul(a.y, b.y), dmul(a.z, b.z)));
 }
 __device__ __forceinline__ V3 normalized(V3 v) {
     const double z = dot3(v, v);
@@ -105,9 +117,12 @@ __device__ __forceinline__ int project_tsai(const V3& c, const Camera& cam, int 
     return (int)v * W + (int)u;
 }
 
-__global__ void k_face_normals(const double* __restrict__ V, const int* __restrict__ F, int nF, double* __restrict__ FN) {
+__global__ void k_face_geometry(const double* __restrict__ V, const int* __restrict__ F, int nF, double* __restrict__ FN,
+                                double* __restrict__ FC) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nF) return;
+    const V3 ctr = centroid_of(V, F, i);
+    FC[3l * i] = ctr.x; FC[3l * i + 1] = ctr.y; FC[3l * i + 2] = ctr.z;
     const V3 v0 = load3(V + 3l * F[3l * i]), v1 = load3(V + 3l * F[3l * i + 1]), v2 = load3(V + 3l * F[3l * i + 2]);
     const V3 e1{dsub(v1.x, v0.x), dsub(v1.y, v0.y), dsub(v1.z, v0.z)};
     const V3 e2{dsub(v2.x, v0.x), dsub(v2.y, v0.y), dsub(v2.z, v0.z)};
@@ -140,12 +155,12 @@ __global__ void k_subtract_ambient(unsigned char* __restrict__ img, const unsign
 // truncated dot product -- face_normals(i, (int)(N.lightDir)) -- instead of using the dot product itself.
 // Same single-rounding arithmetic as the gather; only pow() is the device libm's.
 template <bool LITERAL>
-__global__ void k_shade_faces(const double* __restrict__ V, const int* __restrict__ F, const double* __restrict__ FN, int nF,
+__global__ void k_shade_faces(const double* __restrict__ FC, const double* __restrict__ FN, int nF,
                               V3 eye, V3 center, int model, int single, const double* __restrict__ brdf,
                               double* __restrict__ bgr) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nF) return;
-    const V3 c = centroid_of(V, F, i);
+    const V3 c = load3(FC + 3l * i);
     const V3 N = load3(FN + 3l * i);
     const V3 l = normalized(V3{dsub(eye.x, c.x), dsub(eye.y, c.y), dsub(eye.z, c.z)});
     const V3 v = normalized(V3{dsub(eye.x, center.x), dsub(eye.y, center.y), dsub(eye.z, center.z)});
@@ -213,7 +228,7 @@ __device__ __forceinline__ int project_opts(const V3& c, const V3& N, const Came
 
 // one thread per (view, face) with options: pass 0 records the pixel and (depth test) the nearest depth per pixel
 // (zc > 0, so the bits of the double order like the value); pass 1 lets the faces at that depth claim the pixel
-__global__ void k_project_opts(const double* __restrict__ V, const int* __restrict__ F, const double* __restrict__ FN, int nF,
+__global__ void k_project_opts(const double* __restrict__ FC, const double* __restrict__ FN, int nF,
                                const double* __restrict__ cams, const double* __restrict__ kappa1, int flags, int ncam, int W,
                                int H, int pass, int* __restrict__ pix, unsigned long long* __restrict__ zbits,
                                unsigned long long* __restrict__ depth, int* __restrict__ maps) {
@@ -223,7 +238,7 @@ __global__ void k_project_opts(const double* __restrict__ V, const int* __restri
     if (pass == 0) {
         const Camera cam = load_camera(cams + 16l * v);
         double z = 0.0;
-        const int px = project_opts(centroid_of(V, F, face), load3(FN + 3l * face), cam, kappa1 ? kappa1[v] : 0.0, flags, W, H, &z);
+        const int px = project_opts(load3(FC + 3l * face), load3(FN + 3l * face), cam, kappa1 ? kappa1[v] : 0.0, flags, W, H, &z);
         pix[e] = px;
         if (px < 0) return;
         if (flags & BRDFGPU_GATHER_DEPTH_TEST) {
@@ -244,13 +259,13 @@ __global__ void k_fill_u64(unsigned long long* p, long n, unsigned long long val
 }
 
 // one thread per (view, face): pixel of the centroid, and the per-view map by atomicMax
-__global__ void k_project(const double* __restrict__ V, const int* __restrict__ F, int nF, const double* __restrict__ cams,
+__global__ void k_project(const double* __restrict__ FC, int nF, const double* __restrict__ cams,
                           int ncam, int W, int H, int* __restrict__ pix /*ncam*nF*/, int* __restrict__ maps /*ncam*H*W*/) {
     const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= (long)ncam * nF) return;
     const int v = (int)(e / nF), face = (int)(e % nF);
     const Camera cam = load_camera(cams + 16l * v);
-    const int px = project_tsai(centroid_of(V, F, face), cam, W, H);
+    const int px = project_tsai(load3(FC + 3l * face), cam, W, H);
     pix[e] = px;
     if (px >= 0) atomicMax(maps + (long)v * W * H + px, face);
 }
@@ -339,70 +354,133 @@ __global__ void __launch_bounds__(kScanThreads) k_owner_scatter(const int* pix, 
     if (e == total - 1) cam_first[ncam] = pos + flag;
 }
 
-// one thread per (fit, LED): the three cosines and the three channel intensities of that sample
-__global__ void k_gather_samples(const double* __restrict__ V, const int* __restrict__ F, const double* __restrict__ FN,
-                                 const double* __restrict__ led, const unsigned char* __restrict__ img,
-                                 const double* __restrict__ cams, const int* __restrict__ fit_face,
-                                 const int* __restrict__ fit_pixel, const int* __restrict__ fit_cam, long nfit, int nimg,
-                                 int W, int H, long chan_stride, double* __restrict__ phi, double* __restrict__ thetaDash,
-                                 double* __restrict__ theta, double* __restrict__ I) {
-    const long s = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nfit * nimg) return;
+// Where one gather writes its samples; every pointer may be null (not wanted).  Besides the plain arrays of
+// brdfgpu_gather the kernel fills the arrays of the FIT stage directly -- cosphi, the model's cosine, its
+// log (brdf_model.cuh: log_or_flag) and the measurements of a colour channel -- so the resident paths need no
+// device-to-device hand-over and no separate log pass.  The number of fits is only known on the device when
+// the kernel is launched (no synchronisation in between): offsets that depend on it are formed in the kernel.
+struct GatherOut {
+    double *phi = nullptr, *thetaDash = nullptr, *theta = nullptr;  // fit-major, nimg per fit
+    double* I[3] = {nullptr, nullptr, nullptr};                     // (B, G, R)
+    double *fit_c = nullptr, *fit_t = nullptr, *fit_L = nullptr;    // fit stage: cosphi, model cosine, log of it
+    int fit_reps = 1;              // the three arrays above are written fit_reps times, block r at offset r * nfit * nimg
+    double* fit_x[3] = {nullptr, nullptr, nullptr};  // fit stage: measurements of channel ch
+    int fit_x_chan_blocks = 0;     // 1: channel ch is offset by ch * nfit * nimg (the three channel blocks of ONE batch)
+    int model = 1;                 // cosine the fit stage reads: 1 = thetaDash (Blinn-Phong), 0 = theta (Phong)
+    // second fit-stage destination (brdfgpu_gather_resident asked for a global set AND a batch)
+    double *fit2_c = nullptr, *fit2_t = nullptr, *fit2_L = nullptr, *fit2_x = nullptr;
+    int fit2_channel = 0;
+};
+
+// one thread per (fit, LED): the cosines and the three channel intensities of that sample.
+// NH / RV: compute cos(theta') / the literal cos(theta) (each costs a normalisation = 1 sqrt + 3 divisions, and
+// bit-exactness forbids anything cheaper); SEQ: left-to-right dots in GetCosLN / GetCosNH (BRDFGPU_GATHER_SEQ_DOT).
+template <bool NH, bool RV, bool SEQ>
+__global__ void __launch_bounds__(256) k_gather_samples(const double* __restrict__ FC, const double* __restrict__ FN,
+                                                        const double* __restrict__ led, const unsigned char* __restrict__ img,
+                                                        const double* __restrict__ cams, const int* __restrict__ fit_face,
+                                                        const int* __restrict__ fit_pixel, const int* __restrict__ fit_cam,
+                                                        const int* __restrict__ nfit_dev, int nimg, int W, int H, GatherOut o) {
+    const long ns = (long)*nfit_dev * nimg;
+    if ((long)blockIdx.x * 256 >= ns) return;  // the grid is sized for the capacity (every face of every view mapped)
+    // u8 / 255.0 (brdfdata.cpp:956) for all 256 bytes: one division per thread instead of three
+    __shared__ double lut[256];
+    lut[threadIdx.x] = ddiv((double)threadIdx.x, 255.0);
+    __syncthreads();
+    const long s = (long)blockIdx.x * 256 + threadIdx.x;
+    if (s >= ns) return;
     const long fit = s / nimg;
-    const int k = (int)(s % nimg);
+    const int k = (int)(s - fit * nimg);
     const int face = fit_face[fit];
-    const V3 C = centroid_of(V, F, face);
+    const V3 C = load3(FC + 3l * face);
     const V3 N = load3(FN + 3l * face);
     const V3 Lk = load3(led + 3l * k);
-    const V3 P = load3(cams + 16l * fit_cam[fit] + 13);
 
     // GetCosLN, brdfdata.cpp:887-893
     const V3 l = normalized(V3{dsub(Lk.x, C.x), dsub(Lk.y, C.y), dsub(Lk.z, C.z)});
-    phi[s] = dot3(l, N);
-    // GetCosNH, brdfdata.cpp:931-937: H = L - 2C + P
-    const V3 h = normalized(V3{dadd(dsub(Lk.x, dmul(2.0, C.x)), P.x), dadd(dsub(Lk.y, dmul(2.0, C.y)), P.y),
-                               dadd(dsub(Lk.z, dmul(2.0, C.z)), P.z)});
-    thetaDash[s] = dot3(h, N);
-    // GetCosRV, brdfdata.cpp:829-851, literal (centroid x in all three components, R.P): SURVEY.md Q8
-    const V3 ld = normalized(V3{dsub(C.x, Lk.x), dsub(C.x, Lk.y), dsub(C.x, Lk.z)});
-    const double sc = dot3(N, ld);
-    const V3 Pv{dmul(sc, N.x), dmul(sc, N.y), dmul(sc, N.z)};
-    const V3 R{dsub(ld.x, dmul(2.0, Pv.x)), dsub(ld.y, dmul(2.0, Pv.y)), dsub(ld.z, dmul(2.0, Pv.z))};
-    theta[s] = dot3(R, Pv);
+    const double cphi = SEQ ? dot3(l, N) : dot3_row(l, N);
+    double cnh = 0.0, crv = 0.0;
+    if (NH) {  // GetCosNH, brdfdata.cpp:931-937: H = L - 2C + P
+        const V3 P = load3(cams + 16l * fit_cam[fit] + 13);
+        const V3 h = normalized(V3{dadd(dsub(Lk.x, dmul(2.0, C.x)), P.x), dadd(dsub(Lk.y, dmul(2.0, C.y)), P.y),
+                                   dadd(dsub(Lk.z, dmul(2.0, C.z)), P.z)});
+        cnh = SEQ ? dot3(h, N) : dot3_row(h, N);
+    }
+    if (RV) {  // GetCosRV, brdfdata.cpp:829-851, literal (centroid x in all three components, R.P): SURVEY.md Q8
+        const V3 ld = normalized(V3{dsub(C.x, Lk.x), dsub(C.x, Lk.y), dsub(C.x, Lk.z)});
+        const double sc = dot3(N, ld);  // Block on the left: Eigen's run-time loop, left to right
+        const V3 Pv{dmul(sc, N.x), dmul(sc, N.y), dmul(sc, N.z)};
+        const V3 R{dsub(ld.x, dmul(2.0, Pv.x)), dsub(ld.y, dmul(2.0, Pv.y)), dsub(ld.z, dmul(2.0, Pv.z))};
+        crv = dot3(R, Pv);              // two plain RowVector3d: packet of two, then the third
+    }
+    if (o.phi) o.phi[s] = cphi;
+    if (NH && o.thetaDash) o.thetaDash[s] = cnh;
+    if (RV && o.theta) o.theta[s] = crv;
+    const double t = o.model == 1 ? cnh : crv;
+    if (o.fit_c) {
+        const double Lg = log_or_flag(t);
+        for (int r = 0; r < o.fit_reps; ++r) {
+            o.fit_c[r * ns + s] = cphi;
+            o.fit_t[r * ns + s] = t;
+            o.fit_L[r * ns + s] = Lg;
+        }
+        if (o.fit2_c) {
+            o.fit2_c[s] = cphi;
+            o.fit2_t[s] = t;
+            o.fit2_L[s] = Lg;
+        }
+    }
     // GetIntensities_FromPixel, brdfdata.cpp:955-956 (Tsai rows are top-down: no flip)
     const unsigned char* px = img + ((long)k * H * W + fit_pixel[fit]) * 3;
-    I[s] = ddiv((double)px[0], 255.0);
-    I[chan_stride + s] = ddiv((double)px[1], 255.0);
-    I[2 * chan_stride + s] = ddiv((double)px[2], 255.0);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const double v = lut[px[ch]];
+        if (o.I[ch]) o.I[ch][s] = v;
+        if (o.fit_x[ch]) o.fit_x[ch][(o.fit_x_chan_blocks ? ch * ns : 0) + s] = v;
+        if (o.fit2_x && ch == o.fit2_channel) o.fit2_x[s] = v;
+    }
 }
 
-__global__ void k_log_flag(const double* __restrict__ t, double* __restrict__ L, long n) {
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
-        L[i] = (t[i] >= 0.0) ? log(t[i]) : __longlong_as_double(0x7ff8000000000000LL);
-}
-
-// device-side result of one gather
+// device-side state of one gather
 struct GatherDev {
     long nfit = 0;
+    long cap_fits = 0;  // ncam * nF: rows every per-fit array is sized for (the fit count is not known at launch time)
     int ncam = 0;
+    // Two stream-ordered allocations (cudaMallocAsync on the context's stream, pool kept by brdfgpu_create): a
+    // gather call costs microseconds of allocation instead of the 3-4 ms (and, on a cold box, far more) that
+    // a dozen cudaMalloc / cudaFree pairs take.
+    void *tmp_block = nullptr, *out_block = nullptr;
     int *pix = nullptr, *maps = nullptr, *fit_face = nullptr, *fit_pixel = nullptr, *fit_cam = nullptr, *cam_first = nullptr;
     int* block_sums = nullptr;
     double *cams = nullptr, *phi = nullptr, *thetaDash = nullptr, *theta = nullptr, *I = nullptr;
     std::vector<int> h_cam_first;
-    // Buffers come from the stream-ordered allocator (cudaMallocAsync on the context's stream, pool kept by
-    // brdfgpu_create): a gather call costs microseconds of allocation instead of the 3-4 ms (and, on a cold
-    // box, far more) that 12 cudaMalloc / cudaFree pairs take.
     cudaStream_t stream = nullptr;
     void release() {
-        void* all[] = {pix, maps, fit_face, fit_pixel, fit_cam, cam_first, block_sums, cams, phi, thetaDash, theta, I};
-        for (void* q : all)
-            if (q) cudaFreeAsync(q, stream);
+        if (tmp_block) cudaFreeAsync(tmp_block, stream);
+        if (out_block) cudaFreeAsync(out_block, stream);
         *this = GatherDev();
     }
 };
 
-static int gather_device(brdfgpu_ctx* ctx, const brdfgpu_scene* sc, const double* cams_host, int ncam, bool want_samples,
-                         GatherDev* g) {
+// bump allocation inside one block, 256-byte granules
+struct Carver {
+    char* base;
+    size_t off = 0;
+    template <class T>
+    T* take(size_t count) {
+        T* p = reinterpret_cast<T*>(base + off);
+        off += (count * sizeof(T) + 255) & ~(size_t)255;
+        return p;
+    }
+};
+
+enum { kWantPhi = 1, kWantNH = 2, kWantRV = 4, kWantI = 8 };
+
+// Queues the whole gather on the context's stream WITHOUT synchronising: projection, ordered compaction, sample
+// kernel.  `plain`: which of the plain arrays (GatherDev::phi ...) to allocate and fill; `out`: fit-stage
+// destinations prepared by the caller (may be null).  gather_finish() then waits and reads the counts.
+static int gather_device(brdfgpu_ctx* ctx, const brdfgpu_scene* sc, const double* cams_host, int ncam, int plain,
+                         const GatherOut* fit_out, GatherDev* g) {
     if (ncam < 1) {
         set_error(ctx, "gather: need at least one camera");
         return BRDFGPU_LM_ERROR;
@@ -411,22 +489,25 @@ static int gather_device(brdfgpu_ctx* ctx, const brdfgpu_scene* sc, const double
     const int nblocks = (int)((total + kScanThreads - 1) / kScanThreads);
     Trace tr("gather_device");
     g->ncam = ncam;
+    g->cap_fits = total;
     g->stream = ctx->stream;
-    BG_CUDA_OK(ctx, cudaMallocAsync(&g->cams, sizeof(double) * 16 * ncam, ctx->stream));
-    BG_CUDA_OK(ctx, cudaMallocAsync(&g->pix, sizeof(int) * total, ctx->stream));
-    BG_CUDA_OK(ctx, cudaMallocAsync(&g->maps, sizeof(int) * npix, ctx->stream));
-    BG_CUDA_OK(ctx, cudaMallocAsync(&g->fit_face, sizeof(int) * total, ctx->stream));
-    BG_CUDA_OK(ctx, cudaMallocAsync(&g->fit_pixel, sizeof(int) * total, ctx->stream));
-    BG_CUDA_OK(ctx, cudaMallocAsync(&g->fit_cam, sizeof(int) * total, ctx->stream));
-    BG_CUDA_OK(ctx, cudaMallocAsync(&g->cam_first, sizeof(int) * (ncam + 1), ctx->stream));
-    BG_CUDA_OK(ctx, cudaMallocAsync(&g->block_sums, sizeof(int) * (nblocks + 1), ctx->stream));
+    {
+        Carver sz{nullptr};
+        sz.take<double>(16 * (size_t)ncam); sz.take<int>(total); sz.take<int>(npix); sz.take<int>(total); sz.take<int>(total);
+        sz.take<int>(total); sz.take<int>(ncam + 1); sz.take<int>(nblocks + 1);
+        BG_CUDA_OK(ctx, cudaMallocAsync(&g->tmp_block, sz.off, ctx->stream));
+        Carver cv{static_cast<char*>(g->tmp_block)};
+        g->cams = cv.take<double>(16 * (size_t)ncam); g->pix = cv.take<int>(total); g->maps = cv.take<int>(npix);
+        g->fit_face = cv.take<int>(total); g->fit_pixel = cv.take<int>(total); g->fit_cam = cv.take<int>(total);
+        g->cam_first = cv.take<int>(ncam + 1); g->block_sums = cv.take<int>(nblocks + 1);
+    }
     BG_CUDA_OK(ctx, cudaMemcpyAsync(g->cams, cams_host, sizeof(double) * 16 * ncam, cudaMemcpyHostToDevice, ctx->stream));
-    tr.mark("8 cudaMalloc + H2D of the cameras");
+    tr.mark("allocation + H2D of the cameras");
 
     k_fill_int<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(g->maps, npix, -1);
-    if (sc->gather_flags == 0) {
-        k_project<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(sc->V, sc->F, sc->nF, g->cams, ncam, sc->W, sc->H,
-                                                                            g->pix, g->maps);
+    if ((sc->gather_flags & ~BRDFGPU_GATHER_SEQ_DOT) == 0) {
+        k_project<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(sc->FC, sc->nF, g->cams, ncam, sc->W, sc->H, g->pix,
+                                                                            g->maps);
     } else {
         const int flags = sc->gather_flags;
         double* d_kappa = nullptr;
@@ -446,10 +527,10 @@ static int gather_device(brdfgpu_ctx* ctx, const brdfgpu_scene* sc, const double
             ++ctx->launches;
         }
         const unsigned blocks = (unsigned)((total + 255) / 256);
-        k_project_opts<<<blocks, 256, 0, ctx->stream>>>(sc->V, sc->F, sc->FN, sc->nF, g->cams, d_kappa, flags, ncam, sc->W, sc->H, 0,
+        k_project_opts<<<blocks, 256, 0, ctx->stream>>>(sc->FC, sc->FN, sc->nF, g->cams, d_kappa, flags, ncam, sc->W, sc->H, 0,
                                                         g->pix, d_zbits, d_depth, g->maps);
         if (flags & BRDFGPU_GATHER_DEPTH_TEST) {
-            k_project_opts<<<blocks, 256, 0, ctx->stream>>>(sc->V, sc->F, sc->FN, sc->nF, g->cams, d_kappa, flags, ncam, sc->W, sc->H, 1,
+            k_project_opts<<<blocks, 256, 0, ctx->stream>>>(sc->FC, sc->FN, sc->nF, g->cams, d_kappa, flags, ncam, sc->W, sc->H, 1,
                                                             g->pix, d_zbits, d_depth, g->maps);
             ++ctx->launches;
         }
@@ -463,25 +544,60 @@ static int gather_device(brdfgpu_ctx* ctx, const brdfgpu_scene* sc, const double
                                                                g->fit_face, g->fit_pixel, g->fit_cam, g->cam_first, ncam);
     ctx->launches += 5;
     BG_CUDA_OK(ctx, cudaGetLastError());
-    g->h_cam_first.resize(ncam + 1);
-    BG_CUDA_OK(ctx, cudaMemcpyAsync(g->h_cam_first.data(), g->cam_first, sizeof(int) * (ncam + 1), cudaMemcpyDeviceToHost,
-                                     ctx->stream));
-    BG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-    tr.mark("project + compaction kernels, sync");
-    g->nfit = g->h_cam_first[ncam];
-    if (!want_samples || g->nfit == 0) return 0;
+    // the per-view fit counts travel back through pinned memory behind everything else: no wait here
+    g->h_cam_first.assign(ncam + 1, 0);
+    int* staging = (ncam + 1 <= kCountStagingInts) ? ctx->h_counts : g->h_cam_first.data();
+    BG_CUDA_OK(ctx, cudaMemcpyAsync(staging, g->cam_first, sizeof(int) * (ncam + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    tr.mark("project + compaction kernels queued");
+    if (!plain && !fit_out) return 0;
 
-    const long ns = g->nfit * sc->nimg;
-    BG_CUDA_OK(ctx, cudaMallocAsync(&g->phi, sizeof(double) * ns, ctx->stream));
-    BG_CUDA_OK(ctx, cudaMallocAsync(&g->thetaDash, sizeof(double) * ns, ctx->stream));
-    BG_CUDA_OK(ctx, cudaMallocAsync(&g->theta, sizeof(double) * ns, ctx->stream));
-    BG_CUDA_OK(ctx, cudaMallocAsync(&g->I, sizeof(double) * 3 * ns, ctx->stream));
-    k_gather_samples<<<(unsigned)((ns + 255) / 256), 256, 0, ctx->stream>>>(
-        sc->V, sc->F, sc->FN, sc->led, sc->img, g->cams, g->fit_face, g->fit_pixel, g->fit_cam, g->nfit, sc->nimg, sc->W,
-        sc->H, ns, g->phi, g->thetaDash, g->theta, g->I);
+    GatherOut o;
+    if (fit_out) o = *fit_out;
+    const long cap_ns = total * sc->nimg;
+    if (plain) {
+        const int narr = ((plain & kWantPhi) ? 1 : 0) + ((plain & kWantNH) ? 1 : 0) + ((plain & kWantRV) ? 1 : 0) +
+                         ((plain & kWantI) ? 3 : 0);
+        BG_CUDA_OK(ctx, cudaMallocAsync(&g->out_block, sizeof(double) * (size_t)narr * cap_ns, ctx->stream));
+        double* q = static_cast<double*>(g->out_block);
+        if (plain & kWantPhi) { g->phi = o.phi = q; q += cap_ns; }
+        if (plain & kWantNH) { g->thetaDash = o.thetaDash = q; q += cap_ns; }
+        if (plain & kWantRV) { g->theta = o.theta = q; q += cap_ns; }
+        if (plain & kWantI) {
+            g->I = q;
+            for (int ch = 0; ch < 3; ++ch) o.I[ch] = q + (size_t)ch * cap_ns;
+        }
+    }
+    const bool nh = (plain & kWantNH) || (o.fit_c && o.model == 1), rv = (plain & kWantRV) || (o.fit_c && o.model == 0);
+    const bool seq = (sc->gather_flags & BRDFGPU_GATHER_SEQ_DOT) != 0;
+    const unsigned blocks = (unsigned)((cap_ns + 255) / 256);
+    const int* nfit_dev = g->cam_first + ncam;
+#define BG_GATHER_LAUNCH(NH_, RV_, SEQ_)                                                                                    \
+    k_gather_samples<NH_, RV_, SEQ_><<<blocks, 256, 0, ctx->stream>>>(sc->FC, sc->FN, sc->led, sc->img, g->cams, g->fit_face, \
+                                                                      g->fit_pixel, g->fit_cam, nfit_dev, sc->nimg, sc->W, sc->H, o)
+    if (seq) {
+        if (nh && rv) BG_GATHER_LAUNCH(true, true, true);
+        else if (nh) BG_GATHER_LAUNCH(true, false, true);
+        else if (rv) BG_GATHER_LAUNCH(false, true, true);
+        else BG_GATHER_LAUNCH(false, false, true);
+    } else {
+        if (nh && rv) BG_GATHER_LAUNCH(true, true, false);
+        else if (nh) BG_GATHER_LAUNCH(true, false, false);
+        else if (rv) BG_GATHER_LAUNCH(false, true, false);
+        else BG_GATHER_LAUNCH(false, false, false);
+    }
+#undef BG_GATHER_LAUNCH
     ++ctx->launches;
     BG_CUDA_OK(ctx, cudaGetLastError());
-    tr.mark("4 cudaMalloc + sample kernel launch");
+    tr.mark("sample kernel queued");
+    return 0;
+}
+
+// wait for the queued gather and read the fit counts
+static int gather_finish(brdfgpu_ctx* ctx, GatherDev* g) {
+    BG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (g->ncam + 1 <= kCountStagingInts)
+        for (int v = 0; v <= g->ncam; ++v) g->h_cam_first[v] = ctx->h_counts[v];
+    g->nfit = g->h_cam_first[g->ncam];
     return 0;
 }
 
@@ -535,6 +651,7 @@ extern "C" int brdfgpu_scene_create(brdfgpu_ctx* ctx, const double* V, int nV, c
     cudaError_t e = cudaMalloc(&sc->V, sizeof(double) * 3 * nV);
     if (e == cudaSuccess) e = cudaMalloc(&sc->F, sizeof(int) * 3 * nF);
     if (e == cudaSuccess) e = cudaMalloc(&sc->FN, sizeof(double) * 3 * nF);
+    if (e == cudaSuccess) e = cudaMalloc(&sc->FC, sizeof(double) * 3 * nF);
     if (e == cudaSuccess) e = cudaMalloc(&sc->img, (size_t)per * nimg);
     if (e == cudaSuccess) e = cudaMalloc(&sc->led, sizeof(double) * 3 * nimg);
     if (e == cudaSuccess) e = cudaMemcpyAsync(sc->V, V, sizeof(double) * 3 * nV, cudaMemcpyHostToDevice, ctx->stream);
@@ -553,7 +670,7 @@ extern "C" int brdfgpu_scene_create(brdfgpu_ctx* ctx, const double* V, int nV, c
         }
     }
     if (e == cudaSuccess) {
-        k_face_normals<<<(nF + 255) / 256, 256, 0, ctx->stream>>>(sc->V, sc->F, nF, sc->FN);
+        k_face_geometry<<<(nF + 255) / 256, 256, 0, ctx->stream>>>(sc->V, sc->F, nF, sc->FN, sc->FC);
         ++ctx->launches;
         e = cudaGetLastError();
     }
@@ -571,7 +688,7 @@ extern "C" int brdfgpu_scene_create(brdfgpu_ctx* ctx, const double* V, int nV, c
 extern "C" void brdfgpu_scene_free(brdfgpu_ctx* ctx, brdfgpu_scene* sc) {
     (void)ctx;
     if (!sc) return;
-    cudaFree(sc->V); cudaFree(sc->F); cudaFree(sc->FN); cudaFree(sc->img); cudaFree(sc->led);
+    cudaFree(sc->V); cudaFree(sc->F); cudaFree(sc->FN); cudaFree(sc->FC); cudaFree(sc->img); cudaFree(sc->led);
     delete sc;
 }
 
@@ -587,8 +704,8 @@ extern "C" int brdfgpu_shade_faces(brdfgpu_ctx* ctx, const brdfgpu_scene* sc, co
     if (e == cudaSuccess) {
         const V3 ey{eye[0], eye[1], eye[2]}, ce{center[0], center[1], center[2]};
         const int blocks = (sc->nF + 255) / 256;
-        if (literal_cosln) k_shade_faces<true><<<blocks, 256, 0, ctx->stream>>>(sc->V, sc->F, sc->FN, sc->nF, ey, ce, model, single, d_brdf, d_out);
-        else k_shade_faces<false><<<blocks, 256, 0, ctx->stream>>>(sc->V, sc->F, sc->FN, sc->nF, ey, ce, model, single, d_brdf, d_out);
+        if (literal_cosln) k_shade_faces<true><<<blocks, 256, 0, ctx->stream>>>(sc->FC, sc->FN, sc->nF, ey, ce, model, single, d_brdf, d_out);
+        else k_shade_faces<false><<<blocks, 256, 0, ctx->stream>>>(sc->FC, sc->FN, sc->nF, ey, ce, model, single, d_brdf, d_out);
         ++ctx->launches;
         e = cudaGetLastError();
     }
@@ -606,7 +723,7 @@ extern "C" int brdfgpu_shade_faces(brdfgpu_ctx* ctx, const brdfgpu_scene* sc, co
 extern "C" int brdfgpu_scene_set_gather_options(brdfgpu_ctx* ctx, brdfgpu_scene* sc, int flags, const double* kappa1, int ncam) {
     ctx = ctx_or_default(ctx);
     if (!ctx || !sc) return BRDFGPU_LM_ERROR;
-    const int known = BRDFGPU_GATHER_DEPTH_TEST | BRDFGPU_GATHER_CULL_BACKFACES | BRDFGPU_GATHER_KAPPA1;
+    const int known = BRDFGPU_GATHER_DEPTH_TEST | BRDFGPU_GATHER_CULL_BACKFACES | BRDFGPU_GATHER_KAPPA1 | BRDFGPU_GATHER_SEQ_DOT;
     if (flags & ~known) {
         set_error(ctx, "scene_set_gather_options: unknown flag");
         return BRDFGPU_LM_ERROR;
@@ -648,7 +765,7 @@ extern "C" int brdfgpu_calc_pixel2surface(brdfgpu_ctx* ctx, const brdfgpu_scene*
     ctx = ctx_or_default(ctx);
     if (!ctx || !sc || !cam || !map) return BRDFGPU_LM_ERROR;
     GatherDev g;
-    int rc = gather_device(ctx, sc, cam, 1, false, &g);
+    int rc = gather_device(ctx, sc, cam, 1, 0, nullptr, &g);
     if (rc == 0) {
         cudaError_t e = cudaMemcpyAsync(map, g.maps, sizeof(int) * (size_t)sc->W * sc->H, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -667,13 +784,16 @@ extern "C" long brdfgpu_gather(brdfgpu_ctx* ctx, const brdfgpu_scene* sc, const 
     ctx = ctx_or_default(ctx);
     if (!ctx || !sc || !cams) return BRDFGPU_LM_ERROR;
     GatherDev g;
-    long rc = gather_device(ctx, sc, cams, ncam, true, &g);
+    // only what the caller asked for is computed (each cosine costs a normalisation per sample)
+    const int plain = (phi ? kWantPhi : 0) | (thetaDash ? kWantNH : 0) | (theta ? kWantRV : 0) | (I ? kWantI : 0);
+    long rc = gather_device(ctx, sc, cams, ncam, plain, nullptr, &g);
+    if (rc == 0) rc = gather_finish(ctx, &g);
     if (rc == 0 && g.nfit > capacity && (fit_face || fit_pixel || phi || thetaDash || theta || I)) {
         set_error(ctx, "gather: capacity too small for the number of fits");
         rc = BRDFGPU_LM_ERROR;
     }
     if (rc == 0) {
-        const long ns = g.nfit * sc->nimg;
+        const long ns = g.nfit * sc->nimg, cap_ns = g.cap_fits * sc->nimg;
         cudaError_t e = cudaSuccess;
         auto down = [&](void* dst, const void* src, size_t bytes) {
             if (dst && bytes && e == cudaSuccess) e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream);
@@ -685,7 +805,7 @@ extern "C" long brdfgpu_gather(brdfgpu_ctx* ctx, const brdfgpu_scene* sc, const 
         down(thetaDash, g.thetaDash, sizeof(double) * ns);
         down(theta, g.theta, sizeof(double) * ns);
         if (I)
-            for (int ch = 0; ch < 3; ++ch) down(I + (size_t)ch * capacity * sc->nimg, g.I + (size_t)ch * ns, sizeof(double) * ns);
+            for (int ch = 0; ch < 3; ++ch) down(I + (size_t)ch * capacity * sc->nimg, g.I + (size_t)ch * cap_ns, sizeof(double) * ns);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) {
             set_error(ctx, std::string("gather: ") + cudaGetErrorString(e));
@@ -700,165 +820,129 @@ extern "C" long brdfgpu_gather(brdfgpu_ctx* ctx, const brdfgpu_scene* sc, const 
     return rc;
 }
 
+// The sample kernel writes straight into the arrays of the fit stage, which are sized for the capacity of the
+// gather (every face of every view mapped) because the fit count is only known after the one synchronisation
+// at the end; the handles then get their true sizes.
 extern "C" int brdfgpu_gather_resident(brdfgpu_ctx* ctx, const brdfgpu_scene* sc, const double* cams, int ncam, int model,
                                        int channel, brdfgpu_samples** global_out, brdfgpu_batch** batch_out,
                                        long* nfit_out) {
     ctx = ctx_or_default(ctx);
-    if (!ctx || !sc || !cams || channel < 0 || channel > 2 || (model != 0 && model != 1)) return BRDFGPU_LM_ERROR;
+    if (!ctx || !sc || !cams || ncam < 1 || channel < 0 || channel > 2 || (model != 0 && model != 1)) return BRDFGPU_LM_ERROR;
+    BG_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    const long cap_fits = (long)ncam * sc->nF;
+    brdfgpu_samples* s = nullptr;
+    brdfgpu_batch* b = nullptr;
+    if (global_out) *global_out = nullptr;
+    if (batch_out) *batch_out = nullptr;
+    if (global_out && samples_alloc(ctx, cap_fits * sc->nimg, model, &s) != 0) return BRDFGPU_LM_ERROR;
+    if (batch_out && batch_alloc(ctx, cap_fits, sc->nimg, model, &b) != 0) {
+        brdfgpu_samples_free(ctx, s);
+        return BRDFGPU_LM_ERROR;
+    }
+    GatherOut o;
+    o.model = model;
+    if (s) {
+        o.fit_c = s->c; o.fit_t = s->traw; o.fit_L = s->L; o.fit_x[channel] = s->x;
+        if (b) { o.fit2_c = b->c; o.fit2_t = b->traw; o.fit2_L = b->L; o.fit2_x = b->x; o.fit2_channel = channel; }
+    } else if (b) {
+        o.fit_c = b->c; o.fit_t = b->traw; o.fit_L = b->L; o.fit_x[channel] = b->x;
+    }
     GatherDev g;
-    int rc = gather_device(ctx, sc, cams, ncam, true, &g);
+    int rc = gather_device(ctx, sc, cams, ncam, 0, (s || b) ? &o : nullptr, &g);
+    if (rc == 0) rc = gather_finish(ctx, &g);
+    const long nfit = g.nfit;
+    g.release();
     if (rc != 0) {
-        g.release();
+        brdfgpu_samples_free(ctx, s);
+        brdfgpu_batch_free(ctx, b);
         return rc;
     }
-    const long ns = g.nfit * sc->nimg;
-    if (nfit_out) *nfit_out = g.nfit;
-    const double* t = model == 1 ? g.thetaDash : g.theta;
-    const size_t nb = sizeof(double) * (size_t)ns;
-    cudaError_t e = cudaSuccess;
-    if (global_out) {
-        *global_out = nullptr;
-        brdfgpu_samples* s = nullptr;
-        if (samples_alloc(ctx, ns, model, &s) != 0) rc = BRDFGPU_LM_ERROR;
-        else if (ns > 0) {
-            e = cudaMemcpyAsync(s->c, g.phi, nb, cudaMemcpyDeviceToDevice, ctx->stream);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(s->traw, t, nb, cudaMemcpyDeviceToDevice, ctx->stream);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(s->x, g.I + (size_t)channel * ns, nb, cudaMemcpyDeviceToDevice, ctx->stream);
-            if (e == cudaSuccess && samples_prepare(ctx, s) != 0) rc = BRDFGPU_LM_ERROR;
-        }
-        if (rc == 0 && e == cudaSuccess) *global_out = s;
-        else if (s) brdfgpu_samples_free(ctx, s);
-    }
-    if (batch_out && rc == 0 && e == cudaSuccess) {
-        *batch_out = nullptr;
-        brdfgpu_batch* b = nullptr;
-        if (batch_alloc(ctx, g.nfit, sc->nimg, model, &b) != 0) rc = BRDFGPU_LM_ERROR;
-        else if (ns > 0) {
-            e = cudaMemcpyAsync(b->c, g.phi, nb, cudaMemcpyDeviceToDevice, ctx->stream);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(b->traw, t, nb, cudaMemcpyDeviceToDevice, ctx->stream);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(b->x, g.I + (size_t)channel * ns, nb, cudaMemcpyDeviceToDevice, ctx->stream);
-            if (e == cudaSuccess && batch_prepare(ctx, b) != 0) rc = BRDFGPU_LM_ERROR;
-        }
-        if (rc == 0 && e == cudaSuccess) *batch_out = b;
-        else if (b) brdfgpu_batch_free(ctx, b);
-    }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    g.release();
-    if (e != cudaSuccess) {
-        set_error(ctx, std::string("gather_resident: ") + cudaGetErrorString(e));
-        return BRDFGPU_LM_ERROR;
-    }
-    return rc;
-}
-
-// resident global-fit sample set of one colour channel from a finished gather
-static int samples_from_gather(brdfgpu_ctx* ctx, const brdfgpu_scene* sc, const GatherDev& g, int model, int channel,
-                               brdfgpu_samples** out) {
-    const long ns = g.nfit * sc->nimg;
-    const size_t nb = sizeof(double) * (size_t)ns;
-    const double* t = model == 1 ? g.thetaDash : g.theta;
-    brdfgpu_samples* s = nullptr;
-    if (samples_alloc(ctx, ns, model, &s) != 0) return BRDFGPU_LM_ERROR;
-    cudaError_t e = cudaSuccess;
-    if (ns > 0) {
-        e = cudaMemcpyAsync(s->c, g.phi, nb, cudaMemcpyDeviceToDevice, ctx->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(s->traw, t, nb, cudaMemcpyDeviceToDevice, ctx->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(s->x, g.I + (size_t)channel * ns, nb, cudaMemcpyDeviceToDevice, ctx->stream);
-        if (e == cudaSuccess && samples_prepare(ctx, s) != 0) e = cudaErrorUnknown;
-    }
-    if (e != cudaSuccess) {
-        brdfgpu_samples_free(ctx, s);
-        set_error(ctx, std::string("gather -> samples: ") + cudaGetErrorString(e));
-        return BRDFGPU_LM_ERROR;
-    }
-    *out = s;
+    if (s) s->n = nfit * sc->nimg;
+    if (b) b->nfit = nfit;
+    if (nfit_out) *nfit_out = nfit;
+    if (global_out) *global_out = s;
+    if (batch_out) *batch_out = b;
     return 0;
 }
 
 // CBRDFdata::CalcBRDFEquation (brdfdata.cpp:1188-1227): ONE gather, then the fits of all three colour
-// channels as one batch of 3 x nfit problems (fit ch * nfit + f = face f, channel ch: the B, G, R
-// intensity blocks of the gather are already laid out that way) in a single launch.
+// channels as one batch of 3 x nfit problems (fit ch * nfit + f = face f, channel ch) in a single launch.  The
+// gather kernel writes the three channel blocks of the batch itself.
 extern "C" long brdfgpu_calc_brdf_equation(brdfgpu_ctx* ctx, const brdfgpu_scene* sc, const double* cam, int model,
                                            double* brdf_surfaces) {
     ctx = ctx_or_default(ctx);
-    if (!ctx || !sc || !cam || !brdf_surfaces) return BRDFGPU_LM_ERROR;
+    if (!ctx || !sc || !cam || !brdf_surfaces || (model != 0 && model != 1)) return BRDFGPU_LM_ERROR;
     static const double p0[3] = {0.5, 1.0, 1.0}, lb[3] = {0, 0, 0}, ub[3] = {100, 100, 100};
     static const double opts[5] = {1E-03, 1E-15, 1E-15, 1E-20, 1E-06};
-    GatherDev g;
-    if (gather_device(ctx, sc, cam, 1, true, &g) != 0) {
-        g.release();
-        return BRDFGPU_LM_ERROR;
-    }
-    const long nfit = g.nfit;
-    if (nfit == 0) {
-        g.release();
-        return 0;
-    }
-    const long ns = nfit * sc->nimg;
-    const size_t nb = sizeof(double) * (size_t)ns;
-    const double* t = model == 1 ? g.thetaDash : g.theta;
-    std::vector<int> faces(nfit);
-    std::vector<double> p(9 * (size_t)nfit);
+    BG_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     brdfgpu_batch* b = nullptr;
-    int rc = batch_alloc(ctx, 3 * nfit, sc->nimg, model, &b);
-    cudaError_t e = cudaSuccess;
-    if (rc == 0) {
-        e = cudaMemcpyAsync(faces.data(), g.fit_face, sizeof(int) * nfit, cudaMemcpyDeviceToHost, ctx->stream);
-        for (int ch = 0; ch < 3 && e == cudaSuccess; ++ch) {
-            e = cudaMemcpyAsync(b->c + (size_t)ch * ns, g.phi, nb, cudaMemcpyDeviceToDevice, ctx->stream);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(b->traw + (size_t)ch * ns, t, nb, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (batch_alloc(ctx, 3l * sc->nF, sc->nimg, model, &b) != 0) return BRDFGPU_LM_ERROR;
+    GatherOut o;
+    o.model = model;
+    o.fit_c = b->c; o.fit_t = b->traw; o.fit_L = b->L; o.fit_reps = 3;
+    for (int ch = 0; ch < 3; ++ch) o.fit_x[ch] = b->x;
+    o.fit_x_chan_blocks = 1;
+    GatherDev g;
+    int rc = gather_device(ctx, sc, cam, 1, 0, &o, &g);
+    if (rc == 0) rc = gather_finish(ctx, &g);
+    const long nfit = g.nfit;
+    std::vector<int> faces(nfit > 0 ? nfit : 1);
+    std::vector<double> p(9 * (size_t)(nfit > 0 ? nfit : 1));
+    if (rc == 0 && nfit > 0) {
+        b->nfit = 3 * nfit;
+        cudaError_t e = cudaMemcpyAsync(faces.data(), g.fit_face, sizeof(int) * nfit, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) {
+            set_error(ctx, std::string("calc_brdf_equation: ") + cudaGetErrorString(e));
+            rc = BRDFGPU_LM_ERROR;
         }
-        if (e == cudaSuccess) e = cudaMemcpyAsync(b->x, g.I, 3 * nb, cudaMemcpyDeviceToDevice, ctx->stream);
-        if (e != cudaSuccess) rc = BRDFGPU_LM_ERROR;
-        if (rc == 0) rc = batch_prepare(ctx, b);
         if (rc == 0) rc = brdfgpu_batch_fit(ctx, b, p0, lb, ub, 100, opts, BRDFGPU_JAC_FD);
         if (rc == 0) rc = brdfgpu_batch_results(ctx, b, p.data(), nullptr, nullptr);
     }
-    if (b) brdfgpu_batch_free(ctx, b);
+    brdfgpu_batch_free(ctx, b);
     g.release();
-    if (rc != 0) {
-        if (e != cudaSuccess) set_error(ctx, std::string("calc_brdf_equation: ") + cudaGetErrorString(e));
-        return BRDFGPU_LM_ERROR;
-    }
+    if (rc != 0) return BRDFGPU_LM_ERROR;
     for (int ch = 0; ch < 3; ++ch)          // brdfdata.cpp:1205: B, G, R
         for (long f = 0; f < nfit; ++f)     // SaveValuesToSurface, brdfdata.cpp:368-377
             for (int j = 0; j < 3; ++j) brdf_surfaces[((size_t)faces[f] * 3 + ch) * 3 + j] = p[3 * ((size_t)ch * nfit + f) + j];
     return nfit;
 }
 
-// CBRDFdata::CalcBRDFEquation_SingleBRDF (brdfdata.cpp:1138-1186): one gather, one global fit per channel
+// CBRDFdata::CalcBRDFEquation_SingleBRDF (brdfdata.cpp:1138-1186): one gather, one global fit per channel.  The
+// three channel sets share cosphi / the model cosine / its log and differ in the measurements only.
 extern "C" long brdfgpu_calc_brdf_equation_single(brdfgpu_ctx* ctx, const brdfgpu_scene* sc, const double* cam, int model,
                                                   double* single_brdf, double* info, int* ret) {
     ctx = ctx_or_default(ctx);
-    if (!ctx || !sc || !cam || !single_brdf) return BRDFGPU_LM_ERROR;
+    if (!ctx || !sc || !cam || !single_brdf || (model != 0 && model != 1)) return BRDFGPU_LM_ERROR;
     static const double lb[3] = {0, 0, 0}, ub[3] = {100, 100, 100};
     static const double opts[5] = {1E-03, 1E-15, 1E-10, 1E-50, 1.0};
-    GatherDev g;
-    if (gather_device(ctx, sc, cam, 1, true, &g) != 0) {
-        g.release();
-        return BRDFGPU_LM_ERROR;
-    }
-    const long nfit = g.nfit;
+    BG_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     Trace tr("calc_brdf_equation_single");
-    for (int ch = 0; ch < 3; ++ch) {
-        brdfgpu_samples* s = nullptr;
-        if (samples_from_gather(ctx, sc, g, model, ch, &s) != 0) {
-            g.release();
-            return BRDFGPU_LM_ERROR;
-        }
-        tr.mark("samples from gather (4 cudaMalloc, 3 D2D, log pass)");
+    const size_t stride = (((size_t)sc->nF * sc->nimg) + 15) & ~(size_t)15;
+    double* block = nullptr;
+    BG_CUDA_OK(ctx, cudaMallocAsync(&block, sizeof(double) * 6 * stride, ctx->stream));
+    GatherOut o;
+    o.model = model;
+    o.fit_c = block; o.fit_t = block + stride; o.fit_L = block + 2 * stride;
+    for (int ch = 0; ch < 3; ++ch) o.fit_x[ch] = block + (3 + ch) * stride;
+    GatherDev g;
+    int rc = gather_device(ctx, sc, cam, 1, 0, &o, &g);
+    if (rc == 0) rc = gather_finish(ctx, &g);
+    const long nfit = g.nfit;
+    g.release();
+    tr.mark("gather");
+    for (int ch = 0; ch < 3 && rc == 0; ++ch) {
+        brdfgpu_samples view;  // not an owner: block stays null
+        view.n = nfit * sc->nimg; view.capacity = (long)stride; view.model = model; view.stream = ctx->stream;
+        view.c = o.fit_c; view.traw = o.fit_t; view.L = o.fit_L; view.x = o.fit_x[ch];
         double p[3] = {0.0, 0.0, 0.0}, inf[10] = {0};
-        const int r = brdfgpu_fit_global(ctx, s, p, 3, lb, ub, nullptr, 2000, opts, inf, nullptr, BRDFGPU_DRIVE_PERSISTENT,
+        const int r = brdfgpu_fit_global(ctx, &view, p, 3, lb, ub, nullptr, 2000, opts, inf, nullptr, BRDFGPU_DRIVE_PERSISTENT,
                                          BRDFGPU_JAC_FD);
         tr.mark("global fit");
-        brdfgpu_samples_free(ctx, s);
-        tr.mark("samples free");
         for (int j = 0; j < 3; ++j) single_brdf[ch * 3 + j] = p[j];
         if (info)
             for (int j = 0; j < 10; ++j) info[ch * 10 + j] = inf[j];
         if (ret) ret[ch] = r;
     }
-    g.release();
-    tr.mark("gather release (12 cudaFree)");
-    return nfit;
+    cudaFreeAsync(block, ctx->stream);
+    return rc == 0 ? nfit : (long)BRDFGPU_LM_ERROR;
 }

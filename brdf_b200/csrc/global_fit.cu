@@ -22,6 +22,7 @@
 //                sweeps (GridEval) so that an iteration needs one or two sweeps.
 #include <cooperative_groups.h>
 
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -321,7 +322,12 @@ __global__ void k_model_jac(const double* __restrict__ c, const double* __restri
 int wait_ticket(brdfgpu_ctx* ctx, unsigned long long seq) {
     // the last CTA stores the sums and then the ticket into mapped pinned memory
     for (unsigned spin = 0;; ++spin) {
-        if (*ctx->h_seq == seq) return 0;
+        if (*ctx->h_seq == seq) {
+            // the sums were stored before the ticket (GPU side: __threadfence_system); keep the host's loads of
+            // h_result behind the load of the ticket on weakly ordered hosts too (Grace / aarch64)
+            std::atomic_thread_fence(std::memory_order_acquire);
+            return 0;
+        }
         if ((spin & 0xfffff) == 0xfffff) {
             cudaError_t e = cudaStreamQuery(ctx->stream);
             if (e != cudaSuccess && e != cudaErrorNotReady) {
@@ -486,6 +492,14 @@ int global_residuals(brdfgpu_ctx* ctx, const brdfgpu_samples* s, const double* p
     return 0;
 }
 
+// Memory that came from cudaMallocAsync goes back to the pool in stream order while its context is alive
+// (no device-wide synchronisation, unlike cudaFree); handles that outlive their context fall back to cudaFree.
+void free_block(brdfgpu_ctx* ctx, void* block, cudaStream_t stream) {
+    if (!block) return;
+    if (ctx && ctx->stream == stream && stream) cudaFreeAsync(block, stream);
+    else cudaFree(block);
+}
+
 int samples_alloc(brdfgpu_ctx* ctx, long n, int model, brdfgpu_samples** out) {
     if (n < 0 || (model != 0 && model != 1)) {
         set_error(ctx, "samples: bad size or model");
@@ -493,18 +507,19 @@ int samples_alloc(brdfgpu_ctx* ctx, long n, int model, brdfgpu_samples** out) {
     }
     brdfgpu_samples* s = new brdfgpu_samples;
     s->n = n;
+    s->capacity = n;
     s->model = model;
-    const size_t bytes = sizeof(double) * (size_t)(n > 0 ? n + (n & 1) : 2);
-    cudaError_t e = cudaMalloc(&s->c, bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&s->L, bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&s->x, bytes);
-    if (e == cudaSuccess) e = cudaMalloc(&s->traw, bytes);
+    s->stream = ctx->stream;
+    // every array starts on a 128-byte boundary (16-byte vector loads, bulk async copies) and holds an even count
+    const size_t stride = ((size_t)(n > 0 ? n : 2) + 15) & ~(size_t)15;
+    cudaError_t e = cudaMallocAsync(&s->block, sizeof(double) * 4 * stride, ctx->stream);
     if (e != cudaSuccess) {
-        cudaFree(s->c); cudaFree(s->L); cudaFree(s->x); cudaFree(s->traw);
         delete s;
-        set_error(ctx, std::string("samples: cudaMalloc: ") + cudaGetErrorString(e));
+        set_error(ctx, std::string("samples: cudaMallocAsync: ") + cudaGetErrorString(e));
         return BRDFGPU_LM_ERROR;
     }
+    double* base = static_cast<double*>(s->block);
+    s->c = base; s->L = base + stride; s->x = base + 2 * stride; s->traw = base + 3 * stride;
     *out = s;
     return 0;
 }
@@ -1536,6 +1551,16 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_persistent_fit(SampleVie
     }
     __syncthreads();
 
+    // covariance on several GPUs needs the sample count of ALL ranks (lmbc_core.c:994-1002: sumsq / (n - m)); it
+    // travels through the kernel's own exchange, so a context that only attached peer buffers (no NCCL
+    // communicator) can still return it.  Exact: counts are integers far below 2^53.
+    if (spec.want_n_all) {
+        double cnt[1] = {(blockIdx.x == 0 && threadIdx.x == 0) ? (double)v.n : 0.0};
+        all_reduce<1>(cnt, clock64());
+        if (blockIdx.x == 0 && threadIdx.x == 0) out->n_all = s_res[0];
+        __syncthreads();
+    }
+
     if (threadIdx.x >= 32) {
         serve_sweeps();
         return;
@@ -1711,6 +1736,7 @@ int global_fit(brdfgpu_ctx* ctx, const brdfgpu_samples* s, double* p, int m, con
 
     double fit_info[10], JtJ[9];
     int ret;
+    long n_all_kernel = 0;
     const bool can_persist = ctx->coop && (ctx->nranks == 1 || ctx->peer_attached);
     PersistPlan plan{0, 0, 0};
     // Far beyond on-chip residency (> 4e7 samples per GPU, ~1 GB) the kernel-per-evaluation driver is
@@ -1724,6 +1750,7 @@ int global_fit(brdfgpu_ctx* ctx, const brdfgpu_samples* s, double* p, int m, con
         spec.m = m; spec.itmax = itmax; spec.jac_mode = jkind; spec.delta = delta; spec.opt = o;
         spec.has_lb = lb != nullptr; spec.has_ub = ub != nullptr; spec.has_dscl = dscl != nullptr;
         spec.unconstrained = unconstrained;
+        spec.want_n_all = (covar != nullptr && ctx->nranks > 1) ? 1 : 0;
         // BRDFGPU_SPEC_JAC=0 switches the speculative Jacobians off (A/B tests: results must not change)
         // (a bit mask for experiments: 1 = speculate at the trial / line-search / first-candidate sites, 2 = fuse the
         // announced first candidate into the last line-search probe, 4 = start a walk at the last walk's width)
@@ -1762,7 +1789,7 @@ int global_fit(brdfgpu_ctx* ctx, const brdfgpu_samples* s, double* p, int m, con
         const GlobalFitOut* h = static_cast<const GlobalFitOut*>(ctx->h_fitio);
         if (ctx->nranks > 1) ctx->peer_epoch = h->peer_epoch;
         if (h->aborted) {
-            ctx->peer_attached = false;  // exchange tags are out of step now: peers must be re-attached
+            ctx->peer_attached = false;  // exchange tags are out of step now: every rank exports again and re-attaches
             set_error(ctx, "fit abandoned: an exchange partner (CTA or peer GPU) never delivered its sums");
             return BRDFGPU_LM_ERROR;
         }
@@ -1774,6 +1801,7 @@ int global_fit(brdfgpu_ctx* ctx, const brdfgpu_samples* s, double* p, int m, con
         for (int i = 0; i < 7; ++i) ctx->fit_stats[12 + i] = (unsigned long long)h->cyc_ctl[i];
         ctx->fit_stats[19] = h->spec_issued; ctx->fit_stats[20] = h->spec_hits; ctx->fit_stats[21] = h->creep_fused;
         ret = h->ret;
+        n_all_kernel = (long)h->n_all;
         for (int i = 0; i < 3; ++i) p[i] = h->p[i];
         for (int i = 0; i < 10; ++i) fit_info[i] = h->info[i];
         for (int i = 0; i < 9; ++i) JtJ[i] = h->JtJ[i];
@@ -1795,14 +1823,15 @@ int global_fit(brdfgpu_ctx* ctx, const brdfgpu_samples* s, double* p, int m, con
     if (covar) {  // lmbc_core.c:994-1002
         // ||e||^2 over ALL samples of all ranks went into fit_info[1]; n is the global count
         long n_all = s->n;
-        if (ctx->nranks > 1) {
-            double cnt = (double)s->n;
-            // sample counts differ per rank by at most one: sum them through the same exchange
+        if (ctx->nranks > 1 && persist) {
+            n_all = n_all_kernel;  // summed by the fit kernel's own exchange
+        } else if (ctx->nranks > 1) {
+            double cnt = (double)s->n;  // host-driven fit: the communicator that carried its sums
             double* tmp = ctx->d_result;
-            cudaMemcpyAsync(tmp, &cnt, sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+            BG_CUDA_OK(ctx, cudaMemcpyAsync(tmp, &cnt, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
             if (comm_allreduce_device(ctx, tmp, 1) != 0) return BRDFGPU_LM_ERROR;
-            cudaMemcpyAsync(&cnt, tmp, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
-            cudaStreamSynchronize(ctx->stream);
+            BG_CUDA_OK(ctx, cudaMemcpyAsync(&cnt, tmp, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            BG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
             n_all = (long)cnt;
         }
         lm_covar<3>(JtJ, covar, fit_info[1], m, n_all);

@@ -167,6 +167,10 @@ static bool decode_png(const std::vector<unsigned char>& file, int* W, int* H, s
             return false;
         }
         const unsigned char* data = &file[pos + 8];
+        if ((uint32_t)crc32(crc32(0L, Z_NULL, 0), type, 4 + len) != be32(&file[pos + 8 + len])) {  // type + data, PNG spec 5.3
+            *why = "PNG chunk CRC mismatch (corrupt file)";
+            return false;
+        }
         if (!memcmp(type, "IHDR", 4)) {
             if (len < 13) {
                 *why = "bad IHDR";
@@ -187,6 +191,13 @@ static bool decode_png(const std::vector<unsigned char>& file, int* W, int* H, s
     }
     if (!have_hdr || w <= 0 || h <= 0) {
         *why = "PNG without a valid IHDR";
+        return false;
+    }
+    // a corrupt or crafted IHDR must not turn into a giant allocation (cv::imread returns an empty Mat and the
+    // reference fails cleanly): bound each side, and the pixel count against what the IDAT data can inflate to
+    // (deflate expands by at most ~1032x)
+    if (w > 65535 || h > 65535) {
+        *why = "PNG dimensions out of range (each side <= 65535)";
         return false;
     }
     *W = w;
@@ -210,6 +221,10 @@ static bool decode_png(const std::vector<unsigned char>& file, int* W, int* H, s
         return false;
     }
     const size_t stride = (size_t)w * channels;
+    if ((stride + 1) * (size_t)h > idat.size() * 1032 + 1024) {
+        *why = "PNG header announces more pixels than its IDAT data can hold";
+        return false;
+    }
     std::vector<unsigned char> raw((stride + 1) * (size_t)h);
     uLongf raw_len = (uLongf)raw.size();
     const int zr = uncompress(raw.data(), &raw_len, idat.data(), (uLong)idat.size());
@@ -272,14 +287,14 @@ static bool decode_png(const std::vector<unsigned char>& file, int* W, int* H, s
 
 using namespace brdfgpu;
 
-extern "C" int brdfgpu_read_cal(const char* path, double* cam16) {
+static int read_cal_impl(const char* path, double* cam16) {
     brdfgpu_ctx* ctx = nullptr;
     std::vector<unsigned char> buf;
     if (!cam16 || !read_whole_file(path, &buf, ctx)) return BRDFGPU_LM_ERROR;
     return parse_cal(buf, cam16);
 }
 
-extern "C" int brdfgpu_read_cal_kappa1(const char* path, double* kappa1) {
+static int read_cal_kappa1_impl(const char* path, double* kappa1) {
     brdfgpu_ctx* ctx = nullptr;
     std::vector<unsigned char> buf;
     if (!kappa1 || !read_whole_file(path, &buf, ctx)) return BRDFGPU_LM_ERROR;
@@ -289,7 +304,7 @@ extern "C" int brdfgpu_read_cal_kappa1(const char* path, double* kappa1) {
     return has;
 }
 
-extern "C" int brdfgpu_read_obj(const char* path, double* V, int* F, int* nV, int* nF) {
+static int read_obj_impl(const char* path, double* V, int* F, int* nV, int* nF) {
     brdfgpu_ctx* ctx = nullptr;
     std::vector<unsigned char> buf;
     if (!read_whole_file(path, &buf, ctx)) return BRDFGPU_LM_ERROR;
@@ -313,7 +328,7 @@ extern "C" int brdfgpu_read_obj(const char* path, double* V, int* F, int* nV, in
     return 0;
 }
 
-extern "C" int brdfgpu_read_png(const char* path, unsigned char* bgr, int* W, int* H) {
+static int read_png_impl(const char* path, unsigned char* bgr, int* W, int* H) {
     brdfgpu_ctx* ctx = nullptr;
     std::vector<unsigned char> file, out;
     std::string why;
@@ -335,8 +350,8 @@ extern "C" int brdfgpu_read_png(const char* path, unsigned char* bgr, int* W, in
     return 0;
 }
 
-extern "C" int brdfgpu_scene_load(brdfgpu_ctx* ctx, const char* image_folder, const char* obj_path, const char* cal_path,
-                                  int nimg, brdfgpu_scene** out, double* cam16) {
+static int scene_load_impl(brdfgpu_ctx* ctx, const char* image_folder, const char* obj_path, const char* cal_path,
+                           int nimg, brdfgpu_scene** out, double* cam16) {
     if (!ctx) ctx = default_ctx();  // NULL = the process-wide context, as everywhere in this API
     if (!ctx || !image_folder || !obj_path || !out || nimg < 1) return BRDFGPU_LM_ERROR;
     // LoadModel (main.cpp:41)
@@ -395,4 +410,35 @@ extern "C" int brdfgpu_scene_load(brdfgpu_ctx* ctx, const char* image_folder, co
     // InitLEDs (main.cpp:59): led == NULL selects the reference table when nimg == 16
     return brdfgpu_scene_create(ctx, V.data(), (int)(V.size() / 3), F.data(), (int)(F.size() / 3), ptrs.data(), nimg, W, H,
                                 dark.empty() ? nullptr : dark.data(), nullptr, out);
+}
+
+// The C boundary: nothing thrown by the parsers above (std::bad_alloc / length_error on absurd sizes in a corrupt
+// file) may cross an extern "C" frame -- a C host would see std::terminate.  Failures become BRDFGPU_LM_ERROR with
+// brdfgpu_last_error() set, like a cv::imread that returns an empty Mat.
+template <class Fn>
+static int guarded(const char* what, brdfgpu_ctx* ctx, Fn&& fn) {
+    try {
+        return fn();
+    } catch (const std::exception& e) {
+        set_error(ctx, std::string(what) + ": " + e.what());
+    } catch (...) {
+        set_error(ctx, std::string(what) + ": unknown failure");
+    }
+    return BRDFGPU_LM_ERROR;
+}
+extern "C" int brdfgpu_read_cal(const char* path, double* cam16) {
+    return guarded("brdfgpu_read_cal", nullptr, [&] { return read_cal_impl(path, cam16); });
+}
+extern "C" int brdfgpu_read_cal_kappa1(const char* path, double* kappa1) {
+    return guarded("brdfgpu_read_cal_kappa1", nullptr, [&] { return read_cal_kappa1_impl(path, kappa1); });
+}
+extern "C" int brdfgpu_read_obj(const char* path, double* V, int* F, int* nV, int* nF) {
+    return guarded("brdfgpu_read_obj", nullptr, [&] { return read_obj_impl(path, V, F, nV, nF); });
+}
+extern "C" int brdfgpu_read_png(const char* path, unsigned char* bgr, int* W, int* H) {
+    return guarded("brdfgpu_read_png", nullptr, [&] { return read_png_impl(path, bgr, W, H); });
+}
+extern "C" int brdfgpu_scene_load(brdfgpu_ctx* ctx, const char* image_folder, const char* obj_path, const char* cal_path,
+                                  int nimg, brdfgpu_scene** out, double* cam16) {
+    return guarded("brdfgpu_scene_load", ctx, [&] { return scene_load_impl(ctx, image_folder, obj_path, cal_path, nimg, out, cam16); });
 }

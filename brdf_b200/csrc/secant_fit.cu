@@ -274,10 +274,10 @@ int global_fit_secant(brdfgpu_ctx* ctx, brdfgpu_samples* s, double* p, int m, in
         long n_all = s->n;
         if (ctx->nranks > 1) {
             double cnt = (double)s->n;
-            cudaMemcpyAsync(ctx->d_result, &cnt, sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+            BG_CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_result, &cnt, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
             if (comm_allreduce_device(ctx, ctx->d_result, 1) != 0) return BRDFGPU_LM_ERROR;
-            cudaMemcpyAsync(&cnt, ctx->d_result, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
-            cudaStreamSynchronize(ctx->stream);
+            BG_CUDA_OK(ctx, cudaMemcpyAsync(&cnt, ctx->d_result, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            BG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
             n_all = (long)cnt;
         }
         lm_covar<3>(JtJ, covar, e_cur, m, n_all);

@@ -28,7 +28,12 @@ extern "C" {
 #define BRDFGPU_LM_INIT_MU 1E-03
 #define BRDFGPU_LM_STOP_THRESH 1E-17
 #define BRDFGPU_LM_DIFF_DELTA 1E-06
-#define BRDFGPU_MAX_PARAMS 8 /* "single-digit parameter count" (BASELINE.json north_star) */
+/* The two BRDF models have exactly m == 3 parameters (kd, ks, n: BRDFFunc reads p[0..2] only,
+ * brdfdata.cpp:980-986).  Every fit entry point on BRDF samples (sections 1-3) requires m == 3 and returns
+ * BRDFGPU_LM_ERROR for any other m.  Only the reduced-evaluator control loop of section 6, which never sees a
+ * model, is generic: 1 <= m <= BRDFGPU_MAX_PARAMS ("single-digit parameter count", BASELINE.json north_star). */
+#define BRDFGPU_NUM_PARAMS 3
+#define BRDFGPU_MAX_PARAMS 8
 
 /* BRDF models, CBRDFdata::m_model (brdfdata.cpp:978,983; main.cpp:43 selects 1) */
 #define BRDFGPU_MODEL_PHONG 0
@@ -59,7 +64,10 @@ void brdfgpu_BRDFJac(double *p, double *jac, int m, int n, void *adata);
 /* Replaces dlevmar_bc_dif (levmar/levmar.h:124-127, lmbc_core.c:1062-1129): identical argument
  * list, return value (#iterations or LM_ERROR) and info[0..9] meaning.  `func` must be
  * brdfgpu_BRDFFunc and `adata` a brdfgpu_extraData*; any other callback returns LM_ERROR (no CPU
- * path by design).  3 <= m <= BRDFGPU_MAX_PARAMS, n >= m.  `work` is accepted and ignored. */
+ * path by design).  m must be BRDFGPU_NUM_PARAMS (3): levmar's signature is generic in m
+ * (levmar/levmar.h:124-127) but the only callback this library accepts has three parameters; m != 3 returns
+ * LM_ERROR with brdfgpu_last_error(NULL) = "... the BRDF models have exactly 3 parameters (kd, ks, n) ...",
+ * checked before any GPU work.  n >= m.  `work` is accepted and ignored. */
 int brdfgpu_dlevmar_bc_dif(brdfgpu_func_t func, double *p, double *x, int m, int n, double *lb,
                            double *ub, double *dscl, int itmax, double *opts, double *info,
                            double *work, double *covar, void *adata);
@@ -255,6 +263,11 @@ long brdfgpu_gather(brdfgpu_ctx *ctx, const brdfgpu_scene *sc, const double *cam
 #define BRDFGPU_GATHER_DEPTH_TEST 1
 #define BRDFGPU_GATHER_CULL_BACKFACES 2
 #define BRDFGPU_GATHER_KAPPA1 4
+/* Evaluation order of the final dot products of GetCosLN / GetCosNH (brdfdata.cpp:893, 937).  The default is what
+ * Eigen 3.3 -- the version the reference's Makefile dependency list shows -- does for a fixed-size vector times a
+ * row of a column-major MatrixXd: a0*b0 + (a1*b1 + a2*b2).  SEQ_DOT sums left to right, (a0*b0 + a1*b1) + a2*b2
+ * (round 1's definition; differs in the last bit of some cosines).  oracle/gather_oracle.c has the derivation. */
+#define BRDFGPU_GATHER_SEQ_DOT 8
 int brdfgpu_scene_set_gather_options(brdfgpu_ctx *ctx, brdfgpu_scene *sc, int flags, const double *kappa1, int ncam);
 
 /* Gather that stays on the device and hands the samples straight to the fit stages. */
@@ -332,11 +345,16 @@ int brdfgpu_comm_allreduce(brdfgpu_ctx *ctx, double *buf, int count);
 
 /* Fused in-kernel exchange: with peer buffers attached the persistent fit kernel all-reduces its
  * sums itself, by peer stores over NVLink / NVSwitch inside the same launch (no NCCL call, no host
- * round trip per evaluation).  Every rank exports one 64-byte CUDA-IPC handle, the launcher
- * gathers them (rank order) and every rank attaches all of them.  One process per GPU. */
-#define BRDFGPU_IPC_HANDLE_BYTES 64
-int brdfgpu_peer_export(brdfgpu_ctx *ctx, char *handle64);
-int brdfgpu_peer_attach(brdfgpu_ctx *ctx, const char *handles /* nranks x 64 */, int rank, int nranks);
+ * round trip per evaluation).  Every rank exports one 72-byte record (a 64-byte CUDA-IPC handle + the
+ * exchange tag its buffer has reached), the launcher gathers them (rank order) and every rank attaches
+ * all of them.  One process per GPU.
+ * Re-attaching (after brdfgpu_peer_detach, or after a fit was abandoned because a peer never delivered, which
+ * leaves the ranks' tags out of step): every rank exports AGAIN and attaches the fresh records.  The new session
+ * starts above the highest tag any rank ever wrote, so cells left in the buffers by the old session can never be
+ * taken for fresh ones; no memset and no barrier between attach and the first fit are needed. */
+#define BRDFGPU_IPC_HANDLE_BYTES 72
+int brdfgpu_peer_export(brdfgpu_ctx *ctx, char *handle72);
+int brdfgpu_peer_attach(brdfgpu_ctx *ctx, const char *handles /* nranks x 72 */, int rank, int nranks);
 void brdfgpu_peer_detach(brdfgpu_ctx *ctx);
 
 /* ------------------------------------------------------------------------------------------------

@@ -7,12 +7,46 @@
  * reference cannot land a single centroid inside the photographs).
  *
  * PARITY UNPINNED at this boundary: the reference C++ needs OpenCV/Eigen/libigl/GL and cannot be
- * built here, and it ships no test for these functions, so this file DEFINES the arithmetic the
- * CUDA gather must reproduce bit-for-bit:
+ * built here, and it ships no test for these functions, so no OUTPUT of the reference pins this file.
+ * What narrows the arithmetic down instead is the reference's own build record: its qmake Makefile
+ * (reference Makefile:17) compiles with `-O2 -std=gnu++11`, no -march/-mfma/-ffast-math -> x86-64
+ * baseline = SSE2 packets of two doubles, no FMA contraction possible, no reassociation; and its
+ * dependency list (reference Makefile, the ../libigl/external/eigen/Eigen/src/Core/... entries)
+ * names CoreEvaluators.h, AssignEvaluator.h, arch/CUDA/Half.h, arch/AVX512, arch/ZVector,
+ * arch/Default/ConjHelper.h and no IndexedView.h / Reshaped.h / arch/GPU: that file set is Eigen
+ * 3.3.x (>= 3.3.5; libigl's external/eigen pin is 3.3.7), not 3.2 (no evaluators) and not 3.4.
+ * Eigen 3.3's Redux.h / Dot.h then fix the evaluation order of the three Eigen expressions used:
+ *
+ *   v.normalize() on a RowVector3d (brdfdata.cpp:327, 838, 843, 890, 934)
+ *       Dot.h: z = squaredNorm(); if (z > 0) v /= sqrt(z)  -- a true division per component.
+ *       squaredNorm() = cwiseAbs2().sum() on a plain fixed-size vector: the evaluator has
+ *       PacketAccessBit (3.3 allows unaligned packets) and LinearAccessBit, find_best_packet<double,3>
+ *       is Packet2d, so redux_impl<LinearVectorizedTraversal, CompleteUnrolling> runs:
+ *       predux({x0*x0, x1*x1}) then func(res, x2*x2)         =>  (x0*x0 + x1*x1) + x2*x2
+ *   lightDir.cwiseProduct(face_normals.row(i)).sum(), H.cwiseProduct(face_normals.row(i)).sum()
+ *   (brdfdata.cpp:893, 937)
+ *       face_normals is a column-major MatrixXd, so .row(i) is a Block with a run-time inner stride:
+ *       its evaluator has no PacketAccessBit, hence neither has the CwiseBinaryOp.  The expression
+ *       takes its compile-time size (3) from its LEFT operand (CwiseBinaryOp traits use Lhs), so
+ *       redux_impl<DefaultTraversal, CompleteUnrolling> -> redux_novec_unroller<0, 3>, which splits
+ *       by halves, HalfLength = 3/2 = 1:  func(unroller<0,1>, unroller<1,2>)
+ *                                                             =>  a0*b0 + (a1*b1 + a2*b2)
+ *   face_normals.row(i).cwiseProduct(lightDir).sum() (brdfdata.cpp:841; glutcallbacks.cpp:383, 393)
+ *       same operands the other way round: the LEFT operand is the Block, size Dynamic, so
+ *       redux_impl<DefaultTraversal, NoUnrolling>: res = coeff(0); for i = 1.. res = func(res, coeff(i))
+ *                                                             =>  (a0*b0 + a1*b1) + a2*b2
+ *   R.cwiseProduct(P).sum(), viewDir.cwiseProduct(R).sum() on two plain RowVector3d (brdfdata.cpp:849;
+ *   glutcallbacks.cpp:420): vectorised like squaredNorm       =>  (a0*b0 + a1*b1) + a2*b2
+ *
+ * (Eigen's headers are not installed in this image, so the Redux.h reasoning above is from the 3.3
+ * sources as published, not re-checked against a local copy.)  Round 1 summed every dot left to
+ * right; that order is kept as oracle_set_dot_order(ORACLE_DOT_SEQUENTIAL) / BRDFGPU_GATHER_SEQ_DOT and
+ * differs from the canonical one only in GetCosLN / GetCosNH.  The Tsai projection is not Eigen code
+ * (SURVEY.md 8c defines it): its dots stay (d0*n0 + d1*n1) + d2*n2.
+ *
+ * The CUDA gather must reproduce this file bit-for-bit:
  *   - every operation is a single IEEE-754 double +,-,*,/ or sqrt, never fused (-ffp-contract=off);
- *   - 3-term sums/dots associate left to right: (a0*b0 + a1*b1) + a2*b2;
  *   - centroid = (((0 + v0) + v1) + v2) / 3.0  per component (brdfdata.cpp:653-660);
- *   - normalisation divides each component by sqrt((x*x + y*y) + z*z) when that is > 0;
  *   - double -> int conversion truncates (brdfdata.cpp:677).
  */
 #include <math.h>
@@ -24,6 +58,16 @@
 enum { CAM_CX = 0, CAM_CY, CAM_F, CAM_SX, CAM_N = 4, CAM_O = 7, CAM_A = 10, CAM_P = 13 };
 
 static double dot3(const double *a, const double *b) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
+
+/* fixed-size vector .cwiseProduct(row of a column-major MatrixXd).sum(): Eigen 3.3's unrolled scalar
+ * reduction splits by halves (see the header); ORACLE_DOT_SEQUENTIAL restores round 1's guess */
+static int g_dot_order = ORACLE_DOT_EIGEN33;
+void oracle_set_dot_order(int order) { g_dot_order = order; }
+static double dot3_row(const double *a, const double *b)
+{
+    if (g_dot_order == ORACLE_DOT_SEQUENTIAL) return dot3(a, b);
+    return a[0] * b[0] + (a[1] * b[1] + a[2] * b[2]);
+}
 
 static void normalize3(double *v)
 {
@@ -217,7 +261,7 @@ void oracle_cos_ln(const double *V, const int *F, const double *FN, const double
         l[1] = led[k * 3 + 1] - c[1];
         l[2] = led[k * 3 + 2] - c[2];
         normalize3(l);
-        phi[k] = dot3(l, FN + (size_t)face * 3);
+        phi[k] = dot3_row(l, FN + (size_t)face * 3);
     }
 }
 
@@ -233,7 +277,7 @@ void oracle_cos_nh(const double *V, const int *F, const double *FN, const double
         h[1] = led[k * 3 + 1] - 2 * c[1] + cam[CAM_P + 1];
         h[2] = led[k * 3 + 2] - 2 * c[2] + cam[CAM_P + 2];
         normalize3(h);
-        thetaDash[k] = dot3(h, FN + (size_t)face * 3);
+        thetaDash[k] = dot3_row(h, FN + (size_t)face * 3);
     }
 }
 

@@ -5,7 +5,7 @@
  * (reference: levmar/lmbc_core.c, lm_core.c, misc_core.c, Axb_core.c, built without LAPACK as
  * shipped, levmar/levmar.h:31).  The arithmetic -- operation order, summation order, comparison
  * direction -- follows the cited lines so that results are bit-identical to the reference build
- * (checked against oracle/_ref/liblevmar_ref.so in tests/test_oracle_vs_ref.py); the code
+ * (checked against oracle/_ref/liblevmar_ref.so in tests/test_oracle_kat.py and tests/test_oracle_golden.py); the code
  * organisation (one shared iteration context, helper routines, no macros/templating over the
  * real type) is this repository's own.
  */

@@ -92,6 +92,12 @@ int  oracle_gather(const double *V, const int *F, int nF, const double *cam, con
                    int *map, int *fit_face, int *fit_pixel,
                    double *phi, double *thetaDash, double *theta, double *I /* [3][nfit*nimg] */);
 
+/* Evaluation order of the Eigen reductions in GetCosLN / GetCosNH (gather_oracle.c header): the canonical
+ * order is Eigen 3.3's, a0*b0 + (a1*b1 + a2*b2); ORACLE_DOT_SEQUENTIAL = (a0*b0 + a1*b1) + a2*b2 */
+#define ORACLE_DOT_EIGEN33 0
+#define ORACLE_DOT_SEQUENTIAL 1
+void oracle_set_dot_order(int order);
+
 /* Options beyond the reference (depth test, back-face culling, Tsai kappa1); flags 0 == the functions above */
 #define ORACLE_GATHER_DEPTH_TEST 1
 #define ORACLE_GATHER_CULL_BACKFACES 2

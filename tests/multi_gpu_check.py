@@ -60,9 +60,38 @@ def main():
             assert all(b == all_blobs[0] for b in all_blobs), "%s/%s: ranks disagree" % (name, preset_name)
             results[(name, preset_name)] = (ret, p, info, dt)
 
+    # ---- re-attach: a second (third) session over the SAME exchange buffers.  The buffers still hold the cells of the
+    # earlier sessions; tags never go back (the export record carries the tag reached), so none of them can be taken
+    # for a fresh one.  Each session runs far more exchanges than the two parities a buffer holds.
+    want = np.concatenate([[results[("peer-persistent", "REF_GLOBAL")][0]], results[("peer-persistent", "REF_GLOBAL")][1],
+                           results[("peer-persistent", "REF_GLOBAL")][2]]).tobytes()
+    for session in range(2):
+        ctx.peer_detach()
+        handles = [None] * world
+        dist.all_gather_object(handles, ctx.peer_export())
+        ctx.peer_attach(handles, rank, world)      # no barrier, no memset: the first fit may start at once
+        for _ in range(2):
+            ret, p, info = ctx.fit_global(s, A.REF_GLOBAL, drive=A.DRIVE_PERSISTENT)
+            assert np.concatenate([[ret], p, info]).tobytes() == want, "re-attached session %d differs" % session
+    # ---- covariance from a context that only has peer buffers (no NCCL communicator): the global sample count
+    # travels through the fit kernel's own exchange
+    lone = A.Context(local)
+    handles = [None] * world
+    dist.all_gather_object(handles, lone.peer_export())
+    lone.peer_attach(handles, rank, world)
+    s_lone = lone.upload(c[lo:hi], td[lo:hi], x[lo:hi], A.BLINN_PHONG)
+    ret_l, p_l, info_l, covar_l = lone.fit_global(s_lone, A.REF_GLOBAL, want_covar=True)
+    assert np.concatenate([[ret_l], p_l, info_l]).tobytes() == want
+    s_lone.free()
+    dist.barrier()
+    lone.close()
+
     if rank == 0:
         single = A.Context(local)
         s1 = single.upload(c, td, x, A.BLINN_PHONG)
+        _, _, _, covar_1 = single.fit_global(s1, A.REF_GLOBAL, want_covar=True)
+        np.testing.assert_allclose(covar_l, covar_1, rtol=1e-6)
+        print("re-attached twice, covariance without a communicator: ok", flush=True)
         for preset_name, preset, opreset in (("REF_GLOBAL", A.REF_GLOBAL, O.REF_GLOBAL), ("REF_PERFACE", A.REF_PERFACE, O.REF_PERFACE)):
             r1, p1, i1 = single.fit_global(s1, preset)
             wret, wp, winfo = O.brdf_fit(O.oracle(), "oracle_", c, td, th, x, 1, opreset)

@@ -88,8 +88,18 @@ def oracle():
         lib.oracle_gather.restype = C.c_int
         lib.oracle_gather.argtypes = [dptr, iptr, C.c_int, dptr, dptr, C.POINTER(C.c_void_p), C.c_int,
                                       C.c_int, C.c_int, iptr, iptr, iptr, dptr, dptr, dptr, dptr]
+        lib.oracle_set_dot_order.restype = None
+        lib.oracle_set_dot_order.argtypes = [C.c_int]
         _oracle = lib
     return _oracle
+
+
+DOT_EIGEN33, DOT_SEQUENTIAL = 0, 1
+
+
+def set_dot_order(order):
+    """Evaluation order of the final dots of GetCosLN / GetCosNH in the gather oracle (gather_oracle.c header)."""
+    oracle().oracle_set_dot_order(int(order))
 
 
 def ref():

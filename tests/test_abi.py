@@ -74,3 +74,20 @@ def test_wrong_callback_is_rejected():
     bogus = C.cast(A.lib().brdfgpu_version, C.c_void_p)
     ret, _, _, _ = A.dlevmar_bc_dif([0.5, 1, 1], c, [0] * 3, [100] * 3, 10, None, extra, func=bogus)
     assert ret == A.LM_ERROR
+
+
+def test_m_other_than_3_is_rejected():
+    """include/brdfgpu.h: the BRDF models have exactly 3 parameters; levmar's generic m (levmar.h:124-127) is refused
+    before any GPU work, with the documented message."""
+    n = 8
+    c = np.linspace(0.1, 0.9, n)
+    extra, _keep = A.make_extra(c, c, c, 1)
+    for m in (2, 4, 8):
+        ret, _, _, _ = A.dlevmar_bc_dif([0.5] * m, c, [0] * m, [100] * m, 10, None, extra)
+        assert ret == A.LM_ERROR
+        msg = A.lib().brdfgpu_last_error(None).decode()
+        assert "exactly 3 parameters" in msg and "m = %d" % m in msg, msg
+    ret, _, _, _ = A.dlevmar_dif([0.5] * 4, c, 10, None, extra)
+    assert ret == A.LM_ERROR
+    hdr = open(os.path.join(ROOT, "include", "brdfgpu.h")).read()
+    assert "3 <= m" not in hdr and "BRDFGPU_NUM_PARAMS 3" in hdr

@@ -245,3 +245,38 @@ def test_gather_options_bit_exact(ctx, flags):
     with pytest.raises(A.BrdfGpuError):
         sc.set_gather_options(A.GATHER_KAPPA1)          # kappa1 values missing
     sc.free()
+
+
+def test_dot_order_switch_and_partial_outputs(ctx, scene_inputs):
+    """The default is Eigen 3.3's order for the final dots of GetCosLN / GetCosNH (oracle/gather_oracle.c);
+    GATHER_SEQ_DOT gives the left-to-right order -- each against the oracle in the same mode, as bytes.  The resident
+    hand-over (fit-stage arrays written by the gather kernel itself, theta not computed for Blinn-Phong) carries
+    the same bits as the plain arrays."""
+    V, F, imgs, dark, cams, W, H = scene_inputs
+    sc = ctx.scene(V, F, imgs)
+    led = S.led_table()
+    try:
+        for flag, order in ((0, O.DOT_EIGEN33), (A.GATHER_SEQ_DOT, O.DOT_SEQUENTIAL)):
+            sc.set_gather_options(flag)
+            O.set_dot_order(order)
+            g = sc.gather(cams[:2])
+            off = np.concatenate([[0], np.cumsum(g["nfit_cam"])])
+            for v in range(2):
+                want = S.oracle_gather(V, F, cams[v], led, imgs, W, H)
+                sl = slice(off[v], off[v + 1])
+                for key in ("phi", "thetaDash", "theta"):
+                    assert np.ascontiguousarray(g[key][sl]).tobytes() == want[key].tobytes(), (flag, key)
+            s, b, nfit = sc.gather_resident(cams[:2], model=A.BLINN_PHONG, channel=1, want_global=True, want_batch=True)
+            assert nfit == g["nfit"] and len(s) == nfit * 16 and len(b) == nfit
+            c_dev, t_dev, x_dev = s.download()
+            assert c_dev.tobytes() == g["phi"].tobytes() and t_dev.tobytes() == g["thetaDash"].tobytes()
+            assert x_dev.tobytes() == np.ascontiguousarray(g["I"][1]).tobytes()
+            s.free(); b.free()
+            s, _, _ = sc.gather_resident(cams[:2], model=A.PHONG, channel=2, want_global=True, want_batch=False)
+            c_dev, t_dev, x_dev = s.download()
+            assert t_dev.tobytes() == g["theta"].tobytes() and x_dev.tobytes() == np.ascontiguousarray(g["I"][2]).tobytes()
+            s.free()
+    finally:
+        O.set_dot_order(O.DOT_EIGEN33)
+        sc.set_gather_options(0)
+    sc.free()

@@ -188,6 +188,36 @@ def test_read_png_rejects_what_it_cannot_decode(tmp_path):
         A.read_png(p)
 
 
+def _rewrite_ihdr(data, w, h):
+    """IHDR with new dimensions and a VALID chunk CRC (a crafted file, not a damaged one)."""
+    out = bytearray(data)
+    out[16:24] = struct.pack(">II", w, h)
+    out[29:33] = struct.pack(">I", zlib.crc32(bytes(out[12:29])))
+    return bytes(out)
+
+
+def test_read_png_survives_corrupt_and_crafted_files(tmp_path):
+    """A huge IHDR must not become a huge allocation (or an exception through the C boundary) and damaged chunks
+    are reported: cv::imread returns an empty Mat there and the reference fails cleanly."""
+    img = np.arange(4 * 4 * 3, dtype=np.uint8).reshape(4, 4, 3)
+    good = _png_bytes(img, 2, filters=[0])
+    p = tmp_path / "c.png"
+    for w, h in ((0x7fffffff, 0x7fffffff), (65535, 65535), (70000, 4), (4, 4000)):
+        p.write_bytes(_rewrite_ihdr(good, w, h))
+        with pytest.raises(A.BrdfGpuError):
+            A.read_png(p)
+        msg = A.lib().brdfgpu_last_error(None).decode()
+        assert "IDAT" in msg or "dimension" in msg or "inflate" in msg, msg
+    flipped = bytearray(good)
+    flipped[len(good) - 20] ^= 0x40      # inside the IDAT payload: its CRC no longer matches
+    p.write_bytes(bytes(flipped))
+    with pytest.raises(A.BrdfGpuError):
+        A.read_png(p)
+    assert "CRC" in A.lib().brdfgpu_last_error(None).decode()
+    p.write_bytes(good)
+    assert A.read_png(p).tobytes() == img[:, :, ::-1].tobytes()
+
+
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "img")), reason="reference tree not mounted")
 @pytest.mark.parametrize("scene", ["cup", "bunny"])
 def test_reference_files(scene):
