@@ -348,7 +348,8 @@ class Context:
                     cyc_exchange_phases=[int(buf[8 + i]) for i in range(4)],
                     cyc_control_by_next_sweep=dict(zip(("quit", "jac_fwd", "jac_central", "jac_analytic", "cost", "many", "bad"),
                                                        (int(buf[12 + i]) for i in range(7)))),
-                    spec_jac_issued=int(buf[19]), spec_jac_hits=int(buf[20]), creep_fused=int(buf[21]))
+                    spec_jac_issued=int(buf[19]), spec_jac_hits=int(buf[20]), creep_fused=int(buf[21]),
+                    secant_updates=int(buf[22]), secant_updates_accepted=int(buf[23]))
 
     def synchronize(self):
         self._ok(lib().brdfgpu_synchronize(self.handle))

@@ -146,6 +146,7 @@ int global_fit_secant(brdfgpu_ctx* ctx, brdfgpu_samples* s, double* p, int m, in
     double mu = 0.0, ginf = 0.0, tmp, e_cur, e_new, e_init, p_L2 = 0.0, Dp_L2 = DBL_MAX, dF, dL;
     int k, stop = 0, nu, nfev, njap = 0, nlss = 0;
     int updjac = 0, updp = 1, newjac = 0;
+    unsigned long long n_updates = 0, n_updates_accepted = 0;  // Broyden passes launched (fit_stats)
     bool have_sums = false;  // JtJ / Jte of the current J and e are already on the host (from S1 / S2)
 
     auto publish = [&](void) { return pub_ok ? Publish{ctx->d_result, ctx->h_result_dev, ctx->h_seq_dev, ++ctx->seq}
@@ -237,6 +238,8 @@ int global_fit_secant(brdfgpu_ctx* ctx, brdfgpu_samples* s, double* p, int m, in
                     k_secant_update<<<blocks, kPassThreads, 0, ctx->stream>>>(v, qn, Dp[0], Dp[1], Dp[2], Dp_L2, accepted ? 1 : 0, st,
                                                                              ctx->d_partials, ctx->d_sync, publish());
                     ++ctx->launches;
+                    ++n_updates;
+                    n_updates_accepted += accepted ? 1 : 0;
                     BG_CUDA_OK(ctx, cudaGetLastError());
                     if (fetch_result(ctx, NACC, pub_ok) != 0) return BRDFGPU_LM_ERROR;
                     have_sums = true;
@@ -284,7 +287,8 @@ int global_fit_secant(brdfgpu_ctx* ctx, brdfgpu_samples* s, double* p, int m, in
     }
     ctx->fit_stats[0] = (unsigned long long)njap; ctx->fit_stats[1] = (unsigned long long)(nfev - njap * ((jkind == kJacForward) ? m : 2 * m));
     ctx->fit_stats[2] = ctx->fit_stats[1];
-    for (int i = 3; i < 20; ++i) ctx->fit_stats[i] = 0;
+    for (int i = 3; i < 22; ++i) ctx->fit_stats[i] = 0;
+    ctx->fit_stats[22] = n_updates; ctx->fit_stats[23] = n_updates_accepted;
     return (stop != 4 && stop != 7) ? k : BRDFGPU_LM_ERROR;
 }
 

@@ -108,7 +108,8 @@ unsigned long long brdfgpu_launch_count(brdfgpu_ctx *ctx);
  * sweeping samples / in the grid-wide exchange / in the kernel altogether, out[8..11] the exchange by
  * phase, out[12..18] control-code cycles by the kind of sweep they led to, out[19] cost evaluations answered
  * by a Jacobian sweep (speculative Jacobians), out[20] Jacobians that were then obtained without a
- * sweep, out[21] iterations done in a single fused sweep (up to 24 values). */
+ * sweep, out[21] iterations done in a single fused sweep, out[22..23] (secant fits, brdfgpu_fit_global_unc / _dlevmar_dif)
+ * Broyden update passes launched / of those after an accepted step (up to 24 values). */
 int brdfgpu_fit_stats(brdfgpu_ctx *ctx, unsigned long long *out, int count);
 /* CUDA stream (cudaStream_t) the context launches on, for timing with CUDA events */
 void *brdfgpu_stream(brdfgpu_ctx *ctx);
