@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 
 PHONG, BLINN_PHONG = 0, 1
 DRIVE_HOST, DRIVE_PERSISTENT = 0, 1
-JAC_FD, JAC_ANALYTIC = 0, 1
+JAC_FD, JAC_ANALYTIC, JAC_FD_EXACT = 0, 1, 2
 LM_ERROR = -1
 IPC_HANDLE_BYTES = 72   # BRDFGPU_IPC_HANDLE_BYTES
 

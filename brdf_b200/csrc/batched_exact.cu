@@ -1,0 +1,243 @@
+// batched_exact.cu -- batched mode, levmar-exact: every fit reproduces dlevmar_bc_dif + BRDFFunc bit for bit.
+//
+// The default batched kernel (batched_fit.cu) evaluates t**n as exp(n ln t), forms the difference
+// quotients algebraically and sums with butterflies; its converged fits agree with the reference to the
+// parity bars (1e-4 / 1e-6), but levmar's trajectory is sensitive to the last bit of every sum
+// (SURVEY.md Q13), so fits that levmar itself abandons (itmax, "no further reduction": 86 % of the
+// per-face fits on img/cup) end somewhere else.  This kernel removes every source of difference for
+// the problem sizes of the batched mode (n m < 1024: levmar's small-problem branch, lmbc_core.c:573):
+//
+//   * the model value is BRDFFunc's expression with its roundings (brdfdata.cpp:981, 986: products and sum
+//     rounded separately, the host has no FMA contraction) around glibc's pow() reproduced bit for bit
+//     (glibc_pow.cuh);
+//   * the Jacobian is levmar's literal forward difference jac[i][j] = (f(p + d_j e_j)[i] - f(p)[i]) * (1/d_j)
+//     with d_j = max(|1e-4 p_j|, delta) (misc_core.c:153-170) -- t**n is shared by the kd / ks columns
+//     because the reference's own calls pass identical arguments there;
+//   * J^T J and J^T e are accumulated in the order of levmar's small-problem loop (lmbc_core.c:592-616:
+//     samples downwards, lower triangle, product and sum rounded separately), ||e||^2 in the order of
+//     dlevmar_L2nrmxmy (misc_core.c:721-807: four interleaved partial sums walking downwards in blocks of
+//     eight, the remainder in its switch order, then ((s0 + s1) + s2) + s3);
+//   * the control loop is lm_engine.cuh compiled WITHOUT multiply-add contraction (this file is built with
+//     --fmad=false and BG_LM_LEVMAR_ARITH), i.e. the instantiation that is bit-identical to levmar on the host.
+//
+// One lane group (16 lanes for <= 16 samples, else a warp) owns one fit: lanes evaluate their samples in
+// parallel, the per-sample terms go through shared memory, and a few lanes add them up in levmar's order.
+// Result: p, all ten info[] entries and the return value equal the reference's (tests/test_gpu_exact.py:
+// every fit of BASELINE configs[3] and of the per-face path on img/cup).
+#define BG_LM_LEVMAR_ARITH 1
+#include "glibc_pow.cuh"
+
+#include "brdf_model.cuh"
+#include "common.cuh"
+
+namespace brdfgpu {
+
+constexpr int kExactThreads = 128;
+
+struct ExactSpec {
+    int itmax, has_lb, has_ub, model, nper;
+    double delta;
+    double p0[3], lb[3], ub[3];
+    LmOptions opt;
+};
+
+static __device__ __noinline__ double pow_libm(double x, double y) { return glibc_pow(x, y); }
+
+// model value with BRDFFunc's roundings: kd*c + ks'*pw, ks' = ks (Blinn-Phong) or ((n+2)/2*pi)*ks (Phong)
+__device__ __forceinline__ double model_ks(int model, double ks, double n) {
+    return model == 1 ? ks : __dmul_rn(__dmul_rn(__ddiv_rn(__dadd_rn(n, 2.0), 2.0), kPi), ks);
+}
+__device__ __forceinline__ double model_hx(double kd, double c, double ksp, double pw) {
+    return __dadd_rn(__dmul_rn(kd, c), __dmul_rn(ksp, pw));
+}
+
+template <int G, int S>
+struct ExactEval {
+    static constexpr int kCostBatch = 1;
+    static constexpr bool kLanePgWalk = false;
+    double c[S], t[S], x[S];  // this lane's samples: index s * G + lane
+    double* scratch;          // shared, this group's: 4 doubles per sample
+    int nper, lane, model;
+    unsigned mask;
+    double delta;
+
+    __device__ __forceinline__ double from_lane(double v, int src) const { return __shfl_sync(mask, v, src, G); }
+
+    // ||x - f(p)||^2 in dlevmar_L2nrmxmy's order; bad = VECNORM(e) is not finite (lmbc_core.c:146-170, 748)
+    __device__ __forceinline__ double cost(const double* p, bool& bad) const {
+        const double kd = p[0], n = p[2], ksp = model_ks(model, p[1], n);
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const int idx = s * G + lane;
+            if (idx < nper) {
+                const double e = __dsub_rn(x[s], model_hx(kd, c[s], ksp, pow_libm(t[s], n)));
+                scratch[idx] = __dmul_rn(e, e);
+                scratch[nper + idx] = e;
+            }
+        }
+        __syncwarp(mask);
+        const int blockn = (nper >> 3) << 3;
+        double sum = 0.0;
+        if (lane < 4) {
+            for (int i = blockn - 1 - lane; i >= 0; i -= 4) sum = __dadd_rn(sum, scratch[i]);
+            const int r = nper - blockn;  // the switch of misc_core.c:753-765: sums 0,1,2,3,0,1,2 entered at case r
+            for (int j = 0; j < r; ++j)
+                if (((7 - r + j) & 3) == lane) sum = __dadd_rn(sum, scratch[blockn + j]);
+        }
+        const double s0 = from_lane(sum, 0), s1 = from_lane(sum, 1), s2 = from_lane(sum, 2), s3 = from_lane(sum, 3);
+        const double esq = __dadd_rn(__dadd_rn(__dadd_rn(s0, s1), s2), s3);
+        bad = false;
+        if (!lm_finite(esq)) {  // rare: Blue's scaled norm, literally (every lane redundantly: values are uniform)
+            double mx = 0.0;
+            for (int i = nper; i-- > 0;) {
+                const double v = scratch[nper + i];
+                if (v > mx) mx = v;
+                else if (v < -mx) mx = -v;
+            }
+            double sm = 0.0;
+            for (int i = nper; i-- > 0;) {
+                const double q = scratch[nper + i] / mx;
+                sm += q * q;
+            }
+            bad = !lm_finite(mx * sqrt(sm));
+        }
+        __syncwarp(mask);
+        return esq;
+    }
+
+    // levmar's forward-difference Jacobian and its small-problem normal equations
+    __device__ __forceinline__ void jac(const double* p, double* JtJ, double* Jte) const {
+        double d[3], ph[3], inv[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {  // misc_core.c:153-170
+            double dj = 1E-04 * p[j];
+            dj = lm_abs(dj);
+            if (dj < delta) dj = delta;
+            d[j] = dj;
+            ph[j] = p[j] + dj;
+            inv[j] = 1.0 / dj;
+        }
+        const double kd = p[0], n = p[2];
+        const double ksp = model_ks(model, p[1], n);            // f(p), f(p + d0 e0)
+        const double ksp_hi1 = model_ks(model, ph[1], n);       // f(p + d1 e1)
+        const double ksp_hi2 = model_ks(model, p[1], ph[2]);    // f(p + d2 e2): the Phong factor follows n
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const int idx = s * G + lane;
+            if (idx < nper) {
+                const double pw = pow_libm(t[s], n), pw_hi = pow_libm(t[s], ph[2]);
+                const double hx = model_hx(kd, c[s], ksp, pw);
+                double* row = scratch + 4 * idx;
+                row[0] = __dmul_rn(__dsub_rn(model_hx(ph[0], c[s], ksp, pw), hx), inv[0]);
+                row[1] = __dmul_rn(__dsub_rn(model_hx(kd, c[s], ksp_hi1, pw), hx), inv[1]);
+                row[2] = __dmul_rn(__dsub_rn(model_hx(kd, c[s], ksp_hi2, pw_hi), hx), inv[2]);
+                row[3] = __dsub_rn(x[s], hx);  // e, lmbc_core.c:526 / 779
+            }
+        }
+        __syncwarp(mask);
+        // lmbc_core.c:603-612: for l = n-1 .. 0: JtJ[i][j] += J[l][j] * J[l][i] (j <= i), Jte[i] += J[l][i] * e[l].
+        // Nine independent accumulators, one lane each: (2,2) (2,1) (2,0) (1,1) (1,0) (0,0), then Jte 2, 1, 0.
+        double acc = 0.0;
+        if (lane < 9) {
+            const int a = lane < 3 ? 2 : lane < 5 ? 1 : lane < 6 ? 0 : 8 - lane;             // i (alpha = J[l][i])
+            const int b = lane < 3 ? 2 - lane : lane < 5 ? 4 - lane : lane < 6 ? 0 : 3;       // j, or 3 = e
+            for (int l = nper; l-- > 0;) acc = __dadd_rn(acc, __dmul_rn(scratch[4 * l + b], scratch[4 * l + a]));
+        }
+        const double a22 = from_lane(acc, 0), a21 = from_lane(acc, 1), a20 = from_lane(acc, 2), a11 = from_lane(acc, 3),
+                     a10 = from_lane(acc, 4), a00 = from_lane(acc, 5);
+        Jte[2] = from_lane(acc, 6); Jte[1] = from_lane(acc, 7); Jte[0] = from_lane(acc, 8);
+        JtJ[0] = a00; JtJ[1] = a10; JtJ[2] = a20;
+        JtJ[3] = a10; JtJ[4] = a11; JtJ[5] = a21;
+        JtJ[6] = a20; JtJ[7] = a21; JtJ[8] = a22;
+        __syncwarp(mask);
+    }
+};
+
+template <int G, int S>
+__global__ void __launch_bounds__(kExactThreads) k_batched_fit_exact(const double* __restrict__ c, const double* __restrict__ traw,
+                                                                     const double* __restrict__ x, long nfit, ExactSpec spec,
+                                                                     double* __restrict__ p_out, double* __restrict__ info_out,
+                                                                     int* __restrict__ ret_out) {
+    extern __shared__ double exact_smem[];
+    const long fit = ((long)blockIdx.x * kExactThreads + threadIdx.x) / G;
+    if (fit >= nfit) return;
+    const int lane = threadIdx.x % G, nper = spec.nper;
+    const long base = fit * nper;
+    ExactEval<G, S> ev;
+    ev.scratch = exact_smem + (size_t)(threadIdx.x / G) * 4 * nper;
+    ev.nper = nper; ev.lane = lane; ev.model = spec.model; ev.delta = spec.delta;
+    ev.mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const int idx = s * G + lane;
+        const bool in = idx < nper;
+        ev.c[s] = in ? c[base + idx] : 0.0;
+        ev.t[s] = in ? traw[base + idx] : 0.0;
+        ev.x[s] = in ? x[base + idx] : 0.0;
+    }
+    double p[3] = {spec.p0[0], spec.p0[1], spec.p0[2]};
+    double info[10];
+    const double* lb = spec.has_lb ? spec.lb : nullptr;
+    const double* ub = spec.has_ub ? spec.ub : nullptr;
+    const Box box{lb, ub};
+    box_project(p, box, 3);  // lmbc_core.c:516
+    const int ret = lm_bc_der<3>(ev, 3, p, lb, ub, nullptr, spec.opt, info, nullptr);
+    if (lane == 0) {
+        info[7] += info[8] * 4.0;  // dlevmar_bc_dif charges every forward-difference Jacobian m + 1 calls, lmbc_core.c:1119-1124
+        for (int i = 0; i < 3; ++i) p_out[fit * 3 + i] = p[i];
+        if (info_out)
+            for (int i = 0; i < 10; ++i) info_out[fit * 10 + i] = info[i];
+        if (ret_out) ret_out[fit] = ret;
+    }
+}
+
+template <int G, int S>
+static int launch_exact(brdfgpu_ctx* ctx, brdfgpu_batch* b, const ExactSpec& spec) {
+    const size_t smem = sizeof(double) * 4 * (size_t)b->nper * (kExactThreads / G);
+    if (smem > 48 * 1024)
+        BG_CUDA_OK(ctx, cudaFuncSetAttribute(k_batched_fit_exact<G, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long blocks = (b->nfit * G + kExactThreads - 1) / kExactThreads;
+    k_batched_fit_exact<G, S><<<(unsigned)blocks, kExactThreads, smem, ctx->stream>>>(b->c, b->traw, b->x, b->nfit, spec, b->p, b->info,
+                                                                                   b->ret);
+    ++ctx->launches;
+    BG_CUDA_OK(ctx, cudaGetLastError());
+    return 0;
+}
+
+// BRDFGPU_JAC_FD_EXACT of brdfgpu_batch_fit
+int batch_fit_exact(brdfgpu_ctx* ctx, brdfgpu_batch* b, const double* p0, const double* lb, const double* ub, int itmax,
+                    const double* opts) {
+    if (b->nfit == 0) return 0;
+    const double delta_signed = opts ? opts[4] : kDiffDelta;
+    if (delta_signed < 0.0) {
+        set_error(ctx, "batch fit, levmar-exact mode: forward differences only (opts[4] >= 0, as both reference presets use)");
+        return BRDFGPU_LM_ERROR;
+    }
+    if (3 * b->nper >= 1024 || b->nper > 128) {  // lmbc_core.c:573: beyond n m = 1024 levmar sums in 32-row blocks
+        set_error(ctx, "batch fit, levmar-exact mode: at most 128 samples per fit (levmar's small-problem summation order)");
+        return BRDFGPU_LM_ERROR;
+    }
+    if (lb && ub)
+        for (int i = 0; i < 3; ++i)
+            if (lb[i] > ub[i]) {
+                fprintf(stderr, "brdfgpu batch fit: at least one lower bound exceeds the upper one\n");
+                return BRDFGPU_LM_ERROR;
+            }
+    ExactSpec spec;
+    spec.itmax = itmax; spec.model = b->model; spec.nper = b->nper;
+    spec.delta = delta_signed;
+    spec.has_lb = lb != nullptr; spec.has_ub = ub != nullptr;
+    for (int i = 0; i < 3; ++i) {
+        spec.p0[i] = p0[i];
+        spec.lb[i] = lb ? lb[i] : 0.0;
+        spec.ub[i] = ub ? ub[i] : 0.0;
+    }
+    spec.opt = lm_options(opts, itmax);
+    const int n = b->nper;
+    if (n <= 16) return launch_exact<16, 1>(ctx, b, spec);
+    if (n <= 32) return launch_exact<32, 1>(ctx, b, spec);
+    if (n <= 64) return launch_exact<32, 2>(ctx, b, spec);
+    return launch_exact<32, 4>(ctx, b, spec);
+}
+
+}  // namespace brdfgpu

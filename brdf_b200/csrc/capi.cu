@@ -496,6 +496,7 @@ extern "C" int brdfgpu_batch_fit(brdfgpu_ctx* ctx, brdfgpu_batch* b, const doubl
     ctx = ctx_or_default(ctx);
     if (!ctx || !b || !p0) return BRDFGPU_LM_ERROR;
     BG_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    if (jac_mode == BRDFGPU_JAC_FD_EXACT) return batch_fit_exact(ctx, b, p0, lb, ub, itmax, opts);
     return batch_fit(ctx, b, p0, lb, ub, itmax, opts, jac_mode);
 }
 

@@ -181,6 +181,10 @@ int batch_prepare(brdfgpu_ctx* ctx, brdfgpu_batch* b);
 int batch_fit(brdfgpu_ctx* ctx, brdfgpu_batch* b, const double* p0, const double* lb, const double* ub, int itmax,
               const double* opts, int jac_mode);
 
+// ---- batched_exact.cu ----
+int batch_fit_exact(brdfgpu_ctx* ctx, brdfgpu_batch* b, const double* p0, const double* lb, const double* ub, int itmax,
+                    const double* opts);
+
 // ---- comm.cu ----
 int comm_allreduce_device(brdfgpu_ctx* ctx, double* d_buf, int count);
 

@@ -58,13 +58,20 @@ BG_HDI double lm_abs(double v) { return (v >= 0.0) ? v : -v; }
 BG_HDI bool lm_finite(double v) { return (v - v) == 0.0; }  // false for NaN and +-Inf
 // y + a*x with ONE spelling per target (device: fused; host: levmar's two roundings), for points that are formed
 // at two places and compared bit for bit (the line-search probe and its announcement)
+// BG_LM_LEVMAR_ARITH (the levmar-exact batched kernel, compiled with --fmad=false): levmar's two roundings on the
+// device as well, and libm's pow() through its reproduction in glibc_pow.cuh.
 BG_HDI double lm_axpy(double a, double x, double y) {
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && !defined(BG_LM_LEVMAR_ARITH)
     return __fma_rn(a, x, y);
 #else
     return y + a * x;
 #endif
 }
+#ifdef BG_LM_LEVMAR_ARITH
+#define BG_LM_POW(x, y) ::brdfgpu::glibc_pow((x), (y))
+#else
+#define BG_LM_POW(x, y) pow((x), (y))
+#endif
 
 struct LmOptions {
     double tau, eps1, eps2, eps2_sq, eps3;
@@ -626,7 +633,7 @@ BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double*
                 const double hi = (Dp_L2 >= dd) ? Dp_L2 : dd, lo = (Dp_L2 >= dd) ? dd : Dp_L2;
                 if (gTd <= -rho * hi * 1.000001) descent = true;
                 else if (gTd > -rho * lo * 0.999999) descent = false;
-                else descent = gTd <= -rho * pow(Dp_L2, kPow / 2.0);
+                else descent = gTd <= -rho * BG_LM_POW(Dp_L2, kPow / 2.0);
             }
             if (descent) {
                 const double steptl = 1e3 * sqrt(DBL_EPSILON);

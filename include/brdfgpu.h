@@ -144,6 +144,13 @@ void brdfgpu_samples_free(brdfgpu_ctx *ctx, brdfgpu_samples *s);
 /* Jacobian definition */
 #define BRDFGPU_JAC_FD 0        /* finite differences exactly as levmar (forward, or central if opts[4]<0) */
 #define BRDFGPU_JAC_ANALYTIC 1  /* exact partials (bc_der / der semantics) */
+/* brdfgpu_batch_fit only: dlevmar_bc_dif + BRDFFunc reproduced operation by operation -- glibc's pow() bit for bit,
+ * levmar's literal forward differences, its small-problem summation orders (lmbc_core.c:592-616, misc_core.c:721-807)
+ * and its control arithmetic without multiply-add contraction -- so p, info[0..9] and the return value of every fit
+ * EQUAL the reference's (not merely within tolerance), including the fits levmar abandons at itmax.  Forward
+ * differences, at most 128 samples per fit (n m < 1024: levmar's small-problem branch).  About 2x slower than
+ * BRDFGPU_JAC_FD, whose converged fits agree to the parity bars (1e-4 parameters, 1e-6 cost). */
+#define BRDFGPU_JAC_FD_EXACT 2
 
 /* Global box-constrained fit on a resident sample set == dlevmar_bc_dif / _bc_der on the same data
  * (lmbc_core.c:369-1129).  With a communicator attached (brdfgpu_comm_init) the samples of all
