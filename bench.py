@@ -545,33 +545,43 @@ def bunny_sharded(rig):
 
 # ---- the other two stages on one GPU -----------------------------------------------------------
 def batched_leg(rig, cpu=True):
-    """BASELINE configs[3]: 65 536 independent per-face fits x 64 samples, one launch."""
+    """BASELINE configs[3]: 65 536 independent per-face fits x 64 samples, one launch.  Two kernels: the levmar-exact one
+    (what the reference's drivers run: every fit EQUALS dlevmar_bc_dif's result) is the stage's number, the fast one
+    (exp(n ln t), butterfly sums: converged fits within the parity bars) is reported beside it."""
     A, ctx, peak = rig.A, rig.ctx, rig.peak
     nfit, nper = 65536, 64
     b = ctx.batch_synth(nfit, nper, seed=2026)
-    for _ in range(2):
-        b.fit(A.REF_PERFACE)
-    ms, _ = rig.timed(lambda: b.fit(A.REF_PERFACE), 3)
-    pp, info, ret = b.results()
+    modes = {}
+    for name, mode, kernel in (("levmar_exact", A.JAC_FD_EXACT, "k_batched_fit_exact<32,2>"), ("fast", A.JAC_FD, "k_batched_fit<32,2>")):
+        for _ in range(2):
+            b.fit(A.REF_PERFACE, jac_mode=mode)
+        ms, _ = rig.timed(lambda: b.fit(A.REF_PERFACE, jac_mode=mode), 3)
+        pp, info, ret = b.results()
+        gbs = 24.0 * nper * nfit / (ms * 1e-3) / 1e9
+        ncu = NCU.get(kernel, {})
+        modes[name] = {"value": nfit / (ms * 1e-3), "unit": "fits/s", "ms_per_launch": ms, "seconds_per_fit": ms * 1e-3 / nfit,
+                       "mean_iterations": float(info[:, 5].mean()), "mean_nfev": float(info[:, 7].mean()),
+                       "sample_evals_per_s": float(info[:, 7].sum() * nper / (ms * 1e-3)),
+                       "converged_fraction": float(np.isin(info[:, 6].astype(int), (1, 2, 6)).mean()),
+                       "roofline": {"bound": "hbm", "kernel": kernel, "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                                    "algorithmic_bytes_per_launch": 24.0 * nper * nfit, "launch_ms": ms, "traffic": ncu.get("dram_bytes"),
+                                    "binding_limit": "latency of per-fit control flow; fp64 pipe %s %% busy (ncu, %s)" % (ncu.get("fp64_pipe_pct", "?"), ncu.get("source", "?")),
+                                    "fp64_pipe_pct": ncu.get("fp64_pipe_pct"),
+                                    "note": "each fit reads its 1 536 B once and then iterates on chip: HBM cannot be the bound (SURVEY.md 8d)"}}
     b.free()
-    gbs = 24.0 * nper * nfit / (ms * 1e-3) / 1e9
-    ncu = NCU.get("k_batched_fit<32,2>", {})
-    out = {"metric": "batched BRDF fits/sec", "value": nfit / (ms * 1e-3), "unit": "fits/s", "nfit": nfit, "samples_per_fit": nper,
-           "ms_per_launch": ms, "seconds_per_fit": ms * 1e-3 / nfit, "preset": "REF_PERFACE", "mean_iterations": float(info[:, 5].mean()),
-           "mean_nfev": float(info[:, 7].mean()), "sample_evals_per_s": float(info[:, 7].sum() * nper / (ms * 1e-3)),
-           "converged_fraction": float(np.isin(info[:, 6].astype(int), (1, 2, 6)).mean()),
-           "roofline": {"bound": "hbm", "kernel": "k_batched_fit<32,2>", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
-                        "algorithmic_bytes_per_launch": 24.0 * nper * nfit, "launch_ms": ms, "traffic": ncu.get("dram_bytes"),
-                        "binding_limit": "latency of per-fit control flow; fp64 pipe %.0f %% busy (ncu, %s)" % (ncu.get("fp64_pipe_pct", float("nan")), ncu.get("source", "?")),
-                        "fp64_pipe_pct": ncu.get("fp64_pipe_pct"),
-                        "note": "each fit reads its 1 536 B once and then iterates in registers: HBM cannot be the bound (SURVEY.md 8d)"}}
+    out = {"metric": "batched BRDF fits/sec", "nfit": nfit, "samples_per_fit": nper, "preset": "REF_PERFACE"}
+    out.update(modes["levmar_exact"])
+    out["mode"] = "levmar-exact (BRDFGPU_JAC_FD_EXACT): p, info[0..9], ret of every fit equal the reference's bit for bit"
+    out["fast"] = modes["fast"]
+    out["fast"]["mode"] = "BRDFGPU_JAC_FD: 99.97 % of the converged fits within 1e-4 / 1e-6 of the reference (profiles/r02_parity.md)"
     if cpu:
         count = 3000
         dt, kind, nfev = cpu_batched_fits(count, nper)
         out["cpu_baseline"] = {"value": count / dt, "unit": "fits/s", "cores": 1, "kind": kind, "seconds_per_fit": dt / count,
                                "sample": "the first %d of the 65 536 configs[3] fits, one dlevmar_bc_dif call each (brdfdata.cpp:1119), %.1f s" % (count, dt),
                                "mean_nfev": nfev, "host_cores_available": os.cpu_count()}
-        out["time_to_solution_ratio"] = (dt / count) / (ms * 1e-3 / nfit)
+        out["time_to_solution_ratio"] = (dt / count) / out["seconds_per_fit"]
+        out["fast"]["time_to_solution_ratio"] = (dt / count) / out["fast"]["seconds_per_fit"]
     return out
 
 
@@ -642,10 +652,13 @@ def batched_sharded(rig, nfit_total):
     A, ctx, world, rank = rig.A, rig.ctx, rig.world, rig.rank
     lo, hi = rank * nfit_total // world, (rank + 1) * nfit_total // world
     b = ctx.batch_synth(hi - lo, 64, seed=2026, first_fit=lo)
-    b.fit(A.REF_PERFACE)
-    ms, _ = rig.timed(lambda: b.fit(A.REF_PERFACE), 3)
+    out = {"nfit_total": nfit_total, "samples_per_fit": 64}
+    for name, mode in (("levmar_exact", A.JAC_FD_EXACT), ("fast", A.JAC_FD)):
+        b.fit(A.REF_PERFACE, jac_mode=mode)
+        ms, _ = rig.timed(lambda: b.fit(A.REF_PERFACE, jac_mode=mode), 3)
+        out[name] = {"ms": ms, "fits_per_s": nfit_total / (ms * 1e-3)}
     b.free()
-    return {"nfit_total": nfit_total, "samples_per_fit": 64, "ms": ms, "fits_per_s": nfit_total / (ms * 1e-3)}
+    return out
 
 
 def run_gpu_arm(args):

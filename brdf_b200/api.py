@@ -120,7 +120,6 @@ SIGNATURES = {
     "brdfgpu_peer_attach": (C.c_int, [_V, C.c_char_p, C.c_int, C.c_int]),
     "brdfgpu_peer_detach": (None, [_V]),
     "brdfgpu_lm_bc_reduced": (C.c_int, [_V, _V, _V, dptr, C.c_int, C.c_long, dptr, dptr, dptr, C.c_int, dptr, dptr, dptr]),
-    "brdfgpu_lm_bc_machine": (C.c_int, [_V, _V, _V, dptr, C.c_int, C.c_long, dptr, dptr, C.c_int, dptr, dptr]),
     "brdfgpu_lm_unc_reduced": (C.c_int, [_V, _V, _V, dptr, C.c_int, C.c_long, C.c_int, dptr, dptr, dptr]),
     "brdfgpu_Ax_eq_b_LU": (C.c_int, [dptr, dptr, dptr, C.c_int]),
     "brdfgpu_version": (C.c_char_p, []),
@@ -640,18 +639,6 @@ def lm_bc_reduced(jac_cb, cost_cb, p0, n, lb, ub, itmax, opts, dscl=None, want_c
     ret = lib().brdfgpu_lm_bc_reduced(C.cast(jc, C.c_void_p), C.cast(cc, C.c_void_p), None, _d(p), m, n, _d(lb), _d(ub),
                                       _d(dscl), int(itmax), _d(opts), _d(info), _d(covar))
     return ret, p, info, covar
-
-
-def lm_bc_machine(jac_cb, cost_cb, p0, n, lb, ub, itmax, opts):
-    """lm_bc_reduced through the resumable state machine (csrc/lm_machine.cuh)"""
-    p = _arr(p0).copy()
-    m = p.size
-    lb, ub, opts = _arr(lb), _arr(ub), _arr(opts)
-    info = np.zeros(10)
-    jc, cc = REDUCED_JAC_T(jac_cb), REDUCED_COST_T(cost_cb)
-    ret = lib().brdfgpu_lm_bc_machine(C.cast(jc, C.c_void_p), C.cast(cc, C.c_void_p), None, _d(p), m, int(n), _d(lb), _d(ub),
-                                      int(itmax), _d(opts), _d(info))
-    return ret, p, info
 
 
 def lm_unc_reduced(jac_cb, cost_cb, p0, n, itmax, opts, want_covar=False):

@@ -51,58 +51,181 @@ __device__ __forceinline__ double model_hx(double kd, double c, double ksp, doub
     return __dadd_rn(__dmul_rn(kd, c), __dmul_rn(ksp, pw));
 }
 
+#ifndef BG_EXACT_PG
+#define BG_EXACT_PG 4
+#endif
+
 template <int G, int S>
 struct ExactEval {
-    static constexpr int kCostBatch = 1;
+    // Candidates of the projected-gradient walk evaluated together (lm_engine.cuh PgBatch): levmar walks t, 0.9 t,
+    // 0.81 t ... one function call at a time and most evaluations of a batch of fits are such candidates (the median
+    // fit makes one 393-step walk that finds nothing).  The candidates depend only on p and J^T e, every evaluation is
+    // deterministic, and they are consumed strictly in levmar's order, so evaluating KB of them per call changes no
+    // value and no count; it gives each lane KB independent exp chains and puts four lanes per candidate to work in
+    // the ordered summation instead of four in all.
+    static constexpr int KB = (BG_EXACT_PG) < G / 4 ? (BG_EXACT_PG) : G / 4;
+    static constexpr int kCostBatch = KB;
     static constexpr bool kLanePgWalk = false;
+    static_assert(4 * KB <= G, "four summing lanes per candidate");
     double c[S], t[S], x[S];  // this lane's samples: index s * G + lane
-    double* scratch;          // shared, this group's: 4 doubles per sample
+    double lhi[S], llo[S];    // log(t) = lhi + llo as glibc's pow computes it: depends on t alone, so once per fit
+    unsigned ordinary;        // bit s: t[s] is positive, normal and finite (the pow() main path)
+    double* scratch;          // shared, this group's: max(4, KB) doubles per sample
+    double* s_pts;            // shared, this group's: KB candidate points + KB costs + KB flags
     int nper, lane, model;
     unsigned mask;
     double delta;
 
     __device__ __forceinline__ double from_lane(double v, int src) const { return __shfl_sync(mask, v, src, G); }
 
-    // ||x - f(p)||^2 in dlevmar_L2nrmxmy's order; bad = VECNORM(e) is not finite (lmbc_core.c:146-170, 748)
+    __device__ __forceinline__ void prepare() {
+        ordinary = 0u;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            lhi[s] = llo[s] = 0.0;
+            if (pow_base_is_ordinary(t[s])) {
+                ordinary |= 1u << s;
+                pow_log_of_base(t[s], &lhi[s], &llo[s]);
+            }
+        }
+    }
+
+    // pw[s][k] = pow(t[s], y[k]) with libm's bits.  The main path of all S x K values is straight-line code (S x K
+    // independent chains); values that leave it -- a base that is not an ordinary number, an exponent below 2^-65, a
+    // result that under- or overflows -- are redone through the complete function under one rarely taken branch.
+    template <int K>
+    __device__ __forceinline__ void powers(const double* y, double (*pw)[K]) const {
+        bool care = false;
+        double ehi[S][K], elo[S][K];
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                pow_scaled_log(lhi[s], llo[s], y[k], &ehi[s][k], &elo[s][k]);
+                care |= glibcpow::exp_needs_care(ehi[s][k]);
+            }
+#pragma unroll
+        for (int k = 0; k < K; ++k) care |= !pow_exponent_is_ordinary(y[k]);
+        care |= ordinary != ((1u << S) - 1u);
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+#pragma unroll
+            for (int k = 0; k < K; ++k) pw[s][k] = glibcpow::exp_ordinary(ehi[s][k], elo[s][k]);
+        if (care) {
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+                    if (!((ordinary >> s) & 1u) || !pow_exponent_is_ordinary(y[k]) || glibcpow::exp_needs_care(ehi[s][k]))
+                        pw[s][k] = pow_libm(t[s], y[k]);
+        }
+    }
+
+    // dlevmar_L2nrmxmy's sum of sq[0 .. nper) (misc_core.c:721-807) by the four lanes q4 .. q4+3 of a quad: lane part p
+    // walks partial sum p downwards through the blocks of eight, then the remainder in its switch order
+    __device__ __forceinline__ double l2_partial(const double* sq, int part) const {
+        const int blockn = (nper >> 3) << 3;
+        double sum = 0.0;
+        for (int i = blockn - 1 - part; i >= 0; i -= 4) sum = __dadd_rn(sum, sq[i]);
+        const int r = nper - blockn;  // sums 0,1,2,3,0,1,2 entered at case r
+        for (int j = 0; j < r; ++j)
+            if (((7 - r + j) & 3) == part) sum = __dadd_rn(sum, sq[blockn + j]);
+        return sum;
+    }
+    __device__ __forceinline__ double l2_combine(double partial, int quad_first) const {
+        const double s0 = from_lane(partial, quad_first), s1 = from_lane(partial, quad_first + 1),
+                     s2 = from_lane(partial, quad_first + 2), s3 = from_lane(partial, quad_first + 3);
+        return __dadd_rn(__dadd_rn(__dadd_rn(s0, s1), s2), s3);
+    }
+
+    // VECNORM(e) is not finite (lmbc_core.c:146-170, 748), literally; e in sq[0 .. nper).  Rare.
+    __device__ __forceinline__ bool vecnorm_not_finite(const double* e) const {
+        double mx = 0.0;
+        for (int i = nper; i-- > 0;) {
+            const double v = e[i];
+            if (v > mx) mx = v;
+            else if (v < -mx) mx = -v;
+        }
+        double sm = 0.0;
+        for (int i = nper; i-- > 0;) {
+            const double q = e[i] / mx;
+            sm += q * q;
+        }
+        return !lm_finite(mx * sqrt(sm));
+    }
+
+    // ||x - f(p)||^2 in dlevmar_L2nrmxmy's order; bad = VECNORM(e) is not finite
     __device__ __forceinline__ double cost(const double* p, bool& bad) const {
         const double kd = p[0], n = p[2], ksp = model_ks(model, p[1], n);
+        double pw[S][1];
+        powers<1>(&n, pw);
 #pragma unroll
         for (int s = 0; s < S; ++s) {
             const int idx = s * G + lane;
             if (idx < nper) {
-                const double e = __dsub_rn(x[s], model_hx(kd, c[s], ksp, pow_libm(t[s], n)));
+                const double e = __dsub_rn(x[s], model_hx(kd, c[s], ksp, pw[s][0]));
                 scratch[idx] = __dmul_rn(e, e);
                 scratch[nper + idx] = e;
             }
         }
         __syncwarp(mask);
-        const int blockn = (nper >> 3) << 3;
-        double sum = 0.0;
-        if (lane < 4) {
-            for (int i = blockn - 1 - lane; i >= 0; i -= 4) sum = __dadd_rn(sum, scratch[i]);
-            const int r = nper - blockn;  // the switch of misc_core.c:753-765: sums 0,1,2,3,0,1,2 entered at case r
-            for (int j = 0; j < r; ++j)
-                if (((7 - r + j) & 3) == lane) sum = __dadd_rn(sum, scratch[blockn + j]);
-        }
-        const double s0 = from_lane(sum, 0), s1 = from_lane(sum, 1), s2 = from_lane(sum, 2), s3 = from_lane(sum, 3);
-        const double esq = __dadd_rn(__dadd_rn(__dadd_rn(s0, s1), s2), s3);
+        const double esq = l2_combine(lane < 4 ? l2_partial(scratch, lane) : 0.0, 0);
         bad = false;
-        if (!lm_finite(esq)) {  // rare: Blue's scaled norm, literally (every lane redundantly: values are uniform)
-            double mx = 0.0;
-            for (int i = nper; i-- > 0;) {
-                const double v = scratch[nper + i];
-                if (v > mx) mx = v;
-                else if (v < -mx) mx = -v;
-            }
-            double sm = 0.0;
-            for (int i = nper; i-- > 0;) {
-                const double q = scratch[nper + i] / mx;
-                sm += q * q;
-            }
-            bad = !lm_finite(mx * sqrt(sm));
-        }
+        if (!lm_finite(esq)) bad = vecnorm_not_finite(scratch + nper);  // (every lane redundantly: the values are uniform)
         __syncwarp(mask);
         return esq;
+    }
+
+    // up to KB trial points at once; the engine wrote them (every lane the same values) into s_pts
+    __device__ __forceinline__ double* batch_points() const { return s_pts; }
+    __device__ __forceinline__ double batch_cost(int k) const { return s_pts[3 * KB + k]; }
+    __device__ __forceinline__ bool batch_bad(int k) const { return s_pts[4 * KB + k] != 0.0; }
+    __device__ __forceinline__ void cost_many(int cnt, const double* /*dscl: batched fits are unscaled*/, int) const {
+        __syncwarp(mask);
+        if (cnt == 1) {  // (the first candidate of every walk: most walks end there)
+            const double pt[3] = {s_pts[0], s_pts[1], s_pts[2]};
+            bool bad;
+            const double e = cost(pt, bad);
+            if (lane == 0) { s_pts[3 * KB] = e; s_pts[4 * KB] = bad ? 1.0 : 0.0; }
+            __syncwarp(mask);
+            return;
+        }
+        double kd[KB], ksp[KB], nn[KB];
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+            const int kk = k < cnt ? k : 0;
+            kd[k] = s_pts[3 * kk];
+            nn[k] = s_pts[3 * kk + 2];
+            ksp[k] = model_ks(model, s_pts[3 * kk + 1], nn[k]);
+        }
+        double pw[S][KB];
+        powers<KB>(nn, pw);
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const int idx = s * G + lane;
+            if (idx < nper) {
+#pragma unroll
+                for (int k = 0; k < KB; ++k) {
+                    const double e = __dsub_rn(x[s], model_hx(kd[k], c[s], ksp[k], pw[s][k]));
+                    scratch[k * nper + idx] = __dmul_rn(e, e);
+                }
+            }
+        }
+        __syncwarp(mask);
+        const int quad = lane >> 2;
+        const double part = quad < cnt ? l2_partial(scratch + quad * nper, lane & 3) : 0.0;
+        const double esq = l2_combine(part, lane & ~3);
+        if (quad < cnt && (lane & 3) == 0) { s_pts[3 * KB + quad] = esq; s_pts[4 * KB + quad] = 0.0; }
+        __syncwarp(mask);
+        for (int k = 0; k < cnt; ++k) {
+            if (!lm_finite(s_pts[3 * KB + k])) {  // rare, uniform: the scaled norm needs the residuals themselves
+                const double pt[3] = {s_pts[3 * k], s_pts[3 * k + 1], s_pts[3 * k + 2]};
+                bool bad;
+                cost(pt, bad);
+                if (lane == 0) s_pts[4 * KB + k] = bad ? 1.0 : 0.0;
+                __syncwarp(mask);
+            }
+        }
     }
 
     // levmar's forward-difference Jacobian and its small-problem normal equations
@@ -121,16 +244,18 @@ struct ExactEval {
         const double ksp = model_ks(model, p[1], n);            // f(p), f(p + d0 e0)
         const double ksp_hi1 = model_ks(model, ph[1], n);       // f(p + d1 e1)
         const double ksp_hi2 = model_ks(model, p[1], ph[2]);    // f(p + d2 e2): the Phong factor follows n
+        const double y2[2] = {n, ph[2]};
+        double pw[S][2];
+        powers<2>(y2, pw);
 #pragma unroll
         for (int s = 0; s < S; ++s) {
             const int idx = s * G + lane;
             if (idx < nper) {
-                const double pw = pow_libm(t[s], n), pw_hi = pow_libm(t[s], ph[2]);
-                const double hx = model_hx(kd, c[s], ksp, pw);
+                const double hx = model_hx(kd, c[s], ksp, pw[s][0]);
                 double* row = scratch + 4 * idx;
-                row[0] = __dmul_rn(__dsub_rn(model_hx(ph[0], c[s], ksp, pw), hx), inv[0]);
-                row[1] = __dmul_rn(__dsub_rn(model_hx(kd, c[s], ksp_hi1, pw), hx), inv[1]);
-                row[2] = __dmul_rn(__dsub_rn(model_hx(kd, c[s], ksp_hi2, pw_hi), hx), inv[2]);
+                row[0] = __dmul_rn(__dsub_rn(model_hx(ph[0], c[s], ksp, pw[s][0]), hx), inv[0]);
+                row[1] = __dmul_rn(__dsub_rn(model_hx(kd, c[s], ksp_hi1, pw[s][0]), hx), inv[1]);
+                row[2] = __dmul_rn(__dsub_rn(model_hx(kd, c[s], ksp_hi2, pw[s][1]), hx), inv[2]);
                 row[3] = __dsub_rn(x[s], hx);  // e, lmbc_core.c:526 / 779
             }
         }
@@ -153,8 +278,12 @@ struct ExactEval {
     }
 };
 
+#ifndef BG_EXACT_MIN_BLOCKS
+#define BG_EXACT_MIN_BLOCKS 4  // 128 registers: measured best on B200 for 64- and 16-sample fits (profiles/r02_batched.md)
+#endif
+
 template <int G, int S>
-__global__ void __launch_bounds__(kExactThreads) k_batched_fit_exact(const double* __restrict__ c, const double* __restrict__ traw,
+__global__ void __launch_bounds__(kExactThreads, BG_EXACT_MIN_BLOCKS) k_batched_fit_exact(const double* __restrict__ c, const double* __restrict__ traw,
                                                                      const double* __restrict__ x, long nfit, ExactSpec spec,
                                                                      double* __restrict__ p_out, double* __restrict__ info_out,
                                                                      int* __restrict__ ret_out) {
@@ -163,8 +292,12 @@ __global__ void __launch_bounds__(kExactThreads) k_batched_fit_exact(const doubl
     if (fit >= nfit) return;
     const int lane = threadIdx.x % G, nper = spec.nper;
     const long base = fit * nper;
+    constexpr int KB = ExactEval<G, S>::KB;
+    constexpr int kPerSample = KB > 4 ? KB : 4;
     ExactEval<G, S> ev;
-    ev.scratch = exact_smem + (size_t)(threadIdx.x / G) * 4 * nper;
+    double* mine = exact_smem + (size_t)(threadIdx.x / G) * ((size_t)kPerSample * nper + 5 * KB);
+    ev.scratch = mine;
+    ev.s_pts = mine + (size_t)kPerSample * nper;
     ev.nper = nper; ev.lane = lane; ev.model = spec.model; ev.delta = spec.delta;
     ev.mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
 #pragma unroll
@@ -172,9 +305,10 @@ __global__ void __launch_bounds__(kExactThreads) k_batched_fit_exact(const doubl
         const int idx = s * G + lane;
         const bool in = idx < nper;
         ev.c[s] = in ? c[base + idx] : 0.0;
-        ev.t[s] = in ? traw[base + idx] : 0.0;
+        ev.t[s] = in ? traw[base + idx] : 0.5;
         ev.x[s] = in ? x[base + idx] : 0.0;
     }
+    ev.prepare();
     double p[3] = {spec.p0[0], spec.p0[1], spec.p0[2]};
     double info[10];
     const double* lb = spec.has_lb ? spec.lb : nullptr;
@@ -193,7 +327,8 @@ __global__ void __launch_bounds__(kExactThreads) k_batched_fit_exact(const doubl
 
 template <int G, int S>
 static int launch_exact(brdfgpu_ctx* ctx, brdfgpu_batch* b, const ExactSpec& spec) {
-    const size_t smem = sizeof(double) * 4 * (size_t)b->nper * (kExactThreads / G);
+    constexpr int KB = ExactEval<G, S>::KB;
+    const size_t smem = sizeof(double) * ((size_t)(KB > 4 ? KB : 4) * b->nper + 5 * KB) * (kExactThreads / G);
     if (smem > 48 * 1024)
         BG_CUDA_OK(ctx, cudaFuncSetAttribute(k_batched_fit_exact<G, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long blocks = (b->nfit * G + kExactThreads - 1) / kExactThreads;

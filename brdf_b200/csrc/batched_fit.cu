@@ -12,7 +12,6 @@
 
 #include "brdf_model.cuh"
 #include "common.cuh"
-#include "lm_machine.cuh"
 
 namespace brdfgpu {
 
@@ -365,158 +364,6 @@ __global__ void __launch_bounds__(kBatchThreads, BG_BATCH_MIN_BLOCKS(G)) k_batch
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Lock-step form: ONE THREAD per fit.  The control loop is the resumable state machine of
-// lm_machine.cuh, so a warp alternates between one evaluation section that all its lanes execute
-// together (each lane streams its own fit's samples from shared memory; no shuffles at all) and
-// one short, divergent control section.  With a warp per fit every lane executed the ~250 control
-// instructions of every evaluation redundantly; here they are shared by 32 fits.
-// Samples are staged once, transposed, in shared memory: element (sample s, fit f) at [s][f] with a
-// pitch of TPB + 1 doubles, so the lanes of a warp read consecutive words.
-// ------------------------------------------------------------------------------------------------
-template <int TPB>
-__global__ void __launch_bounds__(TPB) k_batched_fit_lockstep(const double* __restrict__ c, const double* __restrict__ L,
-                                                              const double* __restrict__ x, const double* __restrict__ traw,
-                                                              long nfit, int nper, int model, BatchSpec spec,
-                                                              unsigned long long* __restrict__ queue,
-                                                              double* __restrict__ p_out, double* __restrict__ info_out,
-                                                              int* __restrict__ ret_out) {
-    extern __shared__ double lock_smem[];
-    __shared__ double s_bounds[6];
-    constexpr int kPitch = TPB + 1;
-    // this thread's column of the CTA's sample tile: element s at [s * kPitch]
-    double* my_c = lock_smem + threadIdx.x;
-    double* my_L = my_c + (size_t)nper * kPitch;
-    double* my_x = my_L + (size_t)nper * kPitch;
-    if (threadIdx.x < 3) {
-        s_bounds[threadIdx.x] = spec.lb[threadIdx.x];
-        s_bounds[3 + threadIdx.x] = spec.ub[threadIdx.x];
-    }
-    __syncthreads();
-    const double p0[3] = {spec.p0[0], spec.p0[1], spec.p0[2]};
-    const double* lbp = spec.has_lb ? s_bounds : nullptr;
-    const double* ubp = spec.has_ub ? s_bounds + 3 : nullptr;
-
-    BcMachine<3> mc;
-    mc.want = kWantNothing;
-    long fit = -1;
-    const double* my_traw = traw;
-    // Fits finish after very different numbers of evaluations (a few percent run into itmax), so a lane
-    // that is done pulls the next fit from a global queue instead of idling until the slowest fit of
-    // its warp ends.
-    auto next_fit = [&]() {
-        const long f = (long)atomicAdd(queue, 1ULL);
-        if (f >= nfit) {
-            fit = -1;
-            mc.want = kWantNothing;
-            return;
-        }
-        fit = f;
-        const long base = f * nper;
-        my_traw = traw + base;
-        for (int s = 0; s < nper; ++s) {
-            my_c[s * kPitch] = c[base + s];
-            my_L[s * kPitch] = L[base + s];
-            my_x[s * kPitch] = x[base + s];
-        }
-        mc.start(3, p0, lbp, ubp, spec.opt);
-    };
-    next_fit();
-
-    for (;;) {
-        const int want = mc.want;
-        if (!__any_sync(0xffffffffu, want != kWantNothing)) break;
-        if (want == kWantCost) {
-            const CostPoint q = make_cost_point(mc.q, model);
-            double esq = 0.0, nbad = 0.0;
-            int s = 0;
-            for (; s + 4 <= nper; s += 4) {  // four samples = four independent exp chains
-                double cc[4], ll[4], xx[4], e[4];
-                long idx[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    cc[u] = my_c[(s + u) * kPitch]; ll[u] = my_L[(s + u) * kPitch]; xx[u] = my_x[(s + u) * kPitch];
-                    idx[u] = s + u;
-                }
-                residuals_n<4>(q, cc, ll, xx, my_traw, idx, e);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    esq = __fma_rn(e[u], e[u], esq);
-                    nbad += lm_finite(e[u]) ? 0.0 : 1.0;
-                }
-            }
-            for (; s < nper; ++s) {
-                const double e = residual_of(q, my_c[s * kPitch], my_L[s * kPitch], my_x[s * kPitch], my_traw, s);
-                esq = __fma_rn(e, e, esq);
-                nbad += lm_finite(e) ? 0.0 : 1.0;
-            }
-            mc.feed_cost(esq, nbad != 0.0);
-        }
-        // Jacobians are rare per lane (one in ~20 evaluations) but with 32 lanes nearly every round
-        // has somebody asking for one, and the warp would pay for both sections every round: lanes
-        // wait until a quarter of the warp wants a Jacobian (or nobody wants a function value).
-        const unsigned want_jac = __ballot_sync(0xffffffffu, want == kWantJac);
-        const unsigned want_cost = __ballot_sync(0xffffffffu, want == kWantCost);
-        const bool jac_round = want_jac != 0u && (__popc(want_jac) >= 8 || want_cost == 0u);
-        if (jac_round && want == kWantJac) {
-            const PassParams q = make_pass_params(mc.q, model, spec.delta, spec.jkind);
-            double acc[NACC];
-#pragma unroll
-            for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
-            int s = 0;
-            for (; s + 2 <= nper; s += 2) {
-                const double cc[2] = {my_c[s * kPitch], my_c[(s + 1) * kPitch]}, ll[2] = {my_L[s * kPitch], my_L[(s + 1) * kPitch]},
-                             xx[2] = {my_x[s * kPitch], my_x[(s + 1) * kPitch]};
-                const long idx[2] = {s, s + 1};
-                if (spec.jkind == kJacForward) accumulate_jac_n<kJacForward, 2>(q, q, cc, ll, xx, my_traw, idx, acc);
-                else if (spec.jkind == kJacCentral) accumulate_jac_n<kJacCentral, 2>(q, q, cc, ll, xx, my_traw, idx, acc);
-                else accumulate_jac_n<kJacAnalytic, 2>(q, q, cc, ll, xx, my_traw, idx, acc);
-            }
-            for (; s < nper; ++s) {
-                if (spec.jkind == kJacForward) accumulate_jac<kJacForward>(q, my_c[s * kPitch], my_L[s * kPitch], my_x[s * kPitch], my_traw, s, acc);
-                else if (spec.jkind == kJacCentral) accumulate_jac<kJacCentral>(q, my_c[s * kPitch], my_L[s * kPitch], my_x[s * kPitch], my_traw, s, acc);
-                else accumulate_jac<kJacAnalytic>(q, my_c[s * kPitch], my_L[s * kPitch], my_x[s * kPitch], my_traw, s, acc);
-            }
-            const double JtJ[9] = {acc[A00], acc[A01], acc[A02], acc[A01], acc[A11], acc[A12], acc[A02], acc[A12], acc[A22]};
-            const double Jte[3] = {acc[G0], acc[G1], acc[G2]};
-            mc.feed_jac(JtJ, Jte);
-        }
-        if (fit >= 0 && mc.want == kWantNothing) {  // this lane's fit is finished: results out, next fit in
-            double info[10];
-            mc.fill_info(info);
-            if (spec.dif_accounting) info[7] += info[8] * (spec.jkind == kJacCentral ? 6.0 : 4.0);  // lmbc_core.c:1119-1124
-            for (int i = 0; i < 3; ++i) p_out[fit * 3 + i] = mc.p[i];
-            if (info_out)
-                for (int i = 0; i < 10; ++i) info_out[fit * 10 + i] = info[i];
-            if (ret_out) ret_out[fit] = mc.ret();
-            next_fit();
-        }
-    }
-}
-
-template <int TPB>
-static bool launch_lockstep(brdfgpu_ctx* ctx, brdfgpu_batch* b, const BatchSpec& spec) {
-    const size_t smem = (size_t)3 * b->nper * (TPB + 1) * sizeof(double);
-    if (smem > 200 * 1024) return false;
-    if (cudaFuncSetAttribute(k_batched_fit_lockstep<TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-        cudaGetLastError();
-        return false;
-    }
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_batched_fit_lockstep<TPB>, TPB, smem) != cudaSuccess || per_sm < 1) {
-        cudaGetLastError();
-        return false;
-    }
-    long blocks = (long)ctx->sm_count * per_sm;  // persistent: every thread pulls fits from the queue
-    const long need = (b->nfit + TPB - 1) / TPB;
-    if (blocks > need) blocks = need;
-    unsigned long long* queue = reinterpret_cast<unsigned long long*>(ctx->d_sync + 8);
-    if (cudaMemsetAsync(queue, 0, sizeof(unsigned long long), ctx->stream) != cudaSuccess) return false;
-    k_batched_fit_lockstep<TPB><<<(unsigned)blocks, TPB, smem, ctx->stream>>>(b->c, b->L, b->x, b->traw, b->nfit, b->nper, b->model,
-                                                                            spec, queue, b->p, b->info, b->ret);
-    return true;
-}
-
 __global__ void k_prepare_batch(const double* __restrict__ traw, double* __restrict__ L, long n) {
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
         L[i] = log_or_flag(traw[i]);
@@ -596,24 +443,6 @@ int batch_fit(brdfgpu_ctx* ctx, brdfgpu_batch* b, const double* p0, const double
     // at their exits), which matters because the control code, not the model, dominates the
     // instruction count of a small fit.  BRDFGPU_BATCH_G overrides the choice (experiments).
     const int n = b->nper;
-    // Thread-per-fit lock-step kernel: opt-in with BRDFGPU_BATCH_LOCKSTEP=<threads per CTA: 128, 64, 32>.
-    // Measured on B200 (profiles/r01_summary.md): on par with the warp-per-fit kernel for 262 144 x 64
-    // (59.9 vs 60.9 ms) and 65 536 x 16 (11.1 vs 10.5 ms), slower for 65 536 x 64 (25.2 vs 16.8 ms):
-    // evaluation counts per fit are heavy-tailed (a few percent run into itmax), a lane owns a fit
-    // for its whole life, and 65 536 fits are only 1.7 fits per resident lane -- the tail dominates.
-    {
-        int tpb = 0;
-        if (const char* e = getenv("BRDFGPU_BATCH_LOCKSTEP")) tpb = atoi(e);
-        bool done = false;
-        if (tpb == 128) done = launch_lockstep<128>(ctx, b, spec);
-        else if (tpb == 64) done = launch_lockstep<64>(ctx, b, spec);
-        else if (tpb == 32) done = launch_lockstep<32>(ctx, b, spec);
-        if (done) {
-            ++ctx->launches;
-            BG_CUDA_OK(ctx, cudaGetLastError());
-            return 0;
-        }
-    }
     int G = n <= 16 ? 16 : 32;
     if (const char* e = getenv("BRDFGPU_BATCH_G")) G = atoi(e);
     const int S = (n + G - 1) / G;

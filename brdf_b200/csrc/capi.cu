@@ -5,7 +5,6 @@
 #include <vector>
 
 #include "common.cuh"
-#include "lm_machine.cuh"
 
 using namespace brdfgpu;
 
@@ -443,7 +442,8 @@ extern "C" int brdfgpu_solve_equation_batch(brdfgpu_ctx* ctx, long nfit, int npe
     static const double opts[5] = {1E-03, 1E-15, 1E-15, 1E-20, 1E-06};                        // brdfdata.cpp:1116-1117
     brdfgpu_batch* b = nullptr;
     if (brdfgpu_batch_upload(ctx, nfit, nper, phi, t, I, model, &b) != 0) return BRDFGPU_LM_ERROR;
-    int rc = brdfgpu_batch_fit(ctx, b, p0, lb, ub, 100, opts, BRDFGPU_JAC_FD);
+    // the reference's drivers promise the reference's results: levmar-exact wherever levmar's small-problem branch applies
+    int rc = brdfgpu_batch_fit(ctx, b, p0, lb, ub, 100, opts, nper <= 128 ? BRDFGPU_JAC_FD_EXACT : BRDFGPU_JAC_FD);
     if (rc == 0) rc = brdfgpu_batch_results(ctx, b, p_out, info_out, ret_out);
     brdfgpu_batch_free(ctx, b);
     return rc;
@@ -604,32 +604,6 @@ extern "C" int brdfgpu_lm_bc_reduced(brdfgpu_reduced_jac_t jac_cb, brdfgpu_reduc
                 for (int j = 0; j < m; ++j) covar[i * m + j] *= dscl[i] * dscl[j];
     }
     return ret;
-}
-
-// the same box-constrained fit driven through the resumable state machine of the batched kernel
-extern "C" int brdfgpu_lm_bc_machine(brdfgpu_reduced_jac_t jac_cb, brdfgpu_reduced_cost_t cost_cb, void* user, double* p,
-                                     int m, long n, const double* lb, const double* ub, int itmax, const double* opts,
-                                     double* info) {
-    if (!jac_cb || !cost_cb || !p || m < 1 || m > kMaxM || n < m) return BRDFGPU_LM_ERROR;
-    if (lb && ub)
-        for (int i = 0; i < m; ++i)
-            if (lb[i] > ub[i]) return BRDFGPU_LM_ERROR;
-    BcMachine<kMaxM> mc;
-    mc.start(m, p, lb, ub, lm_options(opts, itmax));
-    while (mc.want != kWantNothing) {
-        if (mc.want == kWantCost) {
-            double nonfinite = 0.0;
-            const double e = cost_cb(mc.q, m, &nonfinite, user);
-            mc.feed_cost(e, nonfinite != 0.0);
-        } else {
-            double JtJ[kMaxM * kMaxM], Jte[kMaxM];
-            jac_cb(mc.q, m, JtJ, Jte, user);
-            mc.feed_jac(JtJ, Jte);
-        }
-    }
-    for (int i = 0; i < m; ++i) p[i] = mc.p[i];
-    if (info) mc.fill_info(info);
-    return mc.ret();
 }
 
 extern "C" int brdfgpu_lm_unc_reduced(brdfgpu_reduced_jac_t jac_cb, brdfgpu_reduced_cost_t cost_cb, void* user, double* p,

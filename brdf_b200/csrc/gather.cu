@@ -895,7 +895,8 @@ extern "C" long brdfgpu_calc_brdf_equation(brdfgpu_ctx* ctx, const brdfgpu_scene
             set_error(ctx, std::string("calc_brdf_equation: ") + cudaGetErrorString(e));
             rc = BRDFGPU_LM_ERROR;
         }
-        if (rc == 0) rc = brdfgpu_batch_fit(ctx, b, p0, lb, ub, 100, opts, BRDFGPU_JAC_FD);
+        // (levmar-exact: every per-face result equals the reference's, brdfdata.cpp:1119)
+        if (rc == 0) rc = brdfgpu_batch_fit(ctx, b, p0, lb, ub, 100, opts, sc->nimg <= 128 ? BRDFGPU_JAC_FD_EXACT : BRDFGPU_JAC_FD);
         if (rc == 0) rc = brdfgpu_batch_results(ctx, b, p.data(), nullptr, nullptr);
     }
     brdfgpu_batch_free(ctx, b);

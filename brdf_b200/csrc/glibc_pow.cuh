@@ -128,6 +128,28 @@ BG_POW_HD int checkint(uint64_t iy) {
 }
 BG_POW_HD bool zeroinfnan(uint64_t i) { return 2 * i - 1 >= 2 * kInf - 1; }
 
+// Is exp_inline's argument outside the range its main path covers (|x| < 2^-54 or |x| >= 512)?
+BG_POW_HD bool exp_needs_care(double x) { return ((uint32_t)(bits_(x) >> 52) & 0x7ff) - 0x3c9u >= 0x3fu; }
+
+// The main path of exp_inline: sign_bias == 0 and 2^-54 <= |x| < 512, no branches (callers check exp_needs_care).
+BG_POW_HD double exp_ordinary(double x, double xtail) {
+    double kd = fma_(x, BG_EXP_INVLN2N, BG_EXP_SHIFT);
+    const uint64_t ki = bits_(kd);
+    kd = sub_(kd, BG_EXP_SHIFT);
+    double r = fma_(kd, BG_EXP_NEGLN2HIN, x);
+    r = fma_(kd, BG_EXP_NEGLN2LON, r);
+    r = add_(xtail, r);
+    const uint64_t idx = 2 * (ki % 128);
+    const double tail = dbl_(BG_EXP_TABLE[idx]);
+    const double scale = dbl_(BG_EXP_TABLE[idx + 1] + (ki << (52 - 7)));
+    const double r2 = mul_(r, r);
+    const double a = fma_(r, BG_EXP_POLYN[1], BG_EXP_POLYN[0]);
+    const double b = fma_(r, BG_EXP_POLYN[3], BG_EXP_POLYN[2]);
+    double tmp = fma_(a, r2, add_(r, tail));
+    tmp = fma_(b, mul_(r2, r2), tmp);
+    return fma_(tmp, scale, scale);
+}
+
 // exp(x + xtail) * (-1)^(sign_bias != 0), e_pow.c exp_inline + specialcase
 BG_POW_HD double exp_inline(double x, double xtail, uint32_t sign_bias) {
     uint32_t abstop = (uint32_t)(bits_(x) >> 52) & 0x7ff;
@@ -221,6 +243,19 @@ BG_POW_HD double log_inline(uint64_t ix, double* tail) {
 }
 
 }  // namespace glibcpow
+
+// ---- pow(x, y) in two halves, for callers that raise the same base to many exponents -------------------------
+// For an ordinary base (positive, normal, finite) and an ordinary exponent (2^-65 <= |y| < 2^63) pow() is
+// exp_inline(y * log(x)) with log(x) = hi + lo from log_inline, which depends on x alone: it can be computed once per
+// base and reused, with the very same bits as a fresh call.  Everything else goes through glibc_pow().
+BG_POW_HD bool pow_base_is_ordinary(double x) { return (uint32_t)(glibcpow::bits_(x) >> 52) - 0x001u < 0x7ffu - 0x001u; }
+BG_POW_HD bool pow_exponent_is_ordinary(double y) { return ((uint32_t)(glibcpow::bits_(y) >> 52) & 0x7ff) - 0x3beu < 0x43eu - 0x3beu; }
+BG_POW_HD void pow_log_of_base(double x, double* hi, double* lo) { *hi = glibcpow::log_inline(glibcpow::bits_(x), lo); }
+// y * (hi + lo) as ehi + elo (e_pow.c, FMA branch)
+BG_POW_HD void pow_scaled_log(double hi, double lo, double y, double* ehi, double* elo) {
+    *ehi = glibcpow::mul_(y, hi);
+    *elo = glibcpow::fma_(y, lo, glibcpow::fma_(hi, y, -*ehi));
+}
 
 // pow(x, y) with the bits glibc's __pow_fma returns
 BG_POW_HD double glibc_pow(double x, double y) {

@@ -148,8 +148,9 @@ void brdfgpu_samples_free(brdfgpu_ctx *ctx, brdfgpu_samples *s);
  * levmar's literal forward differences, its small-problem summation orders (lmbc_core.c:592-616, misc_core.c:721-807)
  * and its control arithmetic without multiply-add contraction -- so p, info[0..9] and the return value of every fit
  * EQUAL the reference's (not merely within tolerance), including the fits levmar abandons at itmax.  Forward
- * differences, at most 128 samples per fit (n m < 1024: levmar's small-problem branch).  About 2x slower than
- * BRDFGPU_JAC_FD, whose converged fits agree to the parity bars (1e-4 parameters, 1e-6 cost). */
+ * differences, at most 128 samples per fit (n m < 1024: levmar's small-problem branch).  1.5-1.9x the time of
+ * BRDFGPU_JAC_FD, whose converged fits agree to the parity bars (1e-4 parameters, 1e-6 cost).  The reference's own
+ * drivers below (brdfgpu_solve_equation, _solve_equation_batch, brdfgpu_calc_brdf_equation) use this mode. */
 #define BRDFGPU_JAC_FD_EXACT 2
 
 /* Global box-constrained fit on a resident sample set == dlevmar_bc_dif / _bc_der on the same data
@@ -197,7 +198,8 @@ int brdfgpu_solve_equation_single(const double *phi, const double *thetaDash, co
  * nfit independent dlevmar_bc_dif solves of nper samples each, fit f using rows
  * [f*nper, (f+1)*nper) of phi/thetaDash/theta/I.  p_out = nfit x 3, info_out = nfit x 10 (may be
  * NULL), ret_out = nfit levmar return values (may be NULL).  Options as brdfgpu_solve_equation
- * unless p0/opts/itmax are overridden through brdfgpu_batch_fit below. */
+ * unless p0/opts/itmax are overridden through brdfgpu_batch_fit below.  For nper <= 128 the fits run in the
+ * levmar-exact mode (BRDFGPU_JAC_FD_EXACT): p, info and ret equal dlevmar_bc_dif's bit for bit. */
 int brdfgpu_solve_equation_batch(brdfgpu_ctx *ctx, long nfit, int nper, const double *phi,
                                  const double *thetaDash, const double *theta, const double *I,
                                  int model, double *p_out, double *info_out, int *ret_out);
@@ -381,11 +383,6 @@ int brdfgpu_lm_bc_reduced(brdfgpu_reduced_jac_t jac_cb, brdfgpu_reduced_cost_t c
 int brdfgpu_lm_unc_reduced(brdfgpu_reduced_jac_t jac_cb, brdfgpu_reduced_cost_t cost_cb, void *user,
                            double *p, int m, long n, int itmax, const double *opts, double *info,
                            double *covar);
-/* brdfgpu_lm_bc_reduced (without dscl / covar) driven through the resumable state-machine form of the
- * control loop that the batched kernel runs, one fit per thread (csrc/lm_machine.cuh). */
-int brdfgpu_lm_bc_machine(brdfgpu_reduced_jac_t jac_cb, brdfgpu_reduced_cost_t cost_cb, void *user,
-                          double *p, int m, long n, const double *lb, const double *ub, int itmax,
-                          const double *opts, double *info);
 /* Test hook: on != 0 makes brdfgpu_lm_bc_reduced hand the projected-gradient candidates to the
  * evaluator eight at a time, the way the persistent fit kernel receives them (results must not
  * change).  Returns the previous setting; after a batched run, the largest batch that occurred. */

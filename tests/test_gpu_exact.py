@@ -75,6 +75,11 @@ def test_cup_every_per_face_fit_equals_the_reference(ctx):
     p, info, ret = np.concatenate(ps), np.concatenate(infos), np.concatenate(rets)
     _against_stored(p, info, ret, ref)
     # live, in float64: a spread over the faces, among them faces that see an LED from behind (pow(negative, n) = NaN)
+    # the public driver stores the same parameters per face and channel (SaveValuesToSurface, brdfdata.cpp:368-377)
+    n2, surf = scene.calc_brdf_equation(sc["cams"][0])
+    assert n2 == nfit
+    for ch in range(3):
+        assert np.array_equal(surf[ref["fit_face"], ch], p[ch * nfit:(ch + 1) * nfit])
     neg = np.flatnonzero((g["thetaDash"] < 0).any(axis=1))[:40]
     picks = sorted(set(range(0, nfit, 311)) | set(neg.tolist()))
     _against_live(g["phi"], g["thetaDash"], g["I"][1], p[nfit:2 * nfit], info[nfit:2 * nfit], ret[nfit:2 * nfit], picks)

@@ -1,4 +1,5 @@
-"""-m gpu: the TRUE agreement rate of the batched mode with the reference's levmar, over every fit of the two
+"""-m gpu: the TRUE agreement rate of the batched mode's FAST kernel (BRDFGPU_JAC_FD: exp(n ln t), butterfly sums; the
+levmar-exact kernel has tests/test_gpu_exact.py) with the reference's levmar, over every fit of the two
 batched workloads -- BASELINE.json configs[3] (65 536 fits x 64 samples) and the per-face path of configs[0]
 (every mapped face of img/cup x 3 colour channels, CalcBRDFEquation brdfdata.cpp:1188-1227).  The reference
 side is stored (tests/golden/batched_full_cfg3.npz, perface_full_cup.npz; one dlevmar_bc_dif call per fit by the
@@ -38,7 +39,7 @@ def test_configs3_every_fit_against_the_reference(ctx):
     ref = P.load_full("batched_full_cfg3.npz")
     nfit, nper = ref["p"].shape[0], int(ref["nper"])
     b = ctx.batch_synth(nfit, nper, seed=int(ref["seed"]))
-    b.fit(A.REF_PERFACE)
+    b.fit(A.REF_PERFACE, jac_mode=A.JAC_FD)
     p, info, ret = b.results()
     hist, cls = P.histogram(p, info, ret, ref)
     P.record("cfg3", hist)
@@ -58,7 +59,7 @@ def test_cup_every_per_face_fit_against_the_reference(ctx):
     for ch in range(3):
         _, b, n = scene.gather_resident(sc["cams"][:1], model=A.BLINN_PHONG, channel=ch, want_global=False, want_batch=True)
         assert n == nfit
-        b.fit(A.REF_PERFACE)
+        b.fit(A.REF_PERFACE, jac_mode=A.JAC_FD)
         p, info, ret = b.results()
         ps.append(p); infos.append(info); rets.append(ret)
         b.free()
@@ -66,17 +67,14 @@ def test_cup_every_per_face_fit_against_the_reference(ctx):
     hist, cls = P.histogram(p, info, ret, ref)
     P.record("cup", hist)
     print(hist)
-    # the public driver stores the same parameters per face and channel (SaveValuesToSurface, brdfdata.cpp:368-377)
-    n2, surf = scene.calc_brdf_equation(sc["cams"][0])
-    assert n2 == nfit
-    for ch in range(3):
-        assert np.array_equal(surf[ref["fit_face"], ch], p[ch * nfit:(ch + 1) * nfit])
     _check(hist, cls, FLOORS["cup"])
     scene.free()
 
 
 # measured on B200 (profiles/r02_parity.md), minus a small margin
+# measured: configs[3] 63 399 of 63 419 converged fits strict (20 not), 8 fits end > 1e-3 above the reference's cost,
+# 65 516 of 65 536 strict in all; cup 9 145 of 9 155 converged fits strict, 416 worse, 99 999 of 113 007 strict in all
 FLOORS = {
-    "cfg3": dict(converged_not_strict_max=10**9, converged_cost_miss_max=10**9, cost_worse_max=10**9, strict_min_fraction=0.0),
-    "cup": dict(converged_not_strict_max=10**9, converged_cost_miss_max=10**9, cost_worse_max=10**9, strict_min_fraction=0.0),
+    "cfg3": dict(converged_not_strict_max=40, converged_cost_miss_max=40, cost_worse_max=20, strict_min_fraction=0.999),
+    "cup": dict(converged_not_strict_max=25, converged_cost_miss_max=20, cost_worse_max=600, strict_min_fraction=0.87),
 }

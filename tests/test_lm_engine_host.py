@@ -145,18 +145,3 @@ def test_bc_engine_batched_projected_gradient_walk(prob):
     assert info.tobytes() == r_info.tobytes()
     if prob["name"] == "hatfldb":
         assert biggest >= 2   # this problem does walk the projected gradient (batches grow 1, 2, 4, 8)
-
-
-@pytest.mark.parametrize("prob", BC, ids=[p["name"] for p in BC])
-def test_bc_state_machine_matches_levmar(prob):
-    """csrc/lm_machine.cuh: the resumable form of the control loop that the batched kernel runs (one
-    fit per thread, evaluations in lock step across a warp) -- bit for bit levmar's trajectory."""
-    lib, prefix = _ref_or_oracle()
-    f, j = K.callbacks(prob)
-    x = np.array(prob["x"], dtype=np.float64)
-    r_ret, r_p, r_info, _ = O.levmar_bc_der(lib, prefix, f, j, prob["p0"], x, prob["lb"], prob["ub"], prob["itmax"], K.OPTS)
-    jac_cb, cost_cb = _reduced_callbacks(prob)
-    ret, p, info = A.lm_bc_machine(jac_cb, cost_cb, prob["p0"], prob["n"], prob["lb"], prob["ub"], prob["itmax"], K.OPTS)
-    assert ret == r_ret
-    assert p.tobytes() == r_p.tobytes()
-    assert info.tobytes() == r_info.tobytes()

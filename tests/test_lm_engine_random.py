@@ -2,7 +2,6 @@
 with random truth / noise / starts, bounds as in the reference (brdfdata.cpp:1112-1113), solved by
   * the reference's dlevmar_bc_der (oracle/_ref, else the oracle port) with Python callbacks,
   * lm_engine.cuh (brdfgpu_lm_bc_reduced), with and without the batched projected-gradient walk,
-  * lm_machine.cuh (brdfgpu_lm_bc_machine, the resumable form the lock-step batched kernel runs),
 all fed by the same callbacks with the normal equations formed in levmar's own order -- so every
 trajectory must be bit-identical: p and all of info[0..9].  These fits hit everything the BRDF path
 exercises on real data: active bounds, rejected steps, line searches, long projected-gradient walks,
@@ -70,7 +69,6 @@ def test_random_brdf_fits_bit_identical(seed):
         outs["engine, batched walk"] = A.lm_bc_reduced(jac_cb, cost_cb, prob["p0"], prob["n"], prob["lb"], prob["ub"], prob["itmax"], OPTS)[:3]
     finally:
         A.lib().brdfgpu_lm_reduced_batching(0)
-    outs["state machine"] = A.lm_bc_machine(jac_cb, cost_cb, prob["p0"], prob["n"], prob["lb"], prob["ub"], prob["itmax"], OPTS)
     for name, (ret, p, info) in outs.items():
         assert ret == r_ret, name
         assert p.tobytes() == r_p.tobytes(), (name, p, r_p)
