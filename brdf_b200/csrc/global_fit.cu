@@ -1596,6 +1596,20 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_persistent_fit(SampleVie
         info[4] = ev.batch_cost(0);
         info[5] = ev.batch_cost(1);
         ret = 0;
+    } else if (spec.spec_jac & 16) {
+        // scripted sequence (BRDFGPU_SPEC_JAC=16, bench.py's trajectory-invariant scaling figure): itmax rounds of one
+        // Jacobian sweep + one cost sweep at the start point, each with its grid-wide (and cross-GPU) exchange and no LM
+        // control code in between -- the same work on every rank count, whatever the data
+        bool bad;
+        double Jte[3];
+        for (int i = 0; i < 10; ++i) info[i] = 0.0;
+        for (int it = 0; it < spec.itmax; ++it) {
+            ev.jac(p, JtJ, Jte);
+            info[1] = ev.cost(p, bad);
+        }
+        info[5] = (double)spec.itmax;
+        info[2] = Jte[0];
+        ret = spec.itmax;
     } else if (spec.unconstrained)
         ret = lm_der<3>(ev, 3, p, spec.opt, info, JtJ);
     else
@@ -1753,7 +1767,8 @@ int global_fit(brdfgpu_ctx* ctx, const brdfgpu_samples* s, double* p, int m, con
         spec.want_n_all = (covar != nullptr && ctx->nranks > 1) ? 1 : 0;
         // BRDFGPU_SPEC_JAC=0 switches the speculative Jacobians off (A/B tests: results must not change)
         // (a bit mask for experiments: 1 = speculate at the trial / line-search / first-candidate sites, 2 = fuse the
-        // announced first candidate into the last line-search probe, 4 = start a walk at the last walk's width)
+        // announced first candidate into the last line-search probe, 4 = start a walk at the last walk's width,
+        // 8 = self-check of the sweep kinds, 16 = scripted Jacobian + cost sweeps instead of a fit)
         const char* sj = getenv("BRDFGPU_SPEC_JAC");
         spec.spec_jac = sj ? atoi(sj) : 7;
         for (int i = 0; i < 3; ++i) {

@@ -1,7 +1,7 @@
 """Small driver for ncu captures: a few launches of each hot kernel at a chosen size.
     python profiles/prof_kernels.py k2 100000000      K2 fused residual+Jacobian+JtJ pass (+K3 cost pass)
     python profiles/prof_kernels.py fit 1000000       the persistent global fit
-    python profiles/prof_kernels.py batch 65536 64    the batched per-face fits
+    python profiles/prof_kernels.py batch 65536 64 [exact]   the batched per-face fits (fast kernel / levmar-exact kernel)
     python profiles/prof_kernels.py gather            the gather on a synthetic scene
     python profiles/prof_kernels.py gather_scene      the gather on the reference's bunny scene (13 views), tests/_scenes
 """
@@ -30,9 +30,10 @@ elif what == "fit":
     print(r)
 elif what == "batch":
     nfit, nper = int(sys.argv[2]), int(sys.argv[3])
+    mode = A.JAC_FD_EXACT if len(sys.argv) > 4 and sys.argv[4] == "exact" else A.JAC_FD
     b = ctx.batch_synth(nfit, nper, seed=2026)
     for _ in range(2):
-        b.fit(A.REF_PERFACE)
+        b.fit(A.REF_PERFACE, jac_mode=mode)
     ctx.synchronize()
 elif what == "micro":
     # per-launch device times of K2 / K3 at several sizes + the two global-fit drivers
