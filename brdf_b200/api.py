@@ -87,6 +87,7 @@ SIGNATURES = {
     "brdfgpu_eval_repeat": (C.c_int, [_V, _V, dptr, C.c_double, C.c_int, C.c_int]),
     "brdfgpu_solve_equation": (C.c_int, [dptr, dptr, dptr, dptr, C.c_int, C.c_int, dptr, dptr]),
     "brdfgpu_solve_equation_single": (C.c_int, [dptr, dptr, dptr, dptr, C.c_long, C.c_int, dptr, dptr]),
+    "brdfgpu_solve_equation_single_colmajor": (C.c_int, [dptr, dptr, dptr, dptr, C.c_long, C.c_int, C.c_int, dptr, dptr]),
     "brdfgpu_solve_equation_batch": (C.c_int, [_V, C.c_long, C.c_int, dptr, dptr, dptr, dptr, C.c_int, dptr, dptr, iptr]),
     "brdfgpu_batch_upload": (C.c_int, [_V, C.c_long, C.c_int, dptr, dptr, dptr, C.c_int, C.POINTER(_V)]),
     "brdfgpu_batch_synth": (C.c_int, [_V, C.c_long, C.c_int, C.c_ulonglong, C.c_long, C.c_int, C.POINTER(_V)]),
@@ -102,6 +103,8 @@ SIGNATURES = {
     "brdfgpu_scene_dims": (C.c_int, [_V, iptr]),
     "brdfgpu_scene_set_gather_options": (C.c_int, [_V, _V, C.c_int, dptr, C.c_int]),
     "brdfgpu_read_cal_kappa1": (C.c_int, [C.c_char_p, dptr]),
+    "brdfgpu_scene_set_gl_projection": (C.c_int, [_V, _V, dptr, dptr, iptr]),
+    "brdfgpu_reference_gl_matrices": (None, [C.c_double, C.c_double, C.c_int, C.c_int, dptr, dptr]),
     "brdfgpu_shade_faces": (C.c_int, [_V, _V, dptr, dptr, C.c_int, C.c_int, dptr, C.c_int, dptr]),
     "brdfgpu_scene_create": (C.c_int, [_V, dptr, C.c_int, iptr, C.c_int, C.POINTER(_V), C.c_int, C.c_int, C.c_int, _V, dptr, C.POINTER(_V)]),
     "brdfgpu_scene_free": (None, [_V, _V]),
@@ -245,6 +248,15 @@ class Scene:
         GATHER_SEQ_DOT (left-to-right dot products in GetCosLN / GetCosNH instead of Eigen 3.3's order)."""
         k = _arr(kappa1)
         self.ctx._ok(lib().brdfgpu_scene_set_gather_options(self.ctx.handle, self.handle, int(flags), _d(k), 0 if k is None else k.size))
+
+    def set_gl_projection(self, model_view=None, projection=None, viewport=None):
+        """The reference's literal gluProject mapping (brdfdata.cpp:662-677) for later gathers; no arguments: Tsai again."""
+        if model_view is None:
+            self.ctx._ok(lib().brdfgpu_scene_set_gl_projection(self.ctx.handle, self.handle, None, None, None))
+            return
+        mv, pr = _arr(model_view, 16), _arr(projection, 16)
+        vp = np.ascontiguousarray(viewport, dtype=np.int32)
+        self.ctx._ok(lib().brdfgpu_scene_set_gl_projection(self.ctx.handle, self.handle, _d(mv), _d(pr), vp.ctypes.data_as(iptr)))
 
     def shade_faces(self, eye, center, brdf, model=BLINN_PHONG, literal_cosln=True):
         """Per-face (B, G, R) of the BRDF-shaded preview, glutcallbacks.cpp:346-445.  brdf: (3, 3) single or (nF, 3, 3)."""
@@ -585,6 +597,15 @@ def solve_equation_single(phi, thetaDash, theta, inten, model=BLINN_PHONG):
     return ret, p, info
 
 
+def solve_equation_single_colmajor(phi, thetaDash, theta, inten, model=BLINN_PHONG):
+    """SolveEquation_SingleBRDF with the reference's literal flattening (brdfdata.cpp:1008-1042); inputs rows x nimg"""
+    rows, nimg = np.asarray(phi).shape
+    phi, td, th, inten = _arr(phi), _arr(thetaDash), _arr(theta), _arr(inten)
+    p, info = np.zeros(3), np.zeros(10)
+    ret = lib().brdfgpu_solve_equation_single_colmajor(_d(phi), _d(td), _d(th), _d(inten), rows, nimg, model, _d(p), _d(info))
+    return ret, p, info
+
+
 GATHER_DEPTH_TEST, GATHER_CULL_BACKFACES, GATHER_KAPPA1, GATHER_SEQ_DOT = 1, 2, 4, 8
 
 
@@ -595,6 +616,13 @@ def read_cal_kappa1(path):
     if has < 0:
         raise BrdfGpuError(lib().brdfgpu_last_error(None).decode())
     return (k.value if has else None)
+
+
+def reference_gl_matrices(cx, cy, window_width=1920, window_height=1080):
+    """(model_view16, projection16) as the reference's Display_ sets them up (glutcallbacks.cpp:626-642, 672-689)"""
+    mv, pr = np.zeros(16), np.zeros(16)
+    lib().brdfgpu_reference_gl_matrices(float(cx), float(cy), int(window_width), int(window_height), _d(mv), _d(pr))
+    return mv, pr
 
 
 def read_cal(path):

@@ -431,6 +431,27 @@ extern "C" int brdfgpu_solve_equation_single(const double* phi, const double* th
     return ret;
 }
 
+// SolveEquation_SingleBRDF exactly as the reference flattens its matrices (brdfdata.cpp:1008-1042):
+// the measurements row-major, x[i * nimg + j] = I(i, j), but the three angle blocks through Eigen's LINEAR index of a
+// column-major MatrixXd, angles[k] = phi(k) = phi(k % rows, k / rows).  Sample k therefore pairs I(k / nimg, k % nimg)
+// with the cosines of face k % rows and LED k / rows.
+extern "C" int brdfgpu_solve_equation_single_colmajor(const double* phi, const double* thetaDash, const double* theta,
+                                                      const double* I, long rows, int nimg, int model, double* p,
+                                                      double* info) {
+    if (!phi || !I || !p || rows < 1 || nimg < 1) return BRDFGPU_LM_ERROR;
+    const double* t = model == 1 ? thetaDash : theta;
+    if (!t) return BRDFGPU_LM_ERROR;
+    const long n = rows * nimg;
+    std::vector<double> c((size_t)n), tt((size_t)n);
+    for (long k = 0; k < n; ++k) {
+        const long src = (k % rows) * nimg + (k / rows);  // row-major storage of element (k % rows, k / rows)
+        c[(size_t)k] = phi[src];
+        tt[(size_t)k] = t[src];
+    }
+    return brdfgpu_solve_equation_single(c.data(), model == 1 ? tt.data() : nullptr, model == 1 ? nullptr : tt.data(), I, n, model, p,
+                                         info);
+}
+
 extern "C" int brdfgpu_solve_equation_batch(brdfgpu_ctx* ctx, long nfit, int nper, const double* phi,
                                             const double* thetaDash, const double* theta, const double* I, int model,
                                             double* p_out, double* info_out, int* ret_out) {

@@ -19,6 +19,7 @@
 // Face centroids and normals are per-scene constants (computed once by k_face_geometry); the sample
 // kernel writes straight into the arrays of the fit stage (cosphi, model cosine, its log, the channel's
 // intensities), so a resident gather needs no device-to-device hand-over and one synchronisation.
+#include <cmath>
 #include <vector>
 
 #include "brdf_model.cuh"
@@ -52,6 +53,10 @@ struct brdfgpu_scene {
     double* FC = nullptr;          // nF x 3 face centroids, brdfdata.cpp:653-660 (the same for every view and LED)
     unsigned char* img = nullptr;  // nimg x H x W x 3 (BGR), ambient already removed
     double* led = nullptr;         // nimg x 3
+    // the reference's literal projection (brdfgpu_scene_set_gl_projection); off: the Tsai camera
+    bool gl_on = false;
+    double gl_mv[16] = {0}, gl_proj[16] = {0};
+    int gl_viewport[4] = {0, 0, 0, 0};
 };
 
 namespace brdfgpu {
@@ -270,6 +275,38 @@ __global__ void k_project(const double* __restrict__ FC, int nF, const double* _
     if (px >= 0) atomicMax(maps + (long)v * W * H + px, face);
 }
 
+// The reference's literal projection (brdfdata.cpp:662-677): gluProject through the GL MODELVIEW / PROJECTION matrices and
+// the viewport as the caller read them back from GL.  gluProject is libGLU's (SGI / Mesa GLU 9.0 project.c): two
+// column-major 4x4 matrix-vector products summed left to right, perspective divide, * 0.5 + 0.5, viewport scale.  The
+// reference writes the map for winX, winY >= 0 with no upper bound; here only pixels inside the map are written.
+// Rows are GL rows (bottom-up); the radiance fetch flips them (brdfdata.cpp:955).
+struct GlProjection {
+    double mv[16], proj[16];
+    double vx, vy, vw, vh;  // viewport as doubles (the int -> double conversions of in[0] * viewport[2] + viewport[0])
+};
+__device__ __forceinline__ void glu_mult(const double* m, const double* in, double* out) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        out[i] = dadd(dadd(dadd(dmul(in[0], m[i]), dmul(in[1], m[4 + i])), dmul(in[2], m[8 + i])), dmul(in[3], m[12 + i]));
+}
+__global__ void k_project_gl(const double* __restrict__ FC, int nF, GlProjection gl, int W, int H, int* __restrict__ pix,
+                             int* __restrict__ maps) {
+    const int face = blockIdx.x * blockDim.x + threadIdx.x;
+    if (face >= nF) return;
+    const double in[4] = {FC[3l * face], FC[3l * face + 1], FC[3l * face + 2], 1.0};
+    double eye[4], clip[4];
+    glu_mult(gl.mv, in, eye);
+    glu_mult(gl.proj, eye, clip);
+    int px = -1;
+    if (clip[3] != 0.0) {
+        const double winx = dadd(dmul(dadd(dmul(ddiv(clip[0], clip[3]), 0.5), 0.5), gl.vw), gl.vx);
+        const double winy = dadd(dmul(dadd(dmul(ddiv(clip[1], clip[3]), 0.5), 0.5), gl.vh), gl.vy);
+        if (winy >= 0 && winx >= 0 && winx < (double)W && winy < (double)H) px = (int)winy * W + (int)winx;
+    }
+    pix[face] = px;
+    if (px >= 0) atomicMax(maps + px, face);
+}
+
 // ---- ordered compaction of the faces that still own their pixel (view-major, ascending face id) ----
 constexpr int kScanThreads = 1024;
 
@@ -375,12 +412,16 @@ struct GatherOut {
 // one thread per (fit, LED): the cosines and the three channel intensities of that sample.
 // NH / RV: compute cos(theta') / the literal cos(theta) (each costs a normalisation = 1 sqrt + 3 divisions, and
 // bit-exactness forbids anything cheaper); SEQ: left-to-right dots in GetCosLN / GetCosNH (BRDFGPU_GATHER_SEQ_DOT).
+#ifndef BG_GATHER_MIN_BLOCKS
+#define BG_GATHER_MIN_BLOCKS 6  // 40 registers: 138 vs 148 us per 13-view call at 4 (profiles/r02_summary.md)
+#endif
 template <bool NH, bool RV, bool SEQ>
-__global__ void __launch_bounds__(256) k_gather_samples(const double* __restrict__ FC, const double* __restrict__ FN,
+__global__ void __launch_bounds__(256, BG_GATHER_MIN_BLOCKS) k_gather_samples(const double* __restrict__ FC, const double* __restrict__ FN,
                                                         const double* __restrict__ led, const unsigned char* __restrict__ img,
                                                         const double* __restrict__ cams, const int* __restrict__ fit_face,
                                                         const int* __restrict__ fit_pixel, const int* __restrict__ fit_cam,
-                                                        const int* __restrict__ nfit_dev, int nimg, int W, int H, GatherOut o) {
+                                                        const int* __restrict__ nfit_dev, int nimg, int W, int H, int flip_rows,
+                                                        GatherOut o) {
     const long ns = (long)*nfit_dev * nimg;
     if ((long)blockIdx.x * 256 >= ns) return;  // the grid is sized for the capacity (every face of every view mapped)
     // u8 / 255.0 (brdfdata.cpp:956) for all 256 bytes: one division per thread instead of three
@@ -430,8 +471,11 @@ __global__ void __launch_bounds__(256) k_gather_samples(const double* __restrict
             o.fit2_L[s] = Lg;
         }
     }
-    // GetIntensities_FromPixel, brdfdata.cpp:955-956 (Tsai rows are top-down: no flip)
-    const unsigned char* px = img + ((long)k * H * W + fit_pixel[fit]) * 3;
+    // GetIntensities_FromPixel, brdfdata.cpp:955-956: Tsai rows are top-down (no flip); the literal GL projection
+    // yields bottom-up rows and reads image row H-1-y
+    int pixel = fit_pixel[fit];
+    if (flip_rows) pixel = (H - 1 - pixel / W) * W + pixel % W;
+    const unsigned char* px = img + ((long)k * H * W + pixel) * 3;
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
         const double v = lut[px[ch]];
@@ -505,7 +549,17 @@ static int gather_device(brdfgpu_ctx* ctx, const brdfgpu_scene* sc, const double
     tr.mark("allocation + H2D of the cameras");
 
     k_fill_int<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(g->maps, npix, -1);
-    if ((sc->gather_flags & ~BRDFGPU_GATHER_SEQ_DOT) == 0) {
+    if (sc->gl_on) {
+        if (ncam != 1 || (sc->gather_flags & ~BRDFGPU_GATHER_SEQ_DOT)) {
+            set_error(ctx, "gather: the literal GL projection maps one view (one set of GL matrices) and takes no projection options");
+            return BRDFGPU_LM_ERROR;
+        }
+        GlProjection gl;
+        for (int i = 0; i < 16; ++i) { gl.mv[i] = sc->gl_mv[i]; gl.proj[i] = sc->gl_proj[i]; }
+        gl.vx = (double)sc->gl_viewport[0]; gl.vy = (double)sc->gl_viewport[1];
+        gl.vw = (double)sc->gl_viewport[2]; gl.vh = (double)sc->gl_viewport[3];
+        k_project_gl<<<(unsigned)((sc->nF + 255) / 256), 256, 0, ctx->stream>>>(sc->FC, sc->nF, gl, sc->W, sc->H, g->pix, g->maps);
+    } else if ((sc->gather_flags & ~BRDFGPU_GATHER_SEQ_DOT) == 0) {
         k_project<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(sc->FC, sc->nF, g->cams, ncam, sc->W, sc->H, g->pix,
                                                                             g->maps);
     } else {
@@ -573,7 +627,8 @@ static int gather_device(brdfgpu_ctx* ctx, const brdfgpu_scene* sc, const double
     const int* nfit_dev = g->cam_first + ncam;
 #define BG_GATHER_LAUNCH(NH_, RV_, SEQ_)                                                                                    \
     k_gather_samples<NH_, RV_, SEQ_><<<blocks, 256, 0, ctx->stream>>>(sc->FC, sc->FN, sc->led, sc->img, g->cams, g->fit_face, \
-                                                                      g->fit_pixel, g->fit_cam, nfit_dev, sc->nimg, sc->W, sc->H, o)
+                                                                      g->fit_pixel, g->fit_cam, nfit_dev, sc->nimg, sc->W, sc->H, \
+                                                                      sc->gl_on ? 1 : 0, o)
     if (seq) {
         if (nh && rv) BG_GATHER_LAUNCH(true, true, true);
         else if (nh) BG_GATHER_LAUNCH(true, false, true);
@@ -736,6 +791,38 @@ extern "C" int brdfgpu_scene_set_gather_options(brdfgpu_ctx* ctx, brdfgpu_scene*
     sc->kappa1.clear();
     if (flags & BRDFGPU_GATHER_KAPPA1) sc->kappa1.assign(kappa1, kappa1 + ncam);
     return 0;
+}
+
+extern "C" int brdfgpu_scene_set_gl_projection(brdfgpu_ctx* ctx, brdfgpu_scene* sc, const double* model_view16,
+                                               const double* projection16, const int* viewport4) {
+    ctx = ctx_or_default(ctx);
+    if (!ctx || !sc) return BRDFGPU_LM_ERROR;
+    if (!model_view16 || !projection16 || !viewport4) {  // back to the Tsai camera
+        sc->gl_on = false;
+        return 0;
+    }
+    for (int i = 0; i < 16; ++i) { sc->gl_mv[i] = model_view16[i]; sc->gl_proj[i] = projection16[i]; }
+    for (int i = 0; i < 4; ++i) sc->gl_viewport[i] = viewport4[i];
+    sc->gl_on = true;
+    return 0;
+}
+
+// MakeFrustum + glFrustum and gluLookAt(0,0,50, 0,0,0, 0,1,0) as the reference's Display_ sets them up
+// (glutcallbacks.cpp:626-642, 672-689), entries rounded to the float32 GL stores them in
+extern "C" void brdfgpu_reference_gl_matrices(double cx, double cy, int window_width, int window_height, double* mv,
+                                              double* proj) {
+    const double DEG2RAD = 3.14159265 / 180, fov = 78, fovV = 49, front = 1.0, back = 1000.0;  // glutcallbacks.cpp:57-62, 628
+    const double aspect = fov / fovV;
+    const double tangent = tan(fovV / 2 * DEG2RAD), height = front * tangent, width = height * aspect;
+    const double offset_y = 2.0 * (window_height / 2.0 - cy) / window_height, offset_x = 2.0 * (window_width / 2.0 - cx) / window_width;
+    const double l = -width + offset_x, r = width + offset_x, b = -height - offset_y, t = height - offset_y;
+    for (int i = 0; i < 16; ++i) { mv[i] = 0.0; proj[i] = 0.0; }
+    proj[0] = 2 * front / (r - l); proj[5] = 2 * front / (t - b);
+    proj[8] = (r + l) / (r - l); proj[9] = (t + b) / (t - b); proj[10] = -(back + front) / (back - front); proj[11] = -1.0;
+    proj[14] = -2 * back * front / (back - front);
+    mv[0] = mv[5] = mv[10] = mv[15] = 1.0;
+    mv[14] = -50.0;
+    for (int i = 0; i < 16; ++i) { mv[i] = (double)(float)mv[i]; proj[i] = (double)(float)proj[i]; }
 }
 
 extern "C" int brdfgpu_scene_dims(const brdfgpu_scene* sc, int* dims5) {

@@ -194,6 +194,15 @@ int brdfgpu_solve_equation(const double *phi, const double *thetaDash, const dou
 int brdfgpu_solve_equation_single(const double *phi, const double *thetaDash, const double *theta,
                                   const double *I, long nsamples, int model, double *p, double *info);
 
+/* The same with the reference's LITERAL flattening (brdfdata.cpp:1008-1042): phi / thetaDash / theta /
+ * I are rows x nimg row-major (one row per face, as the reference's matrices); the measurements are taken row-major,
+ * x[i*nimg + j] = I(i, j), the angle blocks through Eigen's linear (column-major) index, angles[k] = phi(k % rows, k / rows)
+ * -- so sample k pairs the intensity of face k / nimg with the cosines of face k % rows.  Every row must hold values
+ * (the reference leaves the rows of unmapped faces uninitialised).  For comparing against the reference as written;
+ * brdfgpu_solve_equation_single is the aligned order. */
+int brdfgpu_solve_equation_single_colmajor(const double *phi, const double *thetaDash, const double *theta,
+                                           const double *I, long rows, int nimg, int model, double *p, double *info);
+
 /* The per-pixel loop of CBRDFdata::CalcBRDFEquation (brdfdata.cpp:1195-1221) as one launch:
  * nfit independent dlevmar_bc_dif solves of nper samples each, fit f using rows
  * [f*nper, (f+1)*nper) of phi/thetaDash/theta/I.  p_out = nfit x 3, info_out = nfit x 10 (may be
@@ -279,6 +288,23 @@ long brdfgpu_gather(brdfgpu_ctx *ctx, const brdfgpu_scene *sc, const double *cam
  * (round 1's definition; differs in the last bit of some cosines).  oracle/gather_oracle.c has the derivation. */
 #define BRDFGPU_GATHER_SEQ_DOT 8
 int brdfgpu_scene_set_gather_options(brdfgpu_ctx *ctx, brdfgpu_scene *sc, int flags, const double *kappa1, int ncam);
+
+/* The reference's LITERAL projection instead of the Tsai camera, for every later gather / pixel-map call on this
+ * scene: CalcPixel2SurfaceMapping reads GL_MODELVIEW_MATRIX, GL_PROJECTION_MATRIX and GL_VIEWPORT back and calls
+ * gluProject (brdfdata.cpp:662-671); pass those three arrays as the caller read them (column-major, 16 + 16 doubles,
+ * 4 ints).  gluProject's arithmetic is libGLU's (SGI / Mesa GLU 9.0 project.c), reproduced operation by operation.
+ * Map rows are GL rows (bottom-up) and the radiance fetch reads image row H-1-y (brdfdata.cpp:955).  The reference
+ * writes map(winY, winX) for any winX, winY >= 0 with no upper bound (an out-of-bounds write on the shipped data,
+ * SURVEY.md 2.4-Q1); here pixels outside the W x H map are dropped.  One view per call (one set of GL matrices); the
+ * camera passed to the gather still supplies the position of GetCosNH.  Any pointer NULL: back to the Tsai camera. */
+int brdfgpu_scene_set_gl_projection(brdfgpu_ctx *ctx, brdfgpu_scene *sc, const double *model_view16,
+                                    const double *projection16, const int *viewport4);
+/* The matrices the reference's Display_ leaves in GL before the mapping (glutcallbacks.cpp:626-642, 672-689): the
+ * asymmetric frustum of the constant 78 / 49 degree fields of view around the .cal principal point (cx, cy), offsets
+ * scaled by the WINDOW size (1920 x 1080 by default, main.cpp:22-23), near 1, far 1000, and
+ * gluLookAt(0,0,50, 0,0,0, 0,1,0); entries rounded to float32 as GL stores them.  Host code. */
+void brdfgpu_reference_gl_matrices(double cx, double cy, int window_width, int window_height, double *model_view16,
+                                   double *projection16);
 
 /* Gather that stays on the device and hands the samples straight to the fit stages. */
 int brdfgpu_gather_resident(brdfgpu_ctx *ctx, const brdfgpu_scene *sc, const double *cams, int ncam,

@@ -430,3 +430,114 @@ int oracle_gather_opts(const double *V, const int *F, int nF, const double *cam,
     free(FN);
     return nfit;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * The LITERAL projection of the reference: CalcPixel2SurfaceMapping reads the GL MODELVIEW / PROJECTION
+ * matrices and the viewport back (brdfdata.cpp:662-669) and calls gluProject (:671).  gluProject lives in
+ * libGLU (un-vendored, un-versioned system library; SGI's implementation as shipped by Mesa GLU 9.0,
+ * src/libutil/project.c), restated here from its published source:
+ *     out = M_modelview * (x, y, z, 1);  in = M_projection * out   (column-major matrices, each component
+ *     in[0]*m[0*4+i] + in[1]*m[1*4+i] + in[2]*m[2*4+i] + in[3]*m[3*4+i], left to right)
+ *     fail when in[3] == 0;  in[0..2] /= in[3];  in[k] = in[k] * 0.5 + 0.5;
+ *     winx = in[0] * viewport[2] + viewport[0];  winy = in[1] * viewport[3] + viewport[1]
+ * The reference then writes map.at<int>(winY, winX) = i whenever winY >= 0 && winX >= 0 (:676-677) -- WITHOUT an
+ * upper bound (with the shipped matrices every such write lands outside the 800 x 600 map).  Here the
+ * write is made only inside the map; rows are GL rows (bottom-up), and the radiance fetch flips them,
+ * images[k](H-1-y, x) (brdfdata.cpp:955).
+ * ------------------------------------------------------------------------------------------------ */
+static void glu_mult_matrix_vec(const double *m, const double *in, double *out)
+{
+    int i;
+    for (i = 0; i < 4; ++i)
+        out[i] = in[0] * m[0 * 4 + i] + in[1] * m[1 * 4 + i] + in[2] * m[2 * 4 + i] + in[3] * m[3 * 4 + i];
+}
+
+static int project_gl(const double *c, const double *mv, const double *proj, const int *viewport, int W, int H,
+                      int *col, int *row)
+{
+    double in[4], out[4], winx, winy;
+    in[0] = c[0]; in[1] = c[1]; in[2] = c[2]; in[3] = 1.0;
+    glu_mult_matrix_vec(mv, in, out);
+    glu_mult_matrix_vec(proj, out, in);
+    if (in[3] == 0.0) return 0;
+    in[0] /= in[3]; in[1] /= in[3];
+    in[0] = in[0] * 0.5 + 0.5;
+    in[1] = in[1] * 0.5 + 0.5;
+    winx = in[0] * viewport[2] + viewport[0];
+    winy = in[1] * viewport[3] + viewport[1];
+    if (!(winy >= 0 && winx >= 0)) return 0;                   /* brdfdata.cpp:676 */
+    if (!(winx < (double)W && winy < (double)H)) return 0;     /* (the reference writes out of bounds here) */
+    *col = (int)winx;
+    *row = (int)winy;
+    return 1;
+}
+
+int oracle_calc_pixel2surface_gl(const double *V, const int *F, int nF, const double *mv, const double *proj,
+                                 const int *viewport, int W, int H, int *map)
+{
+    int i, hits = 0;
+    for (i = 0; i < W * H; ++i) map[i] = -1;
+    for (i = 0; i < nF; ++i) {
+        double c[3];
+        int col, row;
+        centroid(V, F, i, c);
+        if (project_gl(c, mv, proj, viewport, W, H, &col, &row)) {
+            map[row * W + col] = i;
+            ++hits;
+        }
+    }
+    return hits;
+}
+
+/* the whole gather through the literal projection; cam supplies the camera position of GetCosNH (m_p) */
+int oracle_gather_gl(const double *V, const int *F, int nF, const double *cam, const double *mv, const double *proj,
+                     const int *viewport, const double *led, const unsigned char *const *images, int nimg, int W, int H,
+                     int *map, int *fit_face, int *fit_pixel, double *phi, double *thetaDash, double *theta, double *I)
+{
+    double *FN;
+    int i, ch, nfit = 0;
+    FN = (double *)malloc((size_t)nF * 3 * sizeof(double));
+    if (!FN) return -1;
+    oracle_face_normals(V, F, nF, FN);
+    oracle_calc_pixel2surface_gl(V, F, nF, mv, proj, viewport, W, H, map);
+    for (i = 0; i < nF; ++i) {
+        double c[3];
+        int col, row;
+        centroid(V, F, i, c);
+        if (!project_gl(c, mv, proj, viewport, W, H, &col, &row)) continue;
+        if (map[row * W + col] != i) continue;
+        fit_face[nfit] = i;
+        fit_pixel[nfit] = row * W + col;
+        oracle_cos_ln(V, F, FN, led, nimg, i, phi + (size_t)nfit * nimg);
+        oracle_cos_nh(V, F, FN, led, nimg, cam, i, thetaDash + (size_t)nfit * nimg);
+        oracle_cos_rv(V, F, FN, led, nimg, cam, i, theta + (size_t)nfit * nimg);
+        for (ch = 0; ch < 3; ++ch)   /* GetIntensities_FromPixel(x, y, c): row H-1-y, brdfdata.cpp:955 */
+            oracle_intensities_from_pixel(images, nimg, W, H, col, H - 1 - row, ch,
+                                          I + (size_t)ch * nF * nimg + (size_t)nfit * nimg);
+        ++nfit;
+    }
+    free(FN);
+    return nfit;
+}
+
+/* The matrices the reference's Display_ sets up before the mapping (glutcallbacks.cpp:626-642, 672-689): an
+ * asymmetric frustum from the constant fields of view 78 / 49 degrees with the principal point of the .cal file,
+ * offsets scaled by the WINDOW size, and gluLookAt(0,0,50, 0,0,0, 0,1,0).  GL keeps matrices in float32 and
+ * glGetDoublev widens them: entries are computed in double here and rounded to float32 once; the
+ * driver's own float arithmetic is not part of any contract. */
+void oracle_reference_gl_matrices(double cx, double cy, int win_w, int win_h, double *mv, double *proj)
+{
+    const double DEG2RAD = 3.14159265 / 180, fov = 78, fovV = 49, front = 1.0, back = 1000.0;
+    const double aspect = fov / fovV;
+    const double tangent = tan(fovV / 2 * DEG2RAD), height = front * tangent, width = height * aspect;
+    const double offset_y = 2.0 * (win_h / 2.0 - cy) / win_h, offset_x = 2.0 * (win_w / 2.0 - cx) / win_w;
+    const double l = -width + offset_x, r = width + offset_x, b = -height - offset_y, t = height - offset_y;
+    int i;
+    for (i = 0; i < 16; ++i) { mv[i] = 0.0; proj[i] = 0.0; }
+    proj[0] = 2 * front / (r - l); proj[5] = 2 * front / (t - b);
+    proj[8] = (r + l) / (r - l); proj[9] = (t + b) / (t - b); proj[10] = -(back + front) / (back - front); proj[11] = -1.0;
+    proj[14] = -2 * back * front / (back - front);
+    mv[0] = mv[5] = mv[10] = mv[15] = 1.0;   /* looking down -z from (0,0,50) with +y up: a pure translation */
+    mv[14] = -50.0;
+    for (i = 0; i < 16; ++i) { mv[i] = (double)(float)mv[i]; proj[i] = (double)(float)proj[i]; }
+}

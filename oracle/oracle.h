@@ -109,6 +109,14 @@ int  oracle_gather_opts(const double *V, const int *F, int nF, const double *cam
                         int *map, int *fit_face, int *fit_pixel,
                         double *phi, double *thetaDash, double *theta, double *I);
 
+/* The reference's LITERAL projection (gluProject through the GL matrices, brdfdata.cpp:662-677) */
+int  oracle_calc_pixel2surface_gl(const double *V, const int *F, int nF, const double *mv, const double *proj,
+                                  const int *viewport, int W, int H, int *map);
+int  oracle_gather_gl(const double *V, const int *F, int nF, const double *cam, const double *mv, const double *proj,
+                      const int *viewport, const double *led, const unsigned char *const *images, int nimg, int W, int H,
+                      int *map, int *fit_face, int *fit_pixel, double *phi, double *thetaDash, double *theta, double *I);
+void oracle_reference_gl_matrices(double cx, double cy, int win_w, int win_h, double *mv, double *proj);
+
 /* BRDF-shaded preview colours per face, (B, G, R) x nF (glutcallbacks.cpp:346-445).  literal != 0 keeps the
  * reference's cosLN = face_normals(i, (int)(N.lightDir)) (column index clamped to 0..2). */
 void oracle_shade_faces(const double *V, const int *F, const double *FN, int nF, const double *eye,

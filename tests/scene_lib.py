@@ -116,3 +116,52 @@ def oracle_gather_opts(V, F, cam, led, images, W, H, flags, kappa1=0.0):
                                O.as_i(m), O.as_i(fit_face), O.as_i(fit_pixel), O.as_d(phi), O.as_d(td), O.as_d(th), O.as_d(inten))
     return dict(nfit=n, map=m, fit_face=fit_face[:n], fit_pixel=fit_pixel[:n], phi=phi[:n], thetaDash=td[:n],
                 theta=th[:n], I=inten[:, :n])
+
+
+def gl_matrices_over(V, W, H, margin=1.08):
+    """A MODELVIEW / PROJECTION / viewport triple (column-major, as glGetDoublev returns them) that looks down -z onto the
+    xy extent of V and fills a W x H viewport: the literal mapping of the reference lands inside the images with it."""
+    lo, hi = V.min(axis=0), V.max(axis=0)
+    half = 0.5 * margin * max((hi[0] - lo[0]) / W, (hi[1] - lo[1]) / H)
+    l, r, b, t = -half * W, half * W, -half * H, half * H
+    n, f = 10.0, 2000.0
+    dist = 400.0
+    # perspective frustum whose near-plane window, scaled to the object distance, covers the mesh
+    k = n / dist
+    proj = np.zeros(16)
+    proj[0] = 2 * n / ((r - l) * k); proj[5] = 2 * n / ((t - b) * k)
+    proj[10] = -(f + n) / (f - n); proj[11] = -1.0; proj[14] = -2 * f * n / (f - n)
+    mv = np.eye(4)
+    mv[0, 3], mv[1, 3], mv[2, 3] = -0.5 * (lo[0] + hi[0]), -0.5 * (lo[1] + hi[1]), -dist - hi[2]
+    mv = mv.T.ravel().copy()    # column-major
+    f32 = lambda a: a.astype(np.float32).astype(np.float64)    # GL keeps float32
+    return f32(mv), f32(proj), np.array([0, 0, W, H], dtype=np.int32)
+
+
+def oracle_gather_gl(V, F, cam, mv, proj, viewport, led, images, W, H):
+    lib = O.oracle()
+    nF, nimg = F.shape[0], len(images)
+    ptrs = (C.c_void_p * nimg)(*[im.ctypes.data for im in images])
+    m = np.empty((H, W), dtype=np.int32)
+    fit_face, fit_pixel = np.empty(nF, dtype=np.int32), np.empty(nF, dtype=np.int32)
+    phi, td, th = (np.empty((nF, nimg)) for _ in range(3))
+    inten = np.empty((3, nF, nimg))
+    cam, led = np.ascontiguousarray(cam, dtype=np.float64), np.ascontiguousarray(led, dtype=np.float64)
+    mv, proj = np.ascontiguousarray(mv, dtype=np.float64), np.ascontiguousarray(proj, dtype=np.float64)
+    vp = np.ascontiguousarray(viewport, dtype=np.int32)
+    lib.oracle_gather_gl.restype = C.c_int
+    lib.oracle_gather_gl.argtypes = [O.dptr, O.iptr, C.c_int, O.dptr, O.dptr, O.dptr, O.iptr, O.dptr, C.POINTER(C.c_void_p), C.c_int,
+                                     C.c_int, C.c_int, O.iptr, O.iptr, O.iptr, O.dptr, O.dptr, O.dptr, O.dptr]
+    n = lib.oracle_gather_gl(O.as_d(V), O.as_i(F), nF, O.as_d(cam), O.as_d(mv), O.as_d(proj), O.as_i(vp), O.as_d(led), ptrs, nimg, W, H,
+                             O.as_i(m), O.as_i(fit_face), O.as_i(fit_pixel), O.as_d(phi), O.as_d(td), O.as_d(th), O.as_d(inten))
+    return dict(nfit=n, map=m, fit_face=fit_face[:n], fit_pixel=fit_pixel[:n], phi=phi[:n], thetaDash=td[:n],
+                theta=th[:n], I=inten[:, :n])
+
+
+def oracle_reference_gl_matrices(cx, cy, win_w=1920, win_h=1080):
+    lib = O.oracle()
+    mv, pr = np.zeros(16), np.zeros(16)
+    lib.oracle_reference_gl_matrices.restype = None
+    lib.oracle_reference_gl_matrices.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int, O.dptr, O.dptr]
+    lib.oracle_reference_gl_matrices(float(cx), float(cy), int(win_w), int(win_h), O.as_d(mv), O.as_d(pr))
+    return mv, pr

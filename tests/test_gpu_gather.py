@@ -280,3 +280,30 @@ def test_dot_order_switch_and_partial_outputs(ctx, scene_inputs):
         O.set_dot_order(O.DOT_EIGEN33)
         sc.set_gather_options(0)
     sc.free()
+
+
+def test_literal_gl_projection_bit_exact(ctx):
+    """The reference's literal mapping -- gluProject through the GL matrices the caller read back (brdfdata.cpp:662-677),
+    bottom-up rows, radiance from image row H-1-y (:955) -- against the oracle's restatement of libGLU: maps, owners,
+    cosines and intensities as bytes; then back to the Tsai camera."""
+    W, H = 320, 240
+    V, F = S.height_field(60, 45, seed=11)
+    imgs, dark = S.random_images(16, W, H, seed=12)
+    mv, proj, vp = S.gl_matrices_over(V, W, H)
+    cam = S.look_at_camera((10.0, -5.0, 400.0), (0.0, 0.0, 0.0), f=400.0, cx=160.0, cy=120.0)
+    sc = ctx.scene(V, F, imgs)
+    sc.set_gl_projection(mv, proj, vp)
+    g = sc.gather(cam)
+    want = S.oracle_gather_gl(V, F, cam, mv, proj, vp, S.led_table(), imgs, W, H)
+    assert g["nfit"] == want["nfit"] > 2000
+    assert g["maps"][0].tobytes() == want["map"].tobytes()
+    assert sc.calc_pixel2surface(cam).tobytes() == want["map"].tobytes()
+    for k in ("fit_face", "fit_pixel", "phi", "thetaDash", "theta"):
+        assert np.ascontiguousarray(g[k]).tobytes() == want[k].tobytes(), k
+    assert np.ascontiguousarray(g["I"]).tobytes() == np.ascontiguousarray(want["I"]).tobytes()
+    with pytest.raises(A.BrdfGpuError):
+        sc.gather(np.stack([cam, cam]))          # one set of GL matrices = one view
+    sc.set_gl_projection()
+    w0 = S.oracle_gather(V, F, cam, S.led_table(), imgs, W, H)
+    assert sc.gather(cam)["maps"][0].tobytes() == w0["map"].tobytes()
+    sc.free()

@@ -380,3 +380,21 @@ def test_every_kind_of_sweep_gives_the_same_cost_bits(ctx, n, monkeypatch):
         assert np.isfinite(v).all(), (p0, v)
         assert all(q.tobytes() == v[0].tobytes() for q in v), (p0, [repr(float(q)) for q in v])
     s.free()
+
+
+def test_solve_equation_single_colmajor_is_the_reference_flattening():
+    """brdfdata.cpp:1008-1042: x row-major, angles through Eigen's column-major linear index -- against
+    levmar on arrays flattened the same way in numpy."""
+    rows, nimg = 700, 16
+    c, td, th, x = synth.samples(rows * nimg, seed=4321)
+    phi, tdm, thm, I = (a.reshape(rows, nimg) for a in (c, td, th, x))
+    ret, p, info = A.solve_equation_single_colmajor(phi, tdm, thm, I, 1)
+    k = np.arange(rows * nimg)
+    lin = lambda m: m[k % rows, k // rows]          # Eigen: m(k) on a column-major rows x nimg matrix
+    wret, wp, winfo = O.brdf_fit(O.oracle(), "oracle_", lin(phi), lin(tdm), lin(thm), I.ravel(), 1, O.REF_GLOBAL)
+    assert (ret >= 0) == (wret >= 0)
+    np.testing.assert_allclose(p, wp, rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(info[1], winfo[1], rtol=1e-6)
+    # the aligned order on the same data is a different (well-posed) problem with a different answer
+    ret2, p2, _ = A.solve_equation_single(c, td, th, x, 1)
+    assert not np.allclose(p, p2, rtol=1e-3)
