@@ -537,12 +537,14 @@ static int model_io(brdfgpu_ctx* ctx, const double* p, const double* angles_host
                     double* out_host, bool jac) {
     if (n <= 0) return 0;
     if (model != 0 && model != 1) return 0;  // BRDFFunc leaves hx untouched for other ids (brdfdata.cpp:978,983)
-    double *d_c = nullptr, *d_t = nullptr, *d_o = nullptr;
+    // one stream-ordered block (a maintainer may well leave this spot check inside a host loop: no cudaMalloc / cudaFree,
+    // which synchronise the device, on a per-call path)
     const size_t nb = sizeof(double) * (size_t)n, ob = jac ? nb * m : nb;
-    cudaError_t e = cudaMalloc(&d_c, nb);
-    if (e == cudaSuccess) e = cudaMalloc(&d_t, nb);
-    if (e == cudaSuccess) e = cudaMalloc(&d_o, ob);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_c, angles_host, nb, cudaMemcpyHostToDevice, ctx->stream);
+    char* block = nullptr;
+    BG_CUDA_OK(ctx, cudaMallocAsync(&block, 2 * nb + ob, ctx->stream));
+    double *d_c = reinterpret_cast<double*>(block), *d_t = reinterpret_cast<double*>(block + nb),
+           *d_o = reinterpret_cast<double*>(block + 2 * nb);
+    cudaError_t e = cudaMemcpyAsync(d_c, angles_host, nb, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(d_t, angles_host + (model == 1 ? (size_t)n : 2 * (size_t)n), nb, cudaMemcpyHostToDevice,
                             ctx->stream);
@@ -553,8 +555,8 @@ static int model_io(brdfgpu_ctx* ctx, const double* p, const double* angles_host
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, d_o, ob, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaFreeAsync(block, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_c); cudaFree(d_t); cudaFree(d_o);
     BG_CUDA_OK(ctx, e);
     return 0;
 }
