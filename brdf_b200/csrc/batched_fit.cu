@@ -348,6 +348,9 @@ __global__ void __launch_bounds__(kBatchThreads, BG_BATCH_MIN_BLOCKS(G)) k_batch
         }
     }
 
+#ifdef BG_FIT_CYCLES
+    const long long t_fit0 = clock64();
+#endif
     double p[3] = {spec.p0[0], spec.p0[1], spec.p0[2]};
     double info[10];
     const double* lb = spec.has_lb ? spec.lb : nullptr;
@@ -361,6 +364,9 @@ __global__ void __launch_bounds__(kBatchThreads, BG_BATCH_MIN_BLOCKS(G)) k_batch
         if (info_out)
             for (int i = 0; i < 10; ++i) info_out[fit * 10 + i] = info[i];
         if (ret_out) ret_out[fit] = ret;
+#ifdef BG_FIT_CYCLES  // debug variant (profiles/fit_cycles.py): SM cycles this fit took, in units of 64, instead of the return value
+        if (ret_out) ret_out[fit] = (int)((clock64() - t_fit0) >> 6);
+#endif
     }
 }
 

@@ -55,8 +55,24 @@ __global__ void __launch_bounds__(kPassThreads, 2) k_secant_fd(SampleView v, Pas
     double acc[NACC];
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
-    const long nth = (long)gridDim.x * blockDim.x;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < v.n; i += nth) {
+    // sample PAIRS: 16-byte loads of c, L, x and 16-byte stores of the three Jacobian columns and hx
+    const long nth = (long)gridDim.x * blockDim.x, npair = v.n >> 1;
+    const double2* __restrict__ c2 = reinterpret_cast<const double2*>(v.c);
+    const double2* __restrict__ l2 = reinterpret_cast<const double2*>(v.L);
+    const double2* __restrict__ x2 = reinterpret_cast<const double2*>(v.x);
+    double2 *j0 = reinterpret_cast<double2*>(st.j0), *j1 = reinterpret_cast<double2*>(st.j1),
+            *j2 = reinterpret_cast<double2*>(st.j2), *h2 = reinterpret_cast<double2*>(st.hx);
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < npair; i += nth) {
+        const double2 c = __ldg(c2 + i), L = __ldg(l2 + i), x = __ldg(x2 + i);
+        double2 hx, r0, r1, r2;
+        model_row<JAC>(q, c.x, L.x, x.x, v.traw, 2 * i, hx.x, r0.x, r1.x, r2.x);
+        model_row<JAC>(q, c.y, L.y, x.y, v.traw, 2 * i + 1, hx.y, r0.y, r1.y, r2.y);
+        j0[i] = r0; j1[i] = r1; j2[i] = r2; h2[i] = hx;
+        accumulate_normal(r0.x, r1.x, r2.x, x.x - hx.x, acc);
+        accumulate_normal(r0.y, r1.y, r2.y, x.y - hx.y, acc);
+    }
+    if ((v.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const long i = v.n - 1;
         const double c = v.c[i], L = v.L[i], x = v.x[i];
         double hx, r0, r1, r2;
         model_row<JAC>(q, c, L, x, v.traw, i, hx, r0, r1, r2);
@@ -78,21 +94,36 @@ __global__ void __launch_bounds__(kPassThreads, 2) k_secant_update(SampleView v,
     double acc[NACC];
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
-    const long nth = (long)gridDim.x * blockDim.x;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < v.n; i += nth) {
-        const double c = v.c[i], L = v.L[i], x = v.x[i];
-        const double hx_old = st.hx[i];
-        double r0 = st.j0[i], r1 = st.j1[i], r2 = st.j2[i];
-        const double hx_new = x - residual_of(qnew, c, L, x, v.traw, i);
-        // tmp = (wrk[i] - hx[i] - sum_l J[i][l] Dp[l]) / Dp_L2, summed from l = 0 as levmar does
-        double dot = __dadd_rn(__dadd_rn(__dadd_rn(0.0, __dmul_rn(r0, d0)), __dmul_rn(r1, d1)), __dmul_rn(r2, d2));
+    // one sample of the update: tmp = (f(pnew) - hx - sum_l J[l] Dp[l]) / ||Dp||^2, summed from l = 0 as levmar does
+    auto update = [&](double c, double L, double x, long i, double hx_old, double& r0, double& r1, double& r2, double& hx_new) {
+        hx_new = x - residual_of(qnew, c, L, x, v.traw, i);
+        const double dot = __dadd_rn(__dadd_rn(__dadd_rn(0.0, __dmul_rn(r0, d0)), __dmul_rn(r1, d1)), __dmul_rn(r2, d2));
         const double tmp = __ddiv_rn(__dsub_rn(__dsub_rn(hx_new, hx_old), dot), dp_l2);
         r0 = __dadd_rn(r0, __dmul_rn(tmp, d0));
         r1 = __dadd_rn(r1, __dmul_rn(tmp, d1));
         r2 = __dadd_rn(r2, __dmul_rn(tmp, d2));
+        accumulate_normal(r0, r1, r2, x - (accepted ? hx_new : hx_old), acc);
+    };
+    const long nth = (long)gridDim.x * blockDim.x, npair = v.n >> 1;
+    const double2* __restrict__ c2 = reinterpret_cast<const double2*>(v.c);
+    const double2* __restrict__ l2 = reinterpret_cast<const double2*>(v.L);
+    const double2* __restrict__ x2 = reinterpret_cast<const double2*>(v.x);
+    double2 *j0 = reinterpret_cast<double2*>(st.j0), *j1 = reinterpret_cast<double2*>(st.j1),
+            *j2 = reinterpret_cast<double2*>(st.j2), *h2 = reinterpret_cast<double2*>(st.hx);
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < npair; i += nth) {
+        const double2 c = __ldg(c2 + i), L = __ldg(l2 + i), x = __ldg(x2 + i), hx_old = h2[i];
+        double2 r0 = j0[i], r1 = j1[i], r2 = j2[i], hx_new;
+        update(c.x, L.x, x.x, 2 * i, hx_old.x, r0.x, r1.x, r2.x, hx_new.x);
+        update(c.y, L.y, x.y, 2 * i + 1, hx_old.y, r0.y, r1.y, r2.y, hx_new.y);
+        j0[i] = r0; j1[i] = r1; j2[i] = r2;
+        if (accepted) h2[i] = hx_new;
+    }
+    if ((v.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const long i = v.n - 1;
+        double r0 = st.j0[i], r1 = st.j1[i], r2 = st.j2[i], hx_new;
+        update(v.c[i], v.L[i], v.x[i], i, st.hx[i], r0, r1, r2, hx_new);
         st.j0[i] = r0; st.j1[i] = r1; st.j2[i] = r2;
         if (accepted) st.hx[i] = hx_new;
-        accumulate_normal(r0, r1, r2, x - (accepted ? hx_new : hx_old), acc);
     }
     block_reduce_to<NACC>(acc, red, partials + (long)blockIdx.x * NACC);
     last_block_finish<NACC>(partials, ticket, red, pub);
@@ -100,7 +131,7 @@ __global__ void __launch_bounds__(kPassThreads, 2) k_secant_update(SampleView v,
 
 // hx = f(p) only (accepted step right before a Jacobian rebuild needs nothing else: S1 rewrites hx)
 static int secant_blocks(const brdfgpu_ctx* ctx, long n) {
-    long want = (n + kPassThreads - 1) / kPassThreads;
+    long want = ((n >> 1) + kPassThreads - 1) / kPassThreads;
     const long cap = (long)ctx->sm_count * 2;
     if (want < 1) want = 1;
     return (int)(want < cap ? want : cap);
