@@ -66,6 +66,13 @@ struct ExactEval {
     static constexpr int KB = (BG_EXACT_PG) < G / 4 ? (BG_EXACT_PG) : G / 4;
     static constexpr int kCostBatch = KB;
     static constexpr bool kLanePgWalk = false;
+    // The engine's J^T J, J^T e, Dp, diag, pDp are identical in every lane: half-warp fits keep one copy per group in
+    // shared memory and run at 64 registers (8 CTAs per SM); measured on B200 (profiles/r02_batched.md): 113 007 x 16
+    // 30.7 -> 27.2 ms, 10^6 x 16 258 -> 219 ms.  For warp fits (64 samples) the same trade is neutral in throughput
+    // (24.4 -> 23.9 ms) and lengthens the tail of small batches (8 192 fits: 4.15 -> 4.56 ms), so they keep registers.
+    static constexpr bool kSharedState = G == 16;
+    double* s_ws;
+    __device__ __forceinline__ double* workspace() const { return s_ws; }
     static_assert(4 * KB <= G, "four summing lanes per candidate");
     double c[S], t[S], x[S];  // this lane's samples: index s * G + lane
     double lhi[S], llo[S];    // log(t) = lhi + llo as glibc's pow computes it: depends on t alone, so once per fit
@@ -279,11 +286,11 @@ struct ExactEval {
 };
 
 #ifndef BG_EXACT_MIN_BLOCKS
-#define BG_EXACT_MIN_BLOCKS 4  // 128 registers: measured best on B200 for 64- and 16-sample fits (profiles/r02_batched.md)
+#define BG_EXACT_MIN_BLOCKS(G) ((G) == 16 ? 8 : 4)  // 64 / 128 registers (profiles/r02_batched.md)
 #endif
 
 template <int G, int S>
-__global__ void __launch_bounds__(kExactThreads, BG_EXACT_MIN_BLOCKS) k_batched_fit_exact(const double* __restrict__ c, const double* __restrict__ traw,
+__global__ void __launch_bounds__(kExactThreads, BG_EXACT_MIN_BLOCKS(G)) k_batched_fit_exact(const double* __restrict__ c, const double* __restrict__ traw,
                                                                      const double* __restrict__ x, long nfit, ExactSpec spec,
                                                                      double* __restrict__ p_out, double* __restrict__ info_out,
                                                                      int* __restrict__ ret_out) {
@@ -295,9 +302,10 @@ __global__ void __launch_bounds__(kExactThreads, BG_EXACT_MIN_BLOCKS) k_batched_
     constexpr int KB = ExactEval<G, S>::KB;
     constexpr int kPerSample = KB > 4 ? KB : 4;
     ExactEval<G, S> ev;
-    double* mine = exact_smem + (size_t)(threadIdx.x / G) * ((size_t)kPerSample * nper + 5 * KB);
+    double* mine = exact_smem + (size_t)(threadIdx.x / G) * ((size_t)kPerSample * nper + 5 * KB + 24);
     ev.scratch = mine;
     ev.s_pts = mine + (size_t)kPerSample * nper;
+    ev.s_ws = ev.s_pts + 5 * KB;
     ev.nper = nper; ev.lane = lane; ev.model = spec.model; ev.delta = spec.delta;
     ev.mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
 #pragma unroll
@@ -334,7 +342,7 @@ __global__ void __launch_bounds__(kExactThreads, BG_EXACT_MIN_BLOCKS) k_batched_
 template <int G, int S>
 static int launch_exact(brdfgpu_ctx* ctx, brdfgpu_batch* b, const ExactSpec& spec) {
     constexpr int KB = ExactEval<G, S>::KB;
-    const size_t smem = sizeof(double) * ((size_t)(KB > 4 ? KB : 4) * b->nper + 5 * KB) * (kExactThreads / G);
+    const size_t smem = sizeof(double) * ((size_t)(KB > 4 ? KB : 4) * b->nper + 5 * KB + 24) * (kExactThreads / G);
     if (smem > 48 * 1024)
         BG_CUDA_OK(ctx, cudaFuncSetAttribute(k_batched_fit_exact<G, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long blocks = (b->nfit * G + kExactThreads - 1) / kExactThreads;

@@ -253,6 +253,15 @@ struct SpecJac : std::false_type {};
 template <class E>
 struct SpecJac<E, std::void_t<decltype(E::kSpecJac)>> : std::integral_constant<bool, E::kSpecJac> {};
 
+// Evaluators with `static constexpr bool kSharedState = true` lend the engine a workspace (double* workspace(), at least
+// MM * MM + 4 * MM doubles) for J^T J, J^T e, Dp, diag and pDp.  In the batched kernels every lane of a group runs the
+// engine on identical values, so that state is the same in all lanes: held once in shared memory instead of in every
+// lane's registers it frees ~42 registers per thread (occupancy is what those latency-bound kernels run on).
+template <class E, class = void>
+struct SharedState : std::false_type {};
+template <class E>
+struct SharedState<E, std::void_t<decltype(E::kSharedState)>> : std::integral_constant<bool, E::kSharedState> {};
+
 template <class Eval>
 BG_HDI double eval_cost_site(Eval& ev, int site, const double* p, bool& bad) {
     if constexpr (SpecJac<Eval>::value) return ev.cost_site(site, p, bad);
@@ -497,7 +506,13 @@ BG_HDI int lm_bc_der(Eval& ev, int m, double* p, const double* lb, const double*
                      const LmOptions& o, double* info, double* JtJ_out) {
     const double alpha = 1e-4, beta = 0.9, gamma = 0.99995, rho = 1e-8;
     const double tini = 1.0, tming = 1e-18;
-    double JtJ[MM * MM], Jte[MM], Dp[MM], diag[MM], pDp[MM];
+    constexpr bool kShared = SharedState<Eval>::value;
+    double local_state[kShared ? 1 : MM * MM + 4 * MM];
+    double* const ws = [&]() -> double* {
+        if constexpr (kShared) return ev.workspace();
+        else return local_state;
+    }();
+    double *const JtJ = ws, *const Jte = ws + MM * MM, *const Dp = Jte + MM, *const diag = Dp + MM, *const pDp = diag + MM;
     double mu = 0.0, ginf = 0.0, t = 0.0, t0, tmp;
     double e_cur, e_new = 0.0, e_init, p_L2 = 0.0, Dp_L2 = DBL_MAX, dF, dL, gTd;
     int k, stop = 0, nu = 2, gprevtaken = 0, numactive, j;
