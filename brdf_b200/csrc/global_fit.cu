@@ -1123,7 +1123,11 @@ __device__ __noinline__ void many_sweep() {
     all_reduce<kGridCostBatch>(acc, t0);
 }
 
+#if defined(BG_RUN_SWEEP_NOINLINE)
+__device__ __noinline__ void run_sweep(int kind) {
+#else
 __device__ __forceinline__ void run_sweep(int kind) {
+#endif
     switch (kind) {
         case kSweepJacForward:
             if (s_req.extra == 2) jac_sweep<kJacForward, 2>(); else if (s_req.extra) jac_sweep<kJacForward, 1>(); else jac_sweep<kJacForward, 0>();
@@ -1188,7 +1192,11 @@ struct GridEval {
         }
     }
 #endif
+#if defined(BG_POST_NOINLINE)
+    __device__ __noinline__ void post(int kind) {
+#else
     __device__ __forceinline__ void post(int kind) {
+#endif
         if (threadIdx.x == 0) {
             s_req.kind = kind;
             s_ctl[kind] += clock64() - s_ctl[7];

@@ -217,13 +217,12 @@ BG_HDI int lm_covar(const double* JtJ, double* C, double sumsq, int m, long n) {
 // ---------------------------------------------------------------------------------------------
 // box helpers (lmbc_core.c:59-88, 94-142)
 // ---------------------------------------------------------------------------------------------
+// (levmar's __MEDIAN3 with the same five comparisons, written as selects: in the lane-parallel projected-gradient walks
+// every lane projects a different candidate, and branches would diverge)
 BG_HDI double lm_median3(double lo, double v, double hi) {
-    if (lo >= v) {
-        if (hi >= lo) return lo;
-        return (hi <= v) ? v : hi;
-    }
-    if (hi >= v) return v;
-    return (hi <= lo) ? lo : hi;
+    const double below = (hi >= lo) ? lo : ((hi <= v) ? v : hi);   // lo >= v
+    const double above = (hi >= v) ? v : ((hi <= lo) ? lo : hi);   // lo <  v (or unordered)
+    return (lo >= v) ? below : above;
 }
 
 struct Box {
