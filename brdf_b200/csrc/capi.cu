@@ -83,7 +83,7 @@ extern "C" int brdfgpu_create(int device, brdfgpu_ctx** out) {
         *ctx->h_seq = 0;
         e = cudaHostGetDevicePointer(&ctx->h_seq_dev, (void*)ctx->h_seq, 0);
     }
-    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_cells, sizeof(uint4) * 2 * 160 * 16);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_cells, sizeof(uint4) * 2 * 160 * 32);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_fitio, sizeof(GlobalFitOut));
     if (e == cudaSuccess) e = cudaHostAlloc(&ctx->h_fitio, sizeof(GlobalFitOut), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->h_counts, sizeof(int) * kCountStagingInts, cudaHostAllocDefault);

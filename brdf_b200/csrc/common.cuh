@@ -16,7 +16,7 @@ constexpr int kPassThreads = 256;    // threads per CTA of the streaming passes
 constexpr int kMaxPassBlocks = 2048; // upper bound on CTAs of one pass (partials buffer)
 constexpr int kResultDoubles = 16;   // >= NACC
 constexpr int kMaxRanks = 8;         // GPUs of one NVSwitch domain
-constexpr int kPeerCellsPerRank = 16;  // >= NACC flagged cells per (parity, rank)
+constexpr int kPeerCellsPerRank = 32;  // flagged cells per (parity, rank): the widest sweep carries 32 sums
 constexpr int kCountStagingInts = 1024;  // pinned staging for the per-view fit counts of a gather
 
 // Exchange buffer of the fused in-kernel all-reduce: [2 parities][kMaxRanks][kPeerCellsPerRank]
@@ -53,7 +53,7 @@ struct brdfgpu_ctx {
     void* d_fitio = nullptr;
     void* h_fitio = nullptr;  // pinned
     int* h_counts = nullptr;      // pinned, kCountStagingInts: per-view fit counts of the running gather
-    uint4* d_cells = nullptr;     // flagged exchange cells of the persistent fit: 2 x kMaxPersistBlocks x 16
+    uint4* d_cells = nullptr;     // flagged exchange cells of the persistent fit: 2 parities x kMaxPersistBlocks x NSUM (32)
     int tma_mode = 0;             // 0: not probed, 1: automatic, 2: never, 3: always (BRDFGPU_TMA)
     long persist_smem_max = 0;    // dynamic shared memory one CTA of the persistent fit may use (0: not probed, <0: unusable)
     // what the last global fit did: sweeps with a Jacobian, cost-only sweeps, trial points evaluated

@@ -685,8 +685,13 @@ struct HostEval {
 #endif
 constexpr int kPersistThreads = BG_PERSIST_THREADS;  // 512: 16 warps, <= 128 registers per thread
 constexpr int kMaxPersistBlocks = 160;  // >= SM count (148 on B200)
-constexpr int kGridCostBatch = 8;       // trial points per cost_many() sweep (<= NACC)
-constexpr int NSUM = NACC + 2;          // sums of the widest sweep: a Jacobian at one point + the cost at two others
+constexpr int kGridCostBatch = 8;       // trial points per cost_many() sweep of the sequential walk (<= NACC)
+// The lane-parallel projected-gradient walk takes up to 32 candidates per sweep when the whole shard is on chip
+// (one candidate per lane of the control warp).  levmar's futile walks try 393 step lengths: at 8 per sweep that is
+// 52 sweeps -- 44 % of all sweeps of a configs[1] fit -- each paying ~15 k cycles of exchange + control on top of its
+// arithmetic; widths 1, 2, 4, 8, 16, 32, 32 ... need 17.  Candidates past the deciding one are discarded uncounted.
+constexpr int kWalkMaxBatch = 32;
+constexpr int NSUM = kWalkMaxBatch;     // sums of the widest sweep (>= NACC + 2: a Jacobian at one point + the cost at two others)
 constexpr long long kSpinCycles = 20000000000LL;  // ~10 s at 2 GHz, then the fit is abandoned (ranks may enter seconds apart on a cold box)
 
 // A cell is two 64-bit words {value.lo | tag << 32, value.hi | tag << 32}; each word is one scalar
@@ -731,12 +736,12 @@ __device__ __forceinline__ double wait_cell(const uint4* src, unsigned tag, int*
 __device__ __forceinline__ unsigned next_tag(unsigned e) { return e + 1u ? e + 1u : 1u; }  // never 0: buffers start zeroed
 
 // What the control warp asks the CTA to do next (shared memory).
-enum SweepKind { kQuit = 0, kSweepJacForward, kSweepJacCentral, kSweepJacAnalytic, kSweepCost, kSweepMany, kSweepBad };
+enum SweepKind { kQuit = 0, kSweepJacForward, kSweepJacCentral, kSweepJacAnalytic, kSweepCost, kSweepMany, kSweepBad, kSweepMany16, kSweepMany32 };
 struct SweepRequest {
     int kind, cnt;  // cnt: trial points of kSweepMany / index of the point of kSweepBad
     int extra;      // Jacobian sweeps: also ||x - f||^2 at pts[0] (.. pts[extra-1]), sums number NACC (, NACC+1)
     PassParams q;   // Jacobian sweeps
-    CostPoint pts[kGridCostBatch];
+    CostPoint pts[kWalkMaxBatch];
 };
 
 // Everything a sweep needs, written once at kernel start.  Shared memory on purpose: the sweeps are
@@ -749,7 +754,7 @@ struct FitContext {
     int res_pairs;        // pairs held by this CTA
     long res_first;       // global index of its first pair
     long stream_first;    // pairs >= stream_first are streamed from global memory by the whole grid
-    uint4* cells;         // [2 parities][gridDim.x][NSUM]
+    uint4* cells;         // [2 parities][kMaxPersistBlocks][NSUM], cell_index()
     PeerView peer;        // nranks == 1: no cross-GPU step
     int* abort_flag;      // global
 };
@@ -759,8 +764,6 @@ __shared__ SweepRequest s_req;
 __shared__ unsigned s_epoch, s_peer_epoch;  // tags of the last grid / peer exchange (uniform in the CTA)
 __shared__ double s_red[(kPersistThreads / 32) * NSUM];
 __shared__ double s_res[NSUM];
-constexpr int kStagePitch = kMaxPersistBlocks + 1;  // quantity-major with an odd pitch: conflict-free both ways
-__shared__ double s_stage[kStagePitch * NSUM];
 __shared__ double s_pstage[kMaxRanks * NSUM];
 __shared__ double s_cand[kGridCostBatch * 3];  // candidate points of the projected-gradient walk
 __shared__ double s_cand_cost[kGridCostBatch];
@@ -779,7 +782,7 @@ __shared__ double s_hint[3];         // first projected-gradient candidate annou
 __shared__ double s_ahead[6 + 4];    // announced before the trial: the lambda = 0.1 probe, the walk's first candidate;
                                      // then the probe's evaluated point and ||e||^2 (GridEval::probe_hint, candidate_hint)
 __shared__ long long s_cyc[6];  // thread 0: cycles in sweeps, exchanges, and the 4 exchange phases
-__shared__ long long s_ctl[8];  // thread 0: control-code cycles by the kind of request they led to; [7] = time of the last exchange end
+__shared__ long long s_ctl[8];  // thread 0: control-code cycles by the kind of request they led to (wide batches count as kSweepMany); [7] = time of the last exchange end
 // TMA ring of the streamed part (sample sets beyond on-chip residency): 3 stages x 48 KB
 using PersistRing = TileRing<kPersistThreads, 3>;
 __shared__ PersistRing s_ring;
@@ -816,13 +819,16 @@ __device__ __forceinline__ void peer_exchange() {
 // The sums of all CTAs (and all ranks) in s_res[0..NV), identical bits everywhere.  Latency is
 // everything here (one exchange per evaluation): every step is written so that the NV quantities
 // advance together instead of one after the other.
+//
+// Stage 1 (warp_sums_to_smem): warp butterflies, step-major; lane 0 of every warp leaves its NV sums in s_red.
+// Stage 2 (grid_exchange): 16 lanes per quantity add the 16 warps and publish the CTA's sum as a flagged cell; then
+// all threads collect the cells of ALL CTAs into shared memory (all loads go out together, late ones are re-polled)
+// and one warp per quantity adds them (lane l takes CTAs l, l + 32, ... in ascending order, then a butterfly) -- a
+// fixed order, so every CTA (and every rank, below) holds identical bits.  16 quantities per round: the 32 sums of
+// the widest sweep take two.
 template <int NV>
-__device__ __forceinline__ void all_reduce(const double* acc, long long t_sweep_start) {
-    const long long t_in = clock64();
-    constexpr int kWarps = kPersistThreads / 32;
+__device__ __forceinline__ void warp_sums_to_smem(const double* acc, int first = 0, int stride = NV) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int grid = gridDim.x;
-    // 1. warp butterflies, step-major
     double s[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k) s[k] = acc[k];
@@ -833,51 +839,71 @@ __device__ __forceinline__ void all_reduce(const double* acc, long long t_sweep_
     }
     if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < NV; ++k) s_red[warp * NV + k] = s[k];
+        for (int k = 0; k < NV; ++k) s_red[warp * stride + first + k] = s[k];
     }
+}
+
+// cell of quantity k of CTA b.  CTA-major on purpose: a CTA's cells share lines with at most one neighbour.  With
+// the quantity-major order (8 CTAs writing into every 128-byte line while 148 poll it) an exchange took 2x longer.
+__device__ __forceinline__ int cell_index(int b, int k) { return b * NSUM + k; }
+constexpr int kStageQuantities = 16;
+constexpr int kStagePitch = kMaxPersistBlocks + 1;  // quantity-major with an odd pitch: conflict-free both ways
+__shared__ double s_stage[kStagePitch * kStageQuantities];
+// Not inlined: with its own register allocation the cells in flight do not push the sweeps' accumulators into local
+// memory (inlined into the Jacobian sweeps it cost them up to 1.3 KB of spills and ~3 k cycles per sweep).
+template <int NV>
+__device__ __noinline__ void grid_exchange(long long t_sweep_start, long long t_in) {
+    static_assert(NV <= kStageQuantities || NV % kStageQuantities == 0, "whole rounds only");
+    constexpr int kWarps = kPersistThreads / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grid = gridDim.x;
     __syncthreads();
     const long long t_a = clock64();
-    // 2. across the 16 warps: 16 lanes per quantity, 4 butterfly steps; publish
+    // across the 16 warps: 16 lanes per quantity, 4 butterfly steps; publish
     const unsigned tag = next_tag(s_epoch);
-    uint4* base = s_ctx.cells + (long)(tag & 1u) * grid * NSUM;
+    uint4* base = s_ctx.cells + (long)(tag & 1u) * NSUM * kMaxPersistBlocks;
     if (threadIdx.x < ((NV * kWarps + 31) & ~31)) {
         const int k = threadIdx.x / kWarps, w = threadIdx.x % kWarps;
         double t = (k < NV) ? s_red[w * NV + k] : 0.0;
 #pragma unroll
         for (int off = kWarps / 2; off; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off, kWarps);
-        if (k < NV && w == 0) store_cell<false>(base + (long)blockIdx.x * NSUM + k, t, tag);
+        if (k < NV && w == 0) store_cell<false>(base + cell_index(blockIdx.x, k), t, tag);
     }
     const long long t_b = clock64();
-    // 3. every thread collects up to 4 cells: all loads go out together, late ones are re-polled
-    constexpr int kPerThread = (kMaxPersistBlocks * NSUM + kPersistThreads - 1) / kPersistThreads;
-    const int total = grid * NV;
-    Cell c[kPerThread];
+    // every thread collects a few cells (consecutive threads = consecutive quantities of one CTA): all loads go out
+    // together, late ones are re-polled; then one warp per quantity adds the staged values in ascending CTA order
+    for (int k0 = 0; k0 < NV; k0 += kStageQuantities) {
+        constexpr int kRound = NV < kStageQuantities ? NV : kStageQuantities;
+        constexpr int kPerThread = (kMaxPersistBlocks * kRound + kPersistThreads - 1) / kPersistThreads;
+        Cell c[kPerThread];
 #pragma unroll
-    for (int j = 0; j < kPerThread; ++j) {
-        const int idx = threadIdx.x + j * kPersistThreads;
-        const int b = idx / NV, k = idx - b * NV;
-        if (idx < total) c[j] = load_cell<false>(base + (long)b * NSUM + k);
-    }
-#pragma unroll
-    for (int j = 0; j < kPerThread; ++j) {
-        const int idx = threadIdx.x + j * kPersistThreads;
-        if (idx < total) {
-            const int b = idx / NV, k = idx - b * NV;
-            s_stage[k * kStagePitch + b] = c[j].has(tag) ? c[j].value() : wait_cell<false>(base + (long)b * NSUM + k, tag, s_ctx.abort_flag);
+        for (int j = 0; j < kPerThread; ++j) {
+            const int idx = threadIdx.x + j * kPersistThreads;
+            const int b = idx / kRound, k = idx - b * kRound;
+            if (k < kRound && b < grid) c[j] = load_cell<false>(base + cell_index(b, k0 + k));
         }
-    }
-    __syncthreads();
-    const long long t_c = clock64();
-    // 4. fixed order: one warp per quantity, lanes stride the CTAs, butterfly
-    for (int k = warp; k < NV; k += kWarps) {
-        double t = 0.0;
-        for (int b = lane; b < grid; b += 32) t += s_stage[k * kStagePitch + b];
 #pragma unroll
-        for (int off = 16; off; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
-        if (lane == 0) s_res[k] = t;
+        for (int j = 0; j < kPerThread; ++j) {
+            const int idx = threadIdx.x + j * kPersistThreads;
+            const int b = idx / kRound, k = idx - b * kRound;
+            if (k < kRound && b < grid) {
+                s_stage[k * kStagePitch + b] =
+                    c[j].has(tag) ? c[j].value() : wait_cell<false>(base + cell_index(b, k0 + k), tag, s_ctx.abort_flag);
+            }
+        }
+        __syncthreads();
+        for (int k = warp; k < kRound; k += kWarps) {
+            double t = 0.0;
+            for (int b = lane; b < grid; b += 32) t += s_stage[k * kStagePitch + b];
+#pragma unroll
+            for (int off = 16; off; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+            if (lane == 0) s_res[k0 + k] = t;
+        }
+        if (k0 + kStageQuantities < NV) __syncthreads();
     }
-    if (threadIdx.x == 0) s_epoch = tag;  // everybody read the old value before the barrier above
-    __syncthreads();
+    const long long t_c = clock64();
+    __syncthreads();  // (everybody read s_epoch before this barrier)
+    if (threadIdx.x == 0) s_epoch = tag;
     if (s_ctx.peer.nranks > 1) peer_exchange<NV>();
     if (threadIdx.x == 0) {
         const long long t_d = clock64();
@@ -885,6 +911,13 @@ __device__ __forceinline__ void all_reduce(const double* acc, long long t_sweep_
         s_cyc[2] += t_a - t_in; s_cyc[3] += t_b - t_a; s_cyc[4] += t_c - t_b; s_cyc[5] += t_d - t_c;
         s_ctl[7] = t_d;
     }
+}
+
+template <int NV>
+__device__ __forceinline__ void all_reduce(const double* acc, long long t_sweep_start) {
+    const long long t_in = clock64();
+    warp_sums_to_smem<NV>(acc);
+    grid_exchange<NV>(t_sweep_start, t_in);
 }
 
 // ---- sweeps (all threads of the CTA) ----
@@ -1126,6 +1159,33 @@ __device__ __noinline__ void many_sweep() {
 #if defined(BG_RUN_SWEEP_NOINLINE)
 __device__ __noinline__ void run_sweep(int kind) {
 #else
+// up to 16 / 32 trial points in ONE sweep + ONE exchange, whole shard on chip (the lane-parallel walk's wide batches).
+// The candidates are taken two at a time and each pair's sums are warp-reduced at once, so no thread ever holds 32
+// accumulators; per candidate the arithmetic -- and with it the value -- is exactly many_sweep's and cost_sweep's.
+template <int NV>
+__device__ __noinline__ void many_sweep_wide() {
+    const long long t0 = clock64();
+    const int cnt = s_req.cnt;
+    const unsigned sc = s_ctx.sc, sl = s_ctx.sl, sx = s_ctx.sx;
+    const int res_pairs = s_ctx.res_pairs;
+    const long res_first = s_ctx.res_first;
+    const SampleView v = s_ctx.v;
+    const bool odd_tail = (v.n & 1) && blockIdx.x == 0 && threadIdx.x == 0;
+#pragma unroll 1
+    for (int k = 0; k < NV; k += 2) {
+        double a[2] = {0.0, 0.0};
+        if (k + 1 < cnt) resident_cost_x2(s_req.pts[k], s_req.pts[k + 1], sc, sl, sx, res_pairs, res_first, v.traw, &a[0], &a[1]);
+        else if (k < cnt) a[0] = resident_cost(s_req.pts[k], sc, sl, sx, res_pairs, res_first, v.traw);
+        if (odd_tail) {
+            const long j = v.n - 1;
+            if (k < cnt) accumulate_cost(s_req.pts[k], v.c[j], v.L[j], v.x[j], v.traw, j, &a[0]);
+            if (k + 1 < cnt) accumulate_cost(s_req.pts[k + 1], v.c[j], v.L[j], v.x[j], v.traw, j, &a[1]);
+        }
+        warp_sums_to_smem<2>(a, k, NV);
+    }
+    grid_exchange<NV>(t0, clock64());
+}
+
 __device__ __forceinline__ void run_sweep(int kind) {
 #endif
     switch (kind) {
@@ -1140,6 +1200,8 @@ __device__ __forceinline__ void run_sweep(int kind) {
             break;
         case kSweepCost: cost_sweep(); break;
         case kSweepMany: many_sweep(); break;
+        case kSweepMany16: many_sweep_wide<16>(); break;
+        case kSweepMany32: many_sweep_wide<32>(); break;
         default: bad_sweep(); break;
     }
 }
@@ -1199,7 +1261,7 @@ struct GridEval {
 #endif
         if (threadIdx.x == 0) {
             s_req.kind = kind;
-            s_ctl[kind] += clock64() - s_ctl[7];
+            s_ctl[kind >= kSweepMany16 ? (int)kSweepMany : kind] += clock64() - s_ctl[7];
         }
         __syncthreads();
         if (kind != kQuit) run_sweep(kind);
@@ -1429,9 +1491,11 @@ struct GridEval {
         const int lane = threadIdx.x;  // control warp: 0..31
         const Box box{lb, ub};
         BG_TICK(6);
-        // walks tend to repeat: start with the batch width the last walk needed (1, 2, 4 or 8 candidates)
+        // wide batches need the whole shard on chip (many_sweep_wide); a streamed shard keeps 8 per sweep
+        const int wmax = (s_ctx.stream_first < (s_ctx.v.n >> 1)) ? kGridCostBatch : kWalkMaxBatch;
+        // walks tend to repeat: start with the batch width the last walk needed (1, 2, 4 ... candidates)
         int width = 1;
-        if (width_on) while (width < pg_last && width < kGridCostBatch) width *= 2;
+        if (width_on) while (width < pg_last && width < wmax) width *= 2;
         bool first_batch = true;
         int consumed = 0;
         while (t > tming) {
@@ -1464,7 +1528,7 @@ struct GridEval {
                 cost_points += nc;
             } else {
                 if (lane == 0) s_req.cnt = nc;
-                post(kSweepMany);
+                post(nc <= kGridCostBatch ? kSweepMany : nc <= 16 ? kSweepMany16 : kSweepMany32);
                 ++cost_passes;
                 cost_points += nc;
             }
@@ -1512,7 +1576,7 @@ struct GridEval {
                 t = t_src * beta;
             }
             first_batch = false;
-            width = (2 * width < kGridCostBatch) ? 2 * width : kGridCostBatch;
+            width = (2 * width < wmax) ? 2 * width : wmax;
         }
         sp_pg = false;
         pg_last = consumed;
@@ -1793,7 +1857,7 @@ int global_fit(brdfgpu_ctx* ctx, const brdfgpu_samples* s, double* p, int m, con
         uint4* cells = ctx->d_cells;
         long resident_pairs = plan.resident_pairs;
         // tags restart at 1 every launch: clear the cells this grid will use and the abort flag
-        BG_CUDA_OK(ctx, cudaMemsetAsync(cells, 0, sizeof(uint4) * 2 * (size_t)plan.grid * NSUM, ctx->stream));
+        BG_CUDA_OK(ctx, cudaMemsetAsync(cells, 0, sizeof(uint4) * 2 * (size_t)kMaxPersistBlocks * NSUM, ctx->stream));
         BG_CUDA_OK(ctx, cudaMemsetAsync(d_out, 0, sizeof(GlobalFitOut), ctx->stream));
         PeerView peer;
         memset(&peer, 0, sizeof(peer));

@@ -27,6 +27,7 @@ ctx.synchronize()
 st = ctx.fit_stats()
 sweeps = st["jac_passes"] + st["cost_passes"]
 ctl = st["cyc_total"] - st["cyc_sweep"] - st["cyc_exchange"]
-print("n=%d: %.4f ms per fit, %d iterations, %d sweeps; cycles/sweep: sweep %.0f exchange %.0f control %.0f; p=%s cost=%.15g nfev=%d" % (
-    n, e0.elapsed_time(e1) / 100, info[5], sweeps, st["cyc_sweep"] / sweeps, st["cyc_exchange"] / sweeps, ctl / sweeps, p, info[1], info[7]))
+print("n=%d: %.4f ms per fit, %d iterations, %d sweeps (%d points); cycles/sweep: sweep %.0f exchange %.0f %s control %.0f; p=%s cost=%.15g nfev=%d" % (
+    n, e0.elapsed_time(e1) / 100, info[5], sweeps, st["cost_points"], st["cyc_sweep"] / sweeps, st["cyc_exchange"] / sweeps,
+    [int(v / sweeps) for v in st["cyc_exchange_phases"]], ctl / sweeps, p, info[1], info[7]))
 ctx.close()
