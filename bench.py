@@ -439,7 +439,9 @@ def hbm_kernels(rig, n=100_000_000):
         res[name] = {"launch_ms": ms, "achieved": gbs, "frac": gbs / peak, "sample_visits_per_s": n / (ms * 1e-3)}
     k2 = res["k_normal_eq_tma<forward>"]
     out = {"bound": "hbm", "kernel": "k_normal_eq_tma<forward>", "samples": n, "achieved": k2["achieved"], "peak": peak,
-           "unit": "GB/s", "frac": k2["frac"], "traffic": 2.4048e9, "traffic_source": "ncu --set full, profiles/r01_ncu_tables.md",
+           "unit": "GB/s", "frac": k2["frac"], "traffic": NCU.get("k_normal_eq_tma<forward>", {}).get("dram_bytes", 2.4048e9),
+           "traffic_source": "ncu --set full, " + NCU.get("k_normal_eq_tma<forward>", {}).get("source", "profiles/r01_ncu_tables.md"),
+           "fp64_pipe_pct": NCU.get("k_normal_eq_tma<forward>", {}).get("fp64_pipe_pct"),
            "algorithmic_bytes_per_launch": 24.0 * n, "launch_ms": k2["launch_ms"], "k_cost": res["k_cost"],
            "note": "inputs 2.4 GB >> 126 MB L2, 10 back-to-back launches after 3 warm-ups; BASELINE.json north_star's "
                    ">= 60 % of HBM target is stated for this regime"}
@@ -713,8 +715,8 @@ def run_gpu_arm(args):
                 "traffic": ncu.get("dram_bytes"), "traffic_source": "ncu --set full, " + ncu.get("source", "?"),
                 "peak_source": rig.peak_src, "algorithmic_bytes_per_launch": swept, "launch_ms": ms,
                 "sweeps_per_launch": h["sweeps"], "levmar_counted_passes_per_launch": h["levmar_passes"],
-                "binding_limit": "fp64 pipe inside the sweeps + exchange/control latency between them (the shard is in shared memory: "
-                                 "HBM is not the bound at this size)",
+                "binding_limit": "fp64 latency inside the sweeps (4 warps per scheduler, ptxas serialises the chains of a trip) + "
+                                 "exchange/control latency between them (the shard is in shared memory: HBM is not the bound at this size)",
                 "fp64_pipe_pct": ncu.get("fp64_pipe_pct"), "issue_slots_pct": ncu.get("issue_slots_pct"),
                 "cycles": {"sweeps": st["cyc_sweep"], "exchange": st["cyc_exchange"], "total": st["cyc_total"]},
                 "note": "achieved = 24 B x samples x PHYSICAL sweeps over the samples / kernel time: the rate at which the kernel walks its "

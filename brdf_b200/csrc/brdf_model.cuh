@@ -126,6 +126,67 @@ __device__ __forceinline__ double exp_core(double y) {
     return __hiloint2double(__double2hiint(v) + (k << 20), __double2loint(v));
 }
 
+#ifdef BG_EXP_TABLE
+// Table-driven variant (global_fit.cu): exp(y) = 2^k T[i] (1 + p(r)) with 64 k + i = round(y 64/ln2), T[i] = 2^(i/64)
+// from shared memory and a degree-5 p on |r| <= ln2/128 -- 10 fp64 instructions per exponential instead of 14 and a
+// dependency chain of 8 instead of 15, max relative error 2.1e-16 (1.9 ulp, against 4 ulp of the polynomial; exact
+// emulation in profiles/tools/make_exp_table.py, which also generated the constants).  The table is replicated so that
+// lane l reads copy l mod 16 whose entries all sit in bank pair l mod 16: an LDS.64 of a warp is conflict-free whatever
+// the 32 indices are.  Every kernel of such a translation unit calls exp_table_load() first.
+// Measured (profiles/r02_persist_control.md): the resident sweeps of the persistent fit take the same ~2.7 k cycles
+// per trial point with either variant -- ptxas runs the chains of a trip nearly one after the other, so the sweeps
+// wait on FP64 latency (13 cycles per dependent step, 4 warps per scheduler), not on the FP64 issue rate this saves.
+#include "exp_table.inc"
+#ifndef BG_EXP_TABLE_COPIES
+#define BG_EXP_TABLE_COPIES 16
+#endif
+constexpr int kExpTabCopies = BG_EXP_TABLE_COPIES;
+__shared__ unsigned long long s_exp_tab[64 * kExpTabCopies];
+
+__device__ __forceinline__ void exp_table_load() {
+    for (int i = threadIdx.x; i < 64 * kExpTabCopies; i += blockDim.x) s_exp_tab[i] = kExp2TabBiased[i / kExpTabCopies];
+    __syncthreads();
+}
+#define BG_EXP_TABLE_LOAD() exp_table_load()
+
+// N independent exponentials, step-major (see the polynomial variant below).  The integer side is spelled out: and +
+// multiply-add for the address of the entry, ONE multiply-add for the scaling by 2^k (the table holds 2^(i/64) with
+// i << 14 taken off the high word, so that adding j << 14 = (64 k + i) << 14 leaves k << 20 on top of the true entry),
+// and the result falls out of the last FMA.
+template <int N>
+__device__ __forceinline__ void exp_core_n(const double* y, double* out) {
+    const double magic = kExpTabRed[1];
+    const unsigned lane_bytes = (unsigned)__cvta_generic_to_shared(s_exp_tab) + ((threadIdx.x & (kExpTabCopies - 1)) << 3);
+    double t[N], r[N], T[N], q0[N], q1[N], r2[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) t[k] = __fma_rn(y[k], kExpTabRed[0], magic);
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const unsigned j = (unsigned)__double2loint(t[k]);
+        unsigned lo, hi, addr;
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(addr) : "r"(j & 63u), "n"(8 * kExpTabCopies), "r"(lane_bytes));  // (kept as ONE IMAD)
+        asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(addr));
+        T[k] = __hiloint2double((int)(hi + j * 0x4000u), (int)lo);  // 2^k T[i]
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) r[k] = __fma_rn(t[k] - magic, kExpTabRed[2], y[k]);
+#pragma unroll
+    for (int k = 0; k < N; ++k) r[k] = __fma_rn(t[k] - magic, kExpTabRed[3], r[k]);
+#pragma unroll
+    for (int k = 0; k < N; ++k) q1[k] = __fma_rn(kExpTabPoly[0], r[k], kExpTabPoly[1]);
+#pragma unroll
+    for (int k = 0; k < N; ++k) q0[k] = __fma_rn(kExpTabPoly[2], r[k], kExpTabPoly[3]);
+#pragma unroll
+    for (int k = 0; k < N; ++k) r2[k] = r[k] * r[k];
+#pragma unroll
+    for (int k = 0; k < N; ++k) q0[k] = __fma_rn(q1[k], r2[k], q0[k]);
+#pragma unroll
+    for (int k = 0; k < N; ++k) r[k] = __fma_rn(q0[k], r2[k], r[k]);
+#pragma unroll
+    for (int k = 0; k < N; ++k) out[k] = __fma_rn(T[k], r[k], T[k]);
+}
+#else
+#define BG_EXP_TABLE_LOAD() ((void)0)
 // N independent exponentials, written step-major (every step for all N before the next step) so the
 // instruction stream interleaves N dependency chains: one warp then keeps the FP64 pipe busy by
 // itself instead of relying on other warps to cover the DFMA latency.
@@ -152,6 +213,8 @@ __device__ __forceinline__ void exp_core_n(const double* y, double* out) {
     for (int k = 0; k < N; ++k) out[k] = __hiloint2double(__double2hiint(v[k]) + (__double2loint(t[k]) << 20), __double2loint(v[k]));
 }
 
+#endif  // BG_EXP_TABLE
+
 // t**n / ln t with libm semantics through the raw cosine.  Deliberately NOT inlined and with
 // by-value arguments only: the careful path is rare and pow() is ~300 instructions per site.
 static __device__ __noinline__ double pow_careful(double traw, double n) { return pow(traw, n); }
@@ -176,10 +239,12 @@ __device__ __forceinline__ void accumulate_normal(double j0, double j1, double j
 }
 
 // Does an exponential with argument y = exponent * log(t) need libm semantics?  exp_core is valid for
-// |y| <= 700; everything else -- results that under/overflow, the NaN flag of t < 0, t == 0 or inf
+// |y| < 700; everything else -- results that under/overflow, the NaN flag of t < 0, t == 0 or inf
 // (y = +-inf, or NaN against a zero exponent), non-finite exponents -- goes through pow().
 // A zero exponent with an ordinary t gives y = 0 and exp_core(0) == 1 == pow(t, 0) exactly.
-__device__ __forceinline__ bool needs_care(double y) { return !(fabs(y) <= kFastExpLimit); }
+// (decided on the high word -- |y| >= 700, Inf and NaN all have one at or above 700.0's -- so the test runs on the
+// integer pipe and leaves the FP64 pipe to the arithmetic)
+__device__ __forceinline__ bool needs_care(double y) { return (unsigned)(__double2hiint(y) & 0x7fffffff) >= 0x4085e000u; }
 
 // model value on the careful path: products and sum rounded separately, as the reference callback
 // compiled without contraction does.  One spelling for every pass, so the residual of a sample at a

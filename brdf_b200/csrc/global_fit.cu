@@ -27,6 +27,9 @@
 #include <cstring>
 #include <vector>
 
+#ifndef BG_EXP_POLY  // (make EXTRA=-DBG_EXP_POLY: the polynomial exponential, for comparisons)
+#define BG_EXP_TABLE 1  // every kernel below that evaluates the model calls exp_table_load() first
+#endif
 #include "brdf_model.cuh"
 #include "common.cuh"
 #include "reduce.cuh"
@@ -222,6 +225,7 @@ template <int JAC>
 __global__ void __launch_bounds__(kTileThreads, 2) k_normal_eq_tma(SampleView v, PassParams q, double* partials,
                                                                    unsigned* ticket, Publish pub) {
     __shared__ double red[(kTileThreads / 32) * NACC];
+    BG_EXP_TABLE_LOAD();
     double acc[NACC];
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
@@ -245,6 +249,7 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_normal_eq_tma(SampleView v,
 __global__ void __launch_bounds__(kTileThreads, 2) k_cost_tma(SampleView v, PassParams q, double* partials, unsigned* ticket,
                                                               Publish pub) {
     __shared__ double red[(kTileThreads / 32)];
+    BG_EXP_TABLE_LOAD();
     double a0 = 0.0, a1 = 0.0;
     stream_tiles(v, [&](double2 c0, double2 l0, double2 x0, long i0, double2 c1, double2 l1, double2 x1, long i1, int valid) {
         if (valid == 2) accumulate_cost_2pairs(q, c0, l0, x0, i0, c1, l1, x1, i1, v.traw, &a0, &a1);
@@ -263,6 +268,7 @@ template <int JAC>
 __global__ void __launch_bounds__(kPassThreads, 2) k_normal_eq(SampleView v, PassParams q, double* partials,
                                                              unsigned* ticket, Publish pub) {
     __shared__ double red[(kPassThreads / 32) * NACC];
+    BG_EXP_TABLE_LOAD();
     double acc[NACC];
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
@@ -275,6 +281,7 @@ template <bool COUNT_BAD>
 __global__ void __launch_bounds__(kPassThreads, 4) k_cost(SampleView v, PassParams q, double* partials, unsigned* ticket,
                                                         Publish pub) {
     __shared__ double red[(kPassThreads / 32)];
+    BG_EXP_TABLE_LOAD();
     double acc[1] = {0.0};
     if (COUNT_BAD) stream_count_bad(v, q, (long)blockIdx.x * blockDim.x + threadIdx.x, (long)gridDim.x * blockDim.x, acc);
     else stream_cost(v, q, 0, (long)blockIdx.x * blockDim.x + threadIdx.x, (long)gridDim.x * blockDim.x, acc);
@@ -284,6 +291,7 @@ __global__ void __launch_bounds__(kPassThreads, 4) k_cost(SampleView v, PassPara
 
 // e_i = x_i - f(p)_i, the vector levmar keeps in `e` (lmbc_core.c:526)
 __global__ void k_residuals(SampleView v, PassParams q, double* e) {
+    BG_EXP_TABLE_LOAD();
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < v.n; i += (long)gridDim.x * blockDim.x) {
         e[i] = residual_of(q, v.c[i], v.L[i], v.x[i], v.traw, i);
     }
@@ -683,7 +691,7 @@ struct HostEval {
 #ifndef BG_PERSIST_THREADS
 #define BG_PERSIST_THREADS 512
 #endif
-constexpr int kPersistThreads = BG_PERSIST_THREADS;  // 512: 16 warps, <= 128 registers per thread
+constexpr int kPersistThreads = BG_PERSIST_THREADS;  // 512 WORKER threads (16 warps) + one control warp: <= 120 registers per thread
 constexpr int kMaxPersistBlocks = 160;  // >= SM count (148 on B200)
 constexpr int kGridCostBatch = 8;       // trial points per cost_many() sweep of the sequential walk (<= NACC)
 // The lane-parallel projected-gradient walk takes up to 32 candidates per sweep when the whole shard is on chip
@@ -789,6 +797,20 @@ __shared__ PersistRing s_ring;
 __shared__ __align__(8) unsigned long long s_ring_bars[2 * 3];
 __shared__ long s_ring_seq;  // tiles that went through the ring so far (uniform in the CTA)
 
+// Roles.  Threads 0..511 (16 warps) are the WORKERS: they own the samples and run the sweeps and the exchanges; warp
+// 16 is the CONTROL warp running lm_engine.cuh and never enters a sweep.  Kept apart, the control code no longer
+// carries the sweeps' code and registers through every evaluation site of the engine (kernel spills 4.0 -> 0.9 KB,
+// control cycles per sweep 12.5 k -> 9.5 k at configs[1]); 17 warps are allocated like 20, which caps the kernel at
+// 96 registers per thread (the Jacobian sweeps pay ~1 k cycles for it).
+// worker_sync(): the 512 workers (named barrier 1); __syncthreads(): all 544 threads, the two hand-overs of a sweep.
+#ifndef BG_SWEEP_FN
+#define BG_SWEEP_FN __noinline__
+#endif
+constexpr int kControlWarpThreads = 32;
+constexpr int kPersistBlockThreads = kPersistThreads + kControlWarpThreads;
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kPersistThreads) : "memory"); }
+__device__ __forceinline__ int ctl_lane() { return (int)threadIdx.x - kPersistThreads; }
+
 // Cross-GPU step, fused into the same kernel: CTA 0 of every rank stores its rank's sums as flagged
 // cells into slot [parity][rank] of EVERY rank's exchange buffer (peer stores over NVLink /
 // NVSwitch); every CTA polls its own rank's buffer until all slots carry the tag and adds them in
@@ -806,14 +828,14 @@ __device__ __forceinline__ void peer_exchange() {
         s_pstage[r * NV + k] =
             wait_cell<true>(s_ctx.peer.local + ((long)(par * kMaxRanks + r) * kPeerCellsPerRank + k), tag, s_ctx.abort_flag);
     }
-    __syncthreads();
+    worker_sync();
     if (threadIdx.x < NV) {
         double sum = 0.0;
         for (int q = 0; q < nranks; ++q) sum += s_pstage[q * NV + threadIdx.x];
         s_res[threadIdx.x] = sum;
     }
     if (threadIdx.x == 0) s_peer_epoch = tag;
-    __syncthreads();
+    worker_sync();
 }
 
 // The sums of all CTAs (and all ranks) in s_res[0..NV), identical bits everywhere.  Latency is
@@ -857,7 +879,7 @@ __device__ __noinline__ void grid_exchange(long long t_sweep_start, long long t_
     constexpr int kWarps = kPersistThreads / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grid = gridDim.x;
-    __syncthreads();
+    worker_sync();
     const long long t_a = clock64();
     // across the 16 warps: 16 lanes per quantity, 4 butterfly steps; publish
     const unsigned tag = next_tag(s_epoch);
@@ -891,7 +913,7 @@ __device__ __noinline__ void grid_exchange(long long t_sweep_start, long long t_
                     c[j].has(tag) ? c[j].value() : wait_cell<false>(base + cell_index(b, k0 + k), tag, s_ctx.abort_flag);
             }
         }
-        __syncthreads();
+        worker_sync();
         for (int k = warp; k < kRound; k += kWarps) {
             double t = 0.0;
             for (int b = lane; b < grid; b += 32) t += s_stage[k * kStagePitch + b];
@@ -899,10 +921,10 @@ __device__ __noinline__ void grid_exchange(long long t_sweep_start, long long t_
             for (int off = 16; off; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
             if (lane == 0) s_res[k0 + k] = t;
         }
-        if (k0 + kStageQuantities < NV) __syncthreads();
+        if (k0 + kStageQuantities < NV) worker_sync();
     }
     const long long t_c = clock64();
-    __syncthreads();  // (everybody read s_epoch before this barrier)
+    worker_sync();  // (everybody read s_epoch before this barrier)
     if (threadIdx.x == 0) s_epoch = tag;
     if (s_ctx.peer.nranks > 1) peer_exchange<NV>();
     if (threadIdx.x == 0) {
@@ -927,7 +949,7 @@ __device__ __forceinline__ void all_reduce(const double* acc, long long t_sweep_
 // EXTRA (0, 1, 2): the same sweep also sums ||x - f||^2 at the trial points s_req.pts[0 .. EXTRA-1] (sums number
 // NACC, NACC+1), again in the order of the cost sweeps.
 template <int JAC, int EXTRA>
-__device__ __noinline__ void jac_sweep() {
+__device__ BG_SWEEP_FN void jac_sweep() {
     const long long t0 = clock64();
     const PassParams q = s_req.q;
     const CostPoint xq = s_req.pts[0], zq = s_req.pts[EXTRA > 1 ? 1 : 0];
@@ -999,7 +1021,7 @@ __device__ __noinline__ void jac_sweep() {
         acc[ESQ] = esq_run;
         extra[0] = x_run;
         extra[1] = z_run;
-        __syncthreads();  // everybody has read s_ring_seq
+        worker_sync();  // everybody has read s_ring_seq
         if (threadIdx.x == 0) s_ring_seq = seq;
     }
     if ((s_ctx.v.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -1040,18 +1062,19 @@ __device__ __forceinline__ double resident_cost(const CostPoint& q, unsigned sc,
 
 // two trial points at once over the resident samples (eight exp chains per thread; each point's sum is
 // accumulated in exactly the order resident_cost uses, so batching never changes a value)
-__device__ __forceinline__ void resident_cost_x2(const CostPoint& qa, const CostPoint& qb, unsigned sc, unsigned sl, unsigned sx,
+__device__ __forceinline__ void resident_cost_x2(const CostPoint& qa_in, const CostPoint& qb_in, unsigned sc, unsigned sl, unsigned sx,
                                                  int res_pairs, long res_first, const double* traw, double* out_a, double* out_b) {
+    const CostPoint qa = qa_in, qb = qb_in;  // (callers pass shared memory: read once, not once per trip)
     double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
     int i = threadIdx.x;
     for (; i + kPersistThreads < res_pairs; i += 2 * kPersistThreads) {
         const int i2 = i + kPersistThreads;
         const double2 c = lds_pair(sc, i), l = lds_pair(sl, i), x = lds_pair(sx, i);
         const double2 d = lds_pair(sc, i2), m = lds_pair(sl, i2), y = lds_pair(sx, i2);
-        const double cc[4] = {c.x, c.y, d.x, d.y}, ll[4] = {l.x, l.y, m.x, m.y}, xx[4] = {x.x, x.y, y.x, y.y};
         const long g = 2 * (res_first + i), h = 2 * (res_first + i2);
-        const long idx[4] = {g, g + 1, h, h + 1};
         double ea[4], eb[4];
+        const double cc[4] = {c.x, c.y, d.x, d.y}, ll[4] = {l.x, l.y, m.x, m.y}, xx[4] = {x.x, x.y, y.x, y.y};
+        const long idx[4] = {g, g + 1, h, h + 1};
         residuals_n_x2<4>(qa, qb, cc, ll, xx, traw, idx, ea, eb);
         a0 = __fma_rn(ea[0], ea[0], a0); a0 = __fma_rn(ea[1], ea[1], a0);
         a1 = __fma_rn(ea[2], ea[2], a1); a1 = __fma_rn(ea[3], ea[3], a1);
@@ -1067,7 +1090,7 @@ __device__ __forceinline__ void resident_cost_x2(const CostPoint& qa, const Cost
     *out_b = b0 + b1;
 }
 
-__device__ __noinline__ void cost_sweep() {
+__device__ BG_SWEEP_FN void cost_sweep() {
     const long long t0 = clock64();
     const CostPoint q = s_req.pts[0];
     double acc[1];
@@ -1083,7 +1106,7 @@ __device__ __noinline__ void cost_sweep() {
                 run += a0 + a1;
             });
         acc[0] = run;
-        __syncthreads();
+        worker_sync();
         if (threadIdx.x == 0) s_ring_seq = seq;
     }
     if ((s_ctx.v.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -1094,7 +1117,7 @@ __device__ __noinline__ void cost_sweep() {
 }
 
 // number of non-finite residuals at point s_req.pts[s_req.cnt] (rare second sweep)
-__device__ __noinline__ void bad_sweep() {
+__device__ BG_SWEEP_FN void bad_sweep() {
     const long long t0 = clock64();
     const CostPoint q = s_req.pts[s_req.cnt];
     const SampleView v = s_ctx.v;
@@ -1112,7 +1135,7 @@ __device__ __noinline__ void bad_sweep() {
 }
 
 // up to kGridCostBatch trial points in ONE sweep + ONE exchange
-__device__ __noinline__ void many_sweep() {
+__device__ BG_SWEEP_FN void many_sweep() {
     const long long t0 = clock64();
     const int cnt = s_req.cnt;
     const unsigned sc = s_ctx.sc, sl = s_ctx.sl, sx = s_ctx.sx;
@@ -1144,7 +1167,7 @@ __device__ __noinline__ void many_sweep() {
                     }
                 }
             });
-        __syncthreads();
+        worker_sync();
         if (threadIdx.x == 0) s_ring_seq = seq;
     }
     if ((v.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -1163,7 +1186,7 @@ __device__ __noinline__ void run_sweep(int kind) {
 // The candidates are taken two at a time and each pair's sums are warp-reduced at once, so no thread ever holds 32
 // accumulators; per candidate the arithmetic -- and with it the value -- is exactly many_sweep's and cost_sweep's.
 template <int NV>
-__device__ __noinline__ void many_sweep_wide() {
+__device__ BG_SWEEP_FN void many_sweep_wide() {
     const long long t0 = clock64();
     const int cnt = s_req.cnt;
     const unsigned sc = s_ctx.sc, sl = s_ctx.sl, sx = s_ctx.sx;
@@ -1206,18 +1229,19 @@ __device__ __forceinline__ void run_sweep(int kind) {
     }
 }
 
-// warps 1..15: serve sweeps until the control warp quits
+// the workers: serve sweeps until the control warp quits
 __device__ __forceinline__ void serve_sweeps() {
     for (;;) {
         __syncthreads();  // the request is posted
         const int kind = s_req.kind;
         if (kind == kQuit) return;
         run_sweep(kind);
+        __syncthreads();  // the sums are in s_res
     }
 }
 
-// The Evaluator of lm_engine.cuh as seen by the control warp (warp 0 of every CTA): each call posts
-// a SweepRequest, joins the sweep and reads the reduced sums.  All 512 threads running the control
+// The Evaluator of lm_engine.cuh as seen by the control warp (warp 16 of every CTA): each call posts
+// a SweepRequest, waits for the workers and reads the reduced sums.  All 512 threads running the control
 // code redundantly cost more than the sweeps themselves.
 struct GridEval {
     static constexpr int kCostBatch = kGridCostBatch;
@@ -1246,7 +1270,7 @@ struct GridEval {
     // 3 trial_outcome, 4 line-search probe cost_site (rejection algebra, pow, search set-up, first backtrack),
     // 5 ls_outcome, 6 pg_walk entry, 7 pg_walk exit (walk control without its sweeps), 8 other cost_site
     __device__ __forceinline__ void tick(int id) {
-        if (threadIdx.x == 0) {
+        if (ctl_lane() == 0) {
             const long long now = clock64(), busy = s_cyc[0] + s_cyc[1];
             s_tick[id] += (now - s_tick_last) - (busy - s_tick_busy);
             s_tick_last = now;
@@ -1259,12 +1283,12 @@ struct GridEval {
 #else
     __device__ __forceinline__ void post(int kind) {
 #endif
-        if (threadIdx.x == 0) {
+        if (ctl_lane() == 0) {
             s_req.kind = kind;
             s_ctl[kind >= kSweepMany16 ? (int)kSweepMany : kind] += clock64() - s_ctl[7];
         }
-        __syncthreads();
-        if (kind != kQuit) run_sweep(kind);
+        __syncthreads();                     // hand the request to the workers ...
+        if (kind != kQuit) __syncthreads();  // ... and wait for the sums
     }
 
     __device__ __forceinline__ int jac_sweep_kind() const {
@@ -1276,7 +1300,7 @@ struct GridEval {
 
     // post a Jacobian sweep at q; extra: also the cost at s_req.pts[0]
     __device__ __forceinline__ void post_jac(const PassParams& q, int extra) {
-        if (threadIdx.x == 0) {
+        if (ctl_lane() == 0) {
             s_req.q = q;
             s_req.extra = extra;
         }
@@ -1286,8 +1310,8 @@ struct GridEval {
     // keep the sums of the Jacobian sweep that just ended, as the Jacobian (and cost) of `pt`
     __device__ __forceinline__ void keep_jac(const double* pt) {
         __syncwarp();  // nobody still reads the previous memo
-        if (threadIdx.x < NACC) s_memo[3 + threadIdx.x] = s_res[threadIdx.x];  // A00..A22, G0..G2, ESQ are 0..9
-        if (threadIdx.x == 0) { s_memo[0] = pt[0]; s_memo[1] = pt[1]; s_memo[2] = pt[2]; }
+        if (ctl_lane() < NACC) s_memo[3 + ctl_lane()] = s_res[ctl_lane()];  // A00..A22, G0..G2, ESQ are 0..9
+        if (ctl_lane() == 0) { s_memo[0] = pt[0]; s_memo[1] = pt[1]; s_memo[2] = pt[2]; }
         __syncwarp();
         memo_valid = true;
         ++spec_issued;
@@ -1314,7 +1338,7 @@ struct GridEval {
 
     // ||x - f(p)||^2 through a Jacobian sweep at p; the normal-equation sums are kept for jac(p)
     __device__ __forceinline__ double cost_with_jac(const double* p, bool& bad) {
-        if (threadIdx.x == 0) s_req.pts[0] = make_cost_point(p, model);  // count_bad(0), should the sum come out non-finite
+        if (ctl_lane() == 0) s_req.pts[0] = make_cost_point(p, model);  // count_bad(0), should the sum come out non-finite
         post_jac(make_pass_params(p, model, delta, jkind), 0);
         const double esq = s_res[ESQ];
         keep_jac(p);
@@ -1326,7 +1350,7 @@ struct GridEval {
     // ||x - f(p)||^2 and, in the same sweep, the Jacobian (and cost) at the announced first candidate h of the
     // projected-gradient walk that follows if this last line-search probe is not accepted
     __device__ __forceinline__ double cost_and_jac_at(const double* p, const double* h, bool& bad) {
-        if (threadIdx.x == 0) s_req.pts[0] = make_cost_point(p, model);
+        if (ctl_lane() == 0) s_req.pts[0] = make_cost_point(p, model);
         post_jac(make_pass_params(h, model, delta, jkind), 1);
         const double esq = s_res[NACC];
         keep_jac(h);
@@ -1347,7 +1371,7 @@ struct GridEval {
         double cand[3];
         pg_candidate(p, g, t, Box{lb, ub}, cand);
         __syncwarp();
-        if (threadIdx.x == 0) { s_hint[0] = cand[0]; s_hint[1] = cand[1]; s_hint[2] = cand[2]; }
+        if (ctl_lane() == 0) { s_hint[0] = cand[0]; s_hint[1] = cand[1]; s_hint[2] = cand[2]; }
         __syncwarp();
         hint_valid = true;
     }
@@ -1361,7 +1385,7 @@ struct GridEval {
     __device__ __forceinline__ void probe_hint(const double* probe) {
         BG_TICK(1);
         __syncwarp();
-        if (threadIdx.x == 0) { s_ahead[0] = probe[0]; s_ahead[1] = probe[1]; s_ahead[2] = probe[2]; }
+        if (ctl_lane() == 0) { s_ahead[0] = probe[0]; s_ahead[1] = probe[1]; s_ahead[2] = probe[2]; }
         __syncwarp();
         ahead_valid = true;
         cand_valid = false;
@@ -1373,7 +1397,7 @@ struct GridEval {
         double cand[3];
         pg_candidate(p, g, t, Box{lb, ub}, cand);
         __syncwarp();
-        if (threadIdx.x == 0) { s_ahead[3] = cand[0]; s_ahead[4] = cand[1]; s_ahead[5] = cand[2]; }
+        if (ctl_lane() == 0) { s_ahead[3] = cand[0]; s_ahead[4] = cand[1]; s_ahead[5] = cand[2]; }
         __syncwarp();
         cand_valid = true;
     }
@@ -1381,7 +1405,7 @@ struct GridEval {
     // costs at the trial point p and at the announced probe, Jacobian (and cost) at the announced candidate
     __device__ __forceinline__ double cost_probe_and_candidate(const double* p, bool& bad) {
         const double probe[3] = {s_ahead[0], s_ahead[1], s_ahead[2]}, cand[3] = {s_ahead[3], s_ahead[4], s_ahead[5]};
-        if (threadIdx.x == 0) {
+        if (ctl_lane() == 0) {
             s_req.pts[0] = make_cost_point(p, model);
             s_req.pts[1] = make_cost_point(probe, model);
         }
@@ -1389,7 +1413,7 @@ struct GridEval {
         const double esq = s_res[NACC], esq_probe = s_res[NACC + 1];
         keep_jac(cand);
         __syncwarp();
-        if (threadIdx.x == 0) { s_ahead[6] = probe[0]; s_ahead[7] = probe[1]; s_ahead[8] = probe[2]; s_ahead[9] = esq_probe; }
+        if (ctl_lane() == 0) { s_ahead[6] = probe[0]; s_ahead[7] = probe[1]; s_ahead[8] = probe[2]; s_ahead[9] = esq_probe; }
         __syncwarp();
         probe_known = lm_finite(esq_probe);
         ++creep_fused;
@@ -1429,7 +1453,7 @@ struct GridEval {
     __device__ __forceinline__ void pg_outcome(bool took_first) { sp_pg = took_first; }  // sequential form of the walk only
 
     __device__ __forceinline__ double count_bad(int k) {
-        if (threadIdx.x == 0) s_req.cnt = k;
+        if (ctl_lane() == 0) s_req.cnt = k;
         post(kSweepBad);
         ++cost_passes;
         return s_res[0];
@@ -1437,7 +1461,7 @@ struct GridEval {
 
     __device__ __forceinline__ double cost(const double* p, bool& bad) {
         const CostPoint q = make_cost_point(p, model);
-        if (threadIdx.x == 0) s_req.pts[0] = q;
+        if (ctl_lane() == 0) s_req.pts[0] = q;
         post(kSweepCost);
         ++cost_passes;
         ++cost_points;
@@ -1452,24 +1476,24 @@ struct GridEval {
     __device__ __forceinline__ double* batch_points() { return s_cand; }
     __device__ __forceinline__ void cost_many(int cnt, const double* dscl, int) {
         __syncwarp();
-        if (threadIdx.x < cnt) {
+        if (ctl_lane() < cnt) {
             double q[3];
-            for (int i = 0; i < 3; ++i) q[i] = dscl ? s_cand[3 * threadIdx.x + i] * dscl[i] : s_cand[3 * threadIdx.x + i];
-            s_req.pts[threadIdx.x] = make_cost_point(q, model);
+            for (int i = 0; i < 3; ++i) q[i] = dscl ? s_cand[3 * ctl_lane() + i] * dscl[i] : s_cand[3 * ctl_lane() + i];
+            s_req.pts[ctl_lane()] = make_cost_point(q, model);
         }
-        if (threadIdx.x == 0) s_req.cnt = cnt;
+        if (ctl_lane() == 0) s_req.cnt = cnt;
         post(kSweepMany);
         ++cost_passes;
         cost_points += cnt;
-        if (threadIdx.x < cnt) {
-            s_cand_cost[threadIdx.x] = s_res[threadIdx.x];
-            s_cand_bad[threadIdx.x] = 0;
+        if (ctl_lane() < cnt) {
+            s_cand_cost[ctl_lane()] = s_res[ctl_lane()];
+            s_cand_bad[ctl_lane()] = 0;
         }
         __syncwarp();
         for (int k = 0; k < cnt; ++k) {
             if (!lm_finite(s_cand_cost[k])) {  // uniform: every lane reads the same value
                 const double nbad = count_bad(k);
-                if (threadIdx.x == 0) s_cand_bad[k] = nbad != 0.0;
+                if (ctl_lane() == 0) s_cand_bad[k] = nbad != 0.0;
                 __syncwarp();
             }
         }
@@ -1488,7 +1512,7 @@ struct GridEval {
                                            double& t, double t0, int& gprevtaken, double* pDp, double* Dp, double& Dp_L2,
                                            double& e_new, int& nfev) {
         const double alpha = 1e-4, beta = 0.9, tming = 1e-18;
-        const int lane = threadIdx.x;  // control warp: 0..31
+        const int lane = ctl_lane();  // control warp: 0..31
         const Box box{lb, ub};
         BG_TICK(6);
         // wide batches need the whole shard on chip (many_sweep_wide); a streamed shard keeps 8 per sweep
@@ -1585,11 +1609,17 @@ struct GridEval {
     }
 };
 
-__global__ void __launch_bounds__(kPersistThreads, 1) k_persistent_fit(SampleView v, int model, GlobalFitSpec spec,
+#ifdef BG_PERSIST_MAXNREG
+__global__ void __maxnreg__(BG_PERSIST_MAXNREG) k_persistent_fit(
+#else
+__global__ void __launch_bounds__(kPersistBlockThreads, 1) k_persistent_fit(
+#endif
+    SampleView v, int model, GlobalFitSpec spec,
                                                                         uint4* cells, long resident_pairs,
                                                                         PeerView peer, GlobalFitOut* out) {
     extern __shared__ double2 smem_dyn[];
     // this CTA's resident slice: pairs [first, last) of the first `resident_pairs` pairs, balanced
+    BG_EXP_TABLE_LOAD();
     const long first = resident_pairs * blockIdx.x / gridDim.x, last = resident_pairs * (blockIdx.x + 1) / gridDim.x;
     const int cap = (int)((resident_pairs + gridDim.x - 1) / gridDim.x);
     const int mine = (int)(last - first);
@@ -1601,7 +1631,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_persistent_fit(SampleVie
         const double2* __restrict__ c2 = reinterpret_cast<const double2*>(v.c);
         const double2* __restrict__ l2 = reinterpret_cast<const double2*>(v.L);
         const double2* __restrict__ x2 = reinterpret_cast<const double2*>(v.x);
-        for (int i = threadIdx.x; i < mine; i += kPersistThreads) {
+        for (int i = threadIdx.x; i < mine; i += kPersistBlockThreads) {
             sc[i] = __ldg(c2 + first + i);
             sl[i] = __ldg(l2 + first + i);
             sx[i] = __ldg(x2 + first + i);
@@ -1628,14 +1658,12 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_persistent_fit(SampleVie
     // covariance on several GPUs needs the sample count of ALL ranks (lmbc_core.c:994-1002: sumsq / (n - m)); it
     // travels through the kernel's own exchange, so a context that only attached peer buffers (no NCCL
     // communicator) can still return it.  Exact: counts are integers far below 2^53.
-    if (spec.want_n_all) {
-        double cnt[1] = {(blockIdx.x == 0 && threadIdx.x == 0) ? (double)v.n : 0.0};
-        all_reduce<1>(cnt, clock64());
-        if (blockIdx.x == 0 && threadIdx.x == 0) out->n_all = s_res[0];
-        __syncthreads();
-    }
-
-    if (threadIdx.x >= 32) {
+    if (threadIdx.x < kPersistThreads) {
+        if (spec.want_n_all) {
+            double cnt[1] = {(blockIdx.x == 0 && threadIdx.x == 0) ? (double)v.n : 0.0};
+            all_reduce<1>(cnt, clock64());
+            if (blockIdx.x == 0 && threadIdx.x == 0) out->n_all = s_res[0];
+        }
         serve_sweeps();
         return;
     }
@@ -1664,7 +1692,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_persistent_fit(SampleVie
         info[2] = ev.cost_and_jac_at(p, p, bad);
         info[3] = s_memo[3 + ESQ];
         __syncwarp();
-        if (threadIdx.x < 6) s_cand[threadIdx.x] = p[threadIdx.x % 3];
+        if (ctl_lane() < 6) s_cand[ctl_lane()] = p[ctl_lane() % 3];
         __syncwarp();
         ev.cost_many(2, nullptr, 3);
         info[4] = ev.batch_cost(0);
@@ -1677,9 +1705,21 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_persistent_fit(SampleVie
         bool bad;
         double Jte[3];
         for (int i = 0; i < 10; ++i) info[i] = 0.0;
+        // (bits 8..13 = W > 0, profiling only: rounds of ONE cost sweep over W trial points instead)
+        const int width = (spec.spec_jac >> 8) & 63;
+        Jte[0] = 0.0;
         for (int it = 0; it < spec.itmax; ++it) {
-            ev.jac(p, JtJ, Jte);
-            info[1] = ev.cost(p, bad);
+            if (width == 0) {
+                ev.jac(p, JtJ, Jte);
+                info[1] = ev.cost(p, bad);
+            } else {
+                if (ctl_lane() < width && ctl_lane() < kWalkMaxBatch) s_req.pts[ctl_lane()] = make_cost_point(p, model);
+                if (ctl_lane() == 0) s_req.cnt = width;
+                ev.post(width == 1 ? kSweepCost : width <= kGridCostBatch ? kSweepMany : width <= 16 ? kSweepMany16 : kSweepMany32);
+                info[1] = s_res[0];
+                ++ev.cost_passes;
+                ev.cost_points += width;
+            }
         }
         info[5] = (double)spec.itmax;
         info[2] = Jte[0];
@@ -1691,11 +1731,11 @@ __global__ void __launch_bounds__(kPersistThreads, 1) k_persistent_fit(SampleVie
                            spec.has_dscl ? spec.dscl : nullptr, spec.opt, info, JtJ);
     ev.post(kQuit);
 #ifdef BG_CTL_TICKS
-    if (blockIdx.x == 0 && threadIdx.x == 0)
+    if (blockIdx.x == 0 && ctl_lane() == 0)
         printf("ticks: iter-end %lld | post-jac+LU+probe %lld | cand-hint %lld | trial-test %lld | reject+LS-setup %lld | LS-tests %lld | to-PG %lld | PG-control %lld | other %lld  (iterations %d)\n",
                s_tick[0], s_tick[1], s_tick[2], s_tick[3], s_tick[4], s_tick[5], s_tick[6], s_tick[7], s_tick[8], (int)info[5]);
 #endif
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (blockIdx.x == 0 && ctl_lane() == 0) {
         out->ret = ret;
         out->peer_epoch = s_peer_epoch;
         out->jac_passes = ev.jac_passes;
@@ -1760,7 +1800,7 @@ static bool persistent_plan(brdfgpu_ctx* ctx, long n, PersistPlan* plan) {
     plan->resident_pairs = resident;
     plan->smem = (size_t)((resident + grid - 1) / grid) * 3 * sizeof(double2) + ring_bytes;
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persistent_fit, kPersistThreads, plan->smem) != cudaSuccess ||
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persistent_fit, kPersistBlockThreads, plan->smem) != cudaSuccess ||
         per_sm < 1)
         return false;
     return true;
@@ -1870,7 +1910,7 @@ int global_fit(brdfgpu_ctx* ctx, const brdfgpu_samples* s, double* p, int m, con
             peer.epoch = ctx->peer_epoch;
         }
         void* args[] = {&v, &model, &spec, &cells, &resident_pairs, &peer, &d_out};
-        BG_CUDA_OK(ctx, cudaLaunchCooperativeKernel((const void*)k_persistent_fit, dim3(plan.grid), dim3(kPersistThreads), args,
+        BG_CUDA_OK(ctx, cudaLaunchCooperativeKernel((const void*)k_persistent_fit, dim3(plan.grid), dim3(kPersistBlockThreads), args,
                                                      plan.smem, ctx->stream));
         ++ctx->launches;
         BG_CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_fitio, d_out, sizeof(GlobalFitOut), cudaMemcpyDeviceToHost, ctx->stream));
