@@ -132,7 +132,8 @@ __device__ __forceinline__ double exp_core(double y) {
 // dependency chain of 8 instead of 15, max relative error 2.1e-16 (1.9 ulp, against 4 ulp of the polynomial; exact
 // emulation in profiles/tools/make_exp_table.py, which also generated the constants).  The table is replicated so that
 // lane l reads copy l mod 16 whose entries all sit in bank pair l mod 16: an LDS.64 of a warp is conflict-free whatever
-// the 32 indices are.  Every kernel of such a translation unit calls exp_table_load() first.
+// the 32 indices are (8 KB; with 8 copies a Jacobian sweep of the persistent fit takes 11 % longer).  Every kernel of
+// such a translation unit calls exp_table_load() first.
 // Measured (profiles/r02_persist_control.md): the resident sweeps of the persistent fit take the same ~2.7 k cycles
 // per trial point with either variant -- ptxas runs the chains of a trip nearly one after the other, so the sweeps
 // wait on FP64 latency (13 cycles per dependent step, 4 warps per scheduler), not on the FP64 issue rate this saves.

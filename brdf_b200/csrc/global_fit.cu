@@ -763,6 +763,8 @@ struct FitContext {
     long res_first;       // global index of its first pair
     long stream_first;    // pairs >= stream_first are streamed from global memory by the whole grid
     uint4* cells;         // [2 parities][kMaxPersistBlocks][NSUM], cell_index()
+    double* stage;        // transposition area of the exchange: stage_q quantities x kStagePitch CTAs
+    int stage_q;          // quantities per round of the transposition (kStageWide or kStageNarrow)
     PeerView peer;        // nranks == 1: no cross-GPU step
     int* abort_flag;      // global
 };
@@ -846,8 +848,8 @@ __device__ __forceinline__ void peer_exchange() {
 // Stage 2 (grid_exchange): 16 lanes per quantity add the 16 warps and publish the CTA's sum as a flagged cell; then
 // all threads collect the cells of ALL CTAs into shared memory (all loads go out together, late ones are re-polled)
 // and one warp per quantity adds them (lane l takes CTAs l, l + 32, ... in ascending order, then a butterfly) -- a
-// fixed order, so every CTA (and every rank, below) holds identical bits.  16 quantities per round: the 32 sums of
-// the widest sweep take two.
+// fixed order, so every CTA (and every rank, below) holds identical bits.  The transposition takes 16 (or 8, when the
+// shard needs the shared memory) quantities per round; the loads behind it all go out at once.
 template <int NV>
 __device__ __forceinline__ void warp_sums_to_smem(const double* acc, int first = 0, int stride = NV) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -868,14 +870,18 @@ __device__ __forceinline__ void warp_sums_to_smem(const double* acc, int first =
 // cell of quantity k of CTA b.  CTA-major on purpose: a CTA's cells share lines with at most one neighbour.  With
 // the quantity-major order (8 CTAs writing into every 128-byte line while 148 poll it) an exchange took 2x longer.
 __device__ __forceinline__ int cell_index(int b, int k) { return b * NSUM + k; }
-constexpr int kStageQuantities = 16;
 constexpr int kStagePitch = kMaxPersistBlocks + 1;  // quantity-major with an odd pitch: conflict-free both ways
-__shared__ double s_stage[kStagePitch * kStageQuantities];
+// The transposition area of the exchange lives in dynamic shared memory behind the shard (and the TMA ring): 16
+// quantities per round when that fits, 8 when the shard needs the room (persistent_plan()).  Shared memory is what the
+// resident shard lives in -- and what is left of the 256 KB is the L1 that catches the spills of the Jacobian sweeps
+// and of the control warp: configs[1] with 16 quantities stays within the 196 KB carve-out (60 KB of L1); with the
+// full 32 it crossed into the 228 KB one and the Jacobian sweeps took 11 % longer.
+constexpr int kStageWide = 16, kStageNarrow = 8;
+constexpr size_t stage_bytes(int q) { return sizeof(double) * kStagePitch * (size_t)q; }
 // Not inlined: with its own register allocation the cells in flight do not push the sweeps' accumulators into local
 // memory (inlined into the Jacobian sweeps it cost them up to 1.3 KB of spills and ~3 k cycles per sweep).
 template <int NV>
 __device__ __noinline__ void grid_exchange(long long t_sweep_start, long long t_in) {
-    static_assert(NV <= kStageQuantities || NV % kStageQuantities == 0, "whole rounds only");
     constexpr int kWarps = kPersistThreads / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grid = gridDim.x;
@@ -892,36 +898,60 @@ __device__ __noinline__ void grid_exchange(long long t_sweep_start, long long t_
         if (k < NV && w == 0) store_cell<false>(base + cell_index(blockIdx.x, k), t, tag);
     }
     const long long t_b = clock64();
-    // every thread collects a few cells (consecutive threads = consecutive quantities of one CTA): all loads go out
-    // together, late ones are re-polled; then one warp per quantity adds the staged values in ascending CTA order
-    for (int k0 = 0; k0 < NV; k0 += kStageQuantities) {
-        constexpr int kRound = NV < kStageQuantities ? NV : kStageQuantities;
-        constexpr int kPerThread = (kMaxPersistBlocks * kRound + kPersistThreads - 1) / kPersistThreads;
-        Cell c[kPerThread];
+    // every thread collects a few cells (consecutive threads = consecutive quantities of one CTA): ALL loads go out
+    // together, late ones are re-polled; then, stage_q quantities per round, the values are transposed through shared
+    // memory and one warp per quantity adds them in ascending CTA order
+    constexpr int kPerThread = (kMaxPersistBlocks * NV + kPersistThreads - 1) / kPersistThreads;
+    double val[kPerThread];
+    {
+        // (re-)load every cell that is still missing, all in one go, until none is: a round costs one L2 round trip
+        // whatever the number of late cells (this thread polls right after publishing, so most cells ARE late)
+        unsigned pending = 0u;
 #pragma unroll
         for (int j = 0; j < kPerThread; ++j) {
-            const int idx = threadIdx.x + j * kPersistThreads;
-            const int b = idx / kRound, k = idx - b * kRound;
-            if (k < kRound && b < grid) c[j] = load_cell<false>(base + cell_index(b, k0 + k));
+            val[j] = 0.0;
+            if ((threadIdx.x + j * kPersistThreads) / NV < grid) pending |= 1u << j;
         }
+        const long long t_poll = clock64();
+        for (unsigned spins = 0; pending; ++spins) {
+            Cell c[kPerThread];
 #pragma unroll
-        for (int j = 0; j < kPerThread; ++j) {
-            const int idx = threadIdx.x + j * kPersistThreads;
-            const int b = idx / kRound, k = idx - b * kRound;
-            if (k < kRound && b < grid) {
-                s_stage[k * kStagePitch + b] =
-                    c[j].has(tag) ? c[j].value() : wait_cell<false>(base + cell_index(b, k0 + k), tag, s_ctx.abort_flag);
+            for (int j = 0; j < kPerThread; ++j) {
+                const int idx = threadIdx.x + j * kPersistThreads;
+                const int b = idx / NV, k = idx - b * NV;
+                if (pending & (1u << j)) c[j] = load_cell<false>(base + cell_index(b, k));
+            }
+#pragma unroll
+            for (int j = 0; j < kPerThread; ++j)
+                if ((pending & (1u << j)) && c[j].has(tag)) {
+                    val[j] = c[j].value();
+                    pending &= ~(1u << j);
+                }
+            if (pending && (spins & 0xffu) == 0xffu && (clock64() - t_poll > kSpinCycles || *(volatile int*)s_ctx.abort_flag)) {
+                *s_ctx.abort_flag = 1;  // somebody never delivered: everybody gives up (the control loop stops on the NaN)
+                val[0] = __longlong_as_double(0x7ff8000000000000LL);
+                pending = 0u;
             }
         }
+    }
+    double* const stage = s_ctx.stage;
+    const int stage_q = s_ctx.stage_q;
+    for (int k0 = 0; k0 < NV; k0 += stage_q) {
+#pragma unroll
+        for (int j = 0; j < kPerThread; ++j) {
+            const int idx = threadIdx.x + j * kPersistThreads;
+            const int b = idx / NV, k = idx - b * NV;
+            if (b < grid && k >= k0 && k < k0 + stage_q) stage[(k - k0) * kStagePitch + b] = val[j];
+        }
         worker_sync();
-        for (int k = warp; k < kRound; k += kWarps) {
+        for (int k = k0 + warp; k < NV && k < k0 + stage_q; k += kWarps) {
             double t = 0.0;
-            for (int b = lane; b < grid; b += 32) t += s_stage[k * kStagePitch + b];
+            for (int b = lane; b < grid; b += 32) t += stage[(k - k0) * kStagePitch + b];
 #pragma unroll
             for (int off = 16; off; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
-            if (lane == 0) s_res[k0 + k] = t;
+            if (lane == 0) s_res[k] = t;
         }
-        if (k0 + kStageQuantities < NV) worker_sync();
+        if (k0 + stage_q < NV) worker_sync();
     }
     const long long t_c = clock64();
     worker_sync();  // (everybody read s_epoch before this barrier)
@@ -1614,9 +1644,8 @@ __global__ void __maxnreg__(BG_PERSIST_MAXNREG) k_persistent_fit(
 #else
 __global__ void __launch_bounds__(kPersistBlockThreads, 1) k_persistent_fit(
 #endif
-    SampleView v, int model, GlobalFitSpec spec,
-                                                                        uint4* cells, long resident_pairs,
-                                                                        PeerView peer, GlobalFitOut* out) {
+    SampleView v, int model, GlobalFitSpec spec, uint4* cells, long resident_pairs, int stage_q, int stage_off, PeerView peer,
+    GlobalFitOut* out) {
     extern __shared__ double2 smem_dyn[];
     // this CTA's resident slice: pairs [first, last) of the first `resident_pairs` pairs, balanced
     BG_EXP_TABLE_LOAD();
@@ -1643,6 +1672,8 @@ __global__ void __launch_bounds__(kPersistBlockThreads, 1) k_persistent_fit(
         s_ctx.sx = (unsigned)__cvta_generic_to_shared(sx);
         s_ctx.res_pairs = mine; s_ctx.res_first = first; s_ctx.stream_first = resident_pairs;
         s_ctx.cells = cells; s_ctx.peer = peer; s_ctx.abort_flag = &out->aborted;
+        s_ctx.stage = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(smem_dyn) + stage_off);  // persistent_plan()
+        s_ctx.stage_q = stage_q;
         s_epoch = 0u; s_peer_epoch = peer.epoch; s_ring_seq = 0;
         for (int i = 0; i < 6; ++i) s_cyc[i] = 0;
         for (int i = 0; i < 7; ++i) s_ctl[i] = 0;
@@ -1760,6 +1791,8 @@ struct PersistPlan {
     int grid;
     long resident_pairs;
     size_t smem;
+    int stage_q;     // quantities per round of the exchange's transposition area ...
+    size_t stage_off;  // ... and where it starts in the dynamic shared memory
 };
 
 static bool persistent_plan(brdfgpu_ctx* ctx, long n, PersistPlan* plan) {
@@ -1785,12 +1818,19 @@ static bool persistent_plan(brdfgpu_ctx* ctx, long n, PersistPlan* plan) {
     long cap = ctx->sm_count < kMaxPersistBlocks ? ctx->sm_count : kMaxPersistBlocks;
     if (grid < 1) grid = 1;
     if (grid > cap) grid = cap;
-    long cap_pairs = ctx->persist_smem_max / (3 * (long)sizeof(double2));
+    // dynamic shared memory = [shard slice | TMA ring if the shard does not fit | transposition area], 128-byte aligned
+    const long pair_bytes = 3 * (long)sizeof(double2), room = ctx->persist_smem_max;
+    int stage_q = kStageWide;
+    long cap_pairs = (room - (long)stage_bytes(stage_q) - 128) / pair_bytes;
+    if (npair > grid * cap_pairs) {  // give the shard the room of the wide transposition area first
+        stage_q = kStageNarrow;
+        cap_pairs = (room - (long)stage_bytes(stage_q) - 128) / pair_bytes;
+    }
     long resident = npair;
     size_t ring_bytes = 0;
     if (npair > grid * cap_pairs) {  // not everything fits on chip: part of the shared memory becomes the TMA ring
         ring_bytes = PersistRing::kBytes + 128;
-        cap_pairs = ((long)ctx->persist_smem_max - (long)ring_bytes) / (3 * (long)sizeof(double2));
+        cap_pairs = (room - (long)ring_bytes - (long)stage_bytes(stage_q) - 128) / pair_bytes;
         if (cap_pairs < 0) return false;
         resident = grid * cap_pairs;
     }
@@ -1798,7 +1838,10 @@ static bool persistent_plan(brdfgpu_ctx* ctx, long n, PersistPlan* plan) {
     while (resident > 0 && (resident + grid - 1) / grid > cap_pairs) --resident;
     plan->grid = (int)grid;
     plan->resident_pairs = resident;
-    plan->smem = (size_t)((resident + grid - 1) / grid) * 3 * sizeof(double2) + ring_bytes;
+    const size_t slice = (size_t)((resident + grid - 1) / grid) * (size_t)pair_bytes;
+    plan->stage_q = stage_q;
+    plan->stage_off = ((slice + 127) & ~(size_t)127) + ring_bytes;  // (the kernel puts the ring at the same aligned offset)
+    plan->smem = plan->stage_off + stage_bytes(stage_q);
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persistent_fit, kPersistBlockThreads, plan->smem) != cudaSuccess ||
         per_sm < 1)
@@ -1909,7 +1952,8 @@ int global_fit(brdfgpu_ctx* ctx, const brdfgpu_samples* s, double* p, int m, con
             peer.nranks = ctx->nranks;
             peer.epoch = ctx->peer_epoch;
         }
-        void* args[] = {&v, &model, &spec, &cells, &resident_pairs, &peer, &d_out};
+        int stage_q = plan.stage_q, stage_off = (int)plan.stage_off;
+        void* args[] = {&v, &model, &spec, &cells, &resident_pairs, &stage_q, &stage_off, &peer, &d_out};
         BG_CUDA_OK(ctx, cudaLaunchCooperativeKernel((const void*)k_persistent_fit, dim3(plan.grid), dim3(kPersistBlockThreads), args,
                                                      plan.smem, ctx->stream));
         ++ctx->launches;

@@ -49,6 +49,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_rate(int pairs, int reps, CostP
                 b0 = __fma_rn(eb[0], eb[0], b0); b0 = __fma_rn(eb[1], eb[1], b0);
                 b1 = __fma_rn(eb[2], eb[2], b1); b1 = __fma_rn(eb[3], eb[3], b1);
             }
+            if (i < pairs) {
+                accumulate_cost_pair(qa, sc[i], sl[i], sx[i], traw, 2L * i, &a0);
+                accumulate_cost_pair(qb, sc[i], sl[i], sx[i], traw, 2L * i, &b0);
+            }
         } else if (FORM == 2) {  // one point, one pair per trip
             for (; i < pairs; i += kThreads) accumulate_cost_pair(qa, sc[i], sl[i], sx[i], traw, 2L * i, &a0);
         } else if (FORM == 3) {  // one point, four pairs per trip
@@ -65,6 +69,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_rate(int pairs, int reps, CostP
 #pragma unroll
                 for (int k = 0; k < 8; k += 2) { a0 = __fma_rn(e[k], e[k], a0); a1 = __fma_rn(e[k + 1], e[k + 1], a1); }
             }
+            for (; i < pairs; i += kThreads) accumulate_cost_pair(qa, sc[i], sl[i], sx[i], traw, 2L * i, &a0);
         }
         total += (a0 + a1) + (b0 + b1);
     }
