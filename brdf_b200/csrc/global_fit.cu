@@ -1728,6 +1728,24 @@ __global__ void __launch_bounds__(kPersistBlockThreads, 1) k_persistent_fit(
         ev.cost_many(2, nullptr, 3);
         info[4] = ev.batch_cost(0);
         info[5] = ev.batch_cost(1);
+        // the wide batches of the lane-parallel walk (resident shards only): the same point in the first and the last
+        // slot of a 13-candidate sweep, in an odd and the last slot of a 32-candidate one.  info[6..9] are rewritten by
+        // the host's accounting, so a value that differs from the cost sweep's takes the place of info[5].
+        if (s_ctx.stream_first >= (s_ctx.v.n >> 1)) {
+            __syncwarp();
+            s_req.pts[ctl_lane()] = make_cost_point(p, model);
+            __syncwarp();
+            if (ctl_lane() == 0) s_req.cnt = 13;
+            ev.post(kSweepMany16);
+            const double w0 = s_res[0], w1 = s_res[12];
+            if (ctl_lane() == 0) s_req.cnt = kWalkMaxBatch;
+            ev.post(kSweepMany32);
+            const double w2 = s_res[17], w3 = s_res[kWalkMaxBatch - 1];
+            if (!GridEval::same_bits(w0, info[0])) info[5] = w0;
+            if (!GridEval::same_bits(w1, info[0])) info[5] = w1;
+            if (!GridEval::same_bits(w2, info[0])) info[5] = w2;
+            if (!GridEval::same_bits(w3, info[0])) info[5] = w3;
+        }
         ret = 0;
     } else if (spec.spec_jac & 16) {
         // scripted sequence (BRDFGPU_SPEC_JAC=16, bench.py's trajectory-invariant scaling figure): itmax rounds of one

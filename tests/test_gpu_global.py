@@ -362,9 +362,9 @@ def test_speculative_jacobians_change_nothing(ctx, case, monkeypatch):
 @pytest.mark.parametrize("n", [200_001, 2_600_001])
 def test_every_kind_of_sweep_gives_the_same_cost_bits(ctx, n, monkeypatch):
     """What the speculation rests on: ||x - f(p)||^2 of one point has the same bits whether the persistent kernel
-    gets it from a cost sweep, a Jacobian sweep, a Jacobian sweep with extra cost points or a batch of candidates
-    (BRDFGPU_SPEC_JAC=8 self-check: info[0..5]) -- on chip (n small) and with a streamed part, with negative,
-    zero and tiny cosines in the data."""
+    gets it from a cost sweep, a Jacobian sweep, a Jacobian sweep with extra cost points, a batch of candidates or a
+    wide batch of the lane-parallel walk (BRDFGPU_SPEC_JAC=8 self-check: info[0..5]) -- on chip (n small) and with a
+    streamed part, with negative, zero and tiny cosines in the data."""
     c, td, th, x = synth.samples(n, seed=91)
     t = td.copy()
     t[::97] *= -1.0
@@ -376,6 +376,7 @@ def test_every_kind_of_sweep_gives_the_same_cost_bits(ctx, n, monkeypatch):
         preset = dict(A.REF_GLOBAL)
         preset["p0"] = p0
         ret, p, info = ctx.fit_global(s, preset)
+        # (resident shards: a wide batch of 13 or 32 candidates that gave the point another value put it into info[5])
         v = info[:6]
         assert np.isfinite(v).all(), (p0, v)
         assert all(q.tobytes() == v[0].tobytes() for q in v), (p0, [repr(float(q)) for q in v])
@@ -398,3 +399,20 @@ def test_solve_equation_single_colmajor_is_the_reference_flattening():
     # the aligned order on the same data is a different (well-posed) problem with a different answer
     ret2, p2, _ = A.solve_equation_single(c, td, th, x, 1)
     assert not np.allclose(p, p2, rtol=1e-3)
+
+
+@pytest.mark.parametrize("n, resident", [(1_250_000, True), (1_300_000, False)])
+def test_shard_residency_boundary(ctx, n, resident):
+    """persistent_plan(): a shard of 1.25e6 samples (BASELINE's 10^7 strong-scaled over 8 GPUs) still lives entirely in
+    shared memory -- it takes the room of half the exchange's transposition area -- and 1.3e6 streams its tail through
+    the TMA ring; both agree with the kernel-per-evaluation driver within the parity tolerances."""
+    s = ctx.synth(n, seed=synth.DEFAULT_SEED)
+    a = ctx.fit_global(s, A.REF_GLOBAL, drive=A.DRIVE_PERSISTENT)
+    st = ctx.fit_stats()
+    assert (st["resident_samples"] >= n - 1) == resident, st
+    assert st["ctas"] > 0 and st["cyc_total"] > 0          # the persistent kernel ran (no silent change of driver)
+    b = ctx.fit_global(s, A.REF_GLOBAL, drive=A.DRIVE_HOST)
+    assert a[0] >= 0 and b[0] >= 0
+    np.testing.assert_allclose(a[1], b[1], rtol=PAR_RTOL)
+    np.testing.assert_allclose(a[2][1], b[2][1], rtol=COST_RTOL)
+    s.free()
