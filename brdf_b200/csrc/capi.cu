@@ -144,7 +144,7 @@ extern "C" int brdfgpu_synchronize(brdfgpu_ctx* ctx) {
 // resident sample sets
 // ------------------------------------------------------------------------------------------------
 static int samples_fill(brdfgpu_ctx* ctx, brdfgpu_samples* s, const double* c, const double* t, const double* x,
-                        cudaMemcpyKind kind) {
+                        cudaMemcpyKind kind, bool wait_for_copies = true) {
     const size_t nb = sizeof(double) * (size_t)s->n;
     if (s->n == 0) return 0;
     BG_CUDA_OK(ctx, cudaMemcpyAsync(s->c, c, nb, kind, ctx->stream));
@@ -153,15 +153,16 @@ static int samples_fill(brdfgpu_ctx* ctx, brdfgpu_samples* s, const double* c, c
     else BG_CUDA_OK(ctx, cudaMemsetAsync(s->x, 0, nb, ctx->stream));  // x == NULL: zeros, lmbc_core.c:373
     if (samples_prepare(ctx, s) != 0) return BRDFGPU_LM_ERROR;
     // host buffers may be reused by the caller as soon as we return: wait for the copies (the log
-    // pass behind them is a few microseconds)
-    if (kind == cudaMemcpyHostToDevice) BG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    // pass behind them is a few microseconds) -- unless the caller is itself a synchronous entry point
+    // that queues the fit right behind them and waits for everything before IT returns
+    if (kind == cudaMemcpyHostToDevice && wait_for_copies) BG_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
 // Sample set backed by the context's reusable buffers (one user at a time; falls back to a fresh
 // allocation when busy).
 static int samples_upload_pooled(brdfgpu_ctx* ctx, long n, const double* cosphi, const double* t, const double* x,
-                                 int model, brdfgpu_samples** out) {
+                                 int model, brdfgpu_samples** out, bool wait_for_copies = true) {
     if (ctx->pooled_busy || n <= 0) return brdfgpu_samples_upload(ctx, n, cosphi, t, x, model, out);
     BG_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     if (!ctx->pooled || ctx->pooled_capacity < n) {
@@ -180,7 +181,7 @@ static int samples_upload_pooled(brdfgpu_ctx* ctx, long n, const double* cosphi,
     s->n = n;
     s->model = model;
     ctx->pooled_busy = true;
-    if (samples_fill(ctx, s, cosphi, t, x, cudaMemcpyHostToDevice) != 0) {
+    if (samples_fill(ctx, s, cosphi, t, x, cudaMemcpyHostToDevice, wait_for_copies) != 0) {
         ctx->pooled_busy = false;
         return BRDFGPU_LM_ERROR;
     }
@@ -367,11 +368,13 @@ static int levmar_entry(const char* name, brdfgpu_func_t func, brdfgpu_jacf_t ja
     if (!ctx) return BRDFGPU_LM_ERROR;
     brdfgpu_samples* s = nullptr;
     const double* t = d->angles + (d->modelInfo == 1 ? (size_t)n : 2 * (size_t)n);
-    if (samples_upload_pooled(ctx, n, d->angles, t, x, d->modelInfo, &s) != 0) return BRDFGPU_LM_ERROR;
+    // the copies, the log pass and the fit are queued back to back; the caller's buffers are released by the wait below
+    if (samples_upload_pooled(ctx, n, d->angles, t, x, d->modelInfo, &s, /*wait_for_copies=*/false) != 0) return BRDFGPU_LM_ERROR;
     int ret;
     const int jm = need_jacf ? BRDFGPU_JAC_ANALYTIC : BRDFGPU_JAC_FD;
     if (constrained) ret = brdfgpu_fit_global(ctx, s, p, m, lb, ub, dscl, itmax, opts, info, covar, BRDFGPU_DRIVE_PERSISTENT, jm);
     else ret = brdfgpu_fit_global_unc(ctx, s, p, m, itmax, opts, info, covar, jm);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) ret = BRDFGPU_LM_ERROR;  // (a fit that was refused never waited)
     brdfgpu_samples_free(ctx, s);
     return ret;
 }
