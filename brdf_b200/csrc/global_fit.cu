@@ -696,8 +696,9 @@ constexpr int kMaxPersistBlocks = 160;  // >= SM count (148 on B200)
 constexpr int kGridCostBatch = 8;       // trial points per cost_many() sweep of the sequential walk (<= NACC)
 // The lane-parallel projected-gradient walk takes up to 32 candidates per sweep when the whole shard is on chip
 // (one candidate per lane of the control warp).  levmar's futile walks try 393 step lengths: at 8 per sweep that is
-// 52 sweeps -- 44 % of all sweeps of a configs[1] fit -- each paying ~15 k cycles of exchange + control on top of its
-// arithmetic; widths 1, 2, 4, 8, 16, 32, 32 ... need 17.  Candidates past the deciding one are discarded uncounted.
+// 52 sweeps, each paying ~8 k cycles of exchange + control on top of its arithmetic.  Widths 1, 2, 4, 8, then 16 and 32
+// once the walk has consumed four times as much (GridEval::pg_walk) need 24.  Candidates past the deciding one are
+// discarded uncounted.
 constexpr int kWalkMaxBatch = 32;
 constexpr int NSUM = kWalkMaxBatch;     // sums of the widest sweep (>= NACC + 2: a Jacobian at one point + the cost at two others)
 constexpr long long kSpinCycles = 20000000000LL;  // ~10 s at 2 GHz, then the fit is abandoned (ranks may enter seconds apart on a cold box)
@@ -1289,6 +1290,7 @@ struct GridEval {
     int model, jkind;
     double delta;
     unsigned jac_passes, cost_passes, cost_points, spec_issued, spec_hits;
+    bool narrow_walk;  // BRDFGPU_SPEC_JAC & 64 (tests): at most 8 candidates per sweep, as for a streamed shard
     bool spec_on, fuse_on, width_on, memo_valid, sp_trial, sp_pg, hint_valid, ahead_valid, cand_valid, probe_known, sp_clip;
     unsigned creep_fused;
     int sp_ls;    // probe number the last line search accepted (0: it failed)
@@ -1546,10 +1548,11 @@ struct GridEval {
         const Box box{lb, ub};
         BG_TICK(6);
         // wide batches need the whole shard on chip (many_sweep_wide); a streamed shard keeps 8 per sweep
-        const int wmax = (s_ctx.stream_first < (s_ctx.v.n >> 1)) ? kGridCostBatch : kWalkMaxBatch;
-        // walks tend to repeat: start with the batch width the last walk needed (1, 2, 4 ... candidates)
+        const int wmax = (narrow_walk || s_ctx.stream_first < (s_ctx.v.n >> 1)) ? kGridCostBatch : kWalkMaxBatch;
+        // walks tend to repeat: start with the batch width the last walk needed (1, 2, 4 or 8 candidates; the wide
+        // batches are left to the walks that get that far -- started wide, a short walk evaluates candidates for nothing)
         int width = 1;
-        if (width_on) while (width < pg_last && width < wmax) width *= 2;
+        if (width_on) while (width < pg_last && width < kGridCostBatch) width *= 2;
         bool first_batch = true;
         int consumed = 0;
         while (t > tming) {
@@ -1630,7 +1633,11 @@ struct GridEval {
                 t = t_src * beta;
             }
             first_batch = false;
-            width = (2 * width < wmax) ? 2 * width : wmax;
+            // 1, 2, 4, 8, then wider only as the walk proves long: a batch never exceeds a quarter of what the walk has
+            // consumed, so a walk that ends wastes at most a quarter of its candidates (a trial point costs a third of
+            // what a sweep's exchange does at 10^6 samples) while the futile 393-candidate walk still takes 24 sweeps
+            // instead of 52
+            if (2 * width <= kGridCostBatch || (2 * width <= wmax && 8 * width <= consumed)) width *= 2;
         }
         sp_pg = false;
         pg_last = consumed;
@@ -1705,6 +1712,7 @@ __global__ void __launch_bounds__(kPersistBlockThreads, 1) k_persistent_fit(
     ev.spec_on = (spec.spec_jac & 1) != 0;
     ev.fuse_on = (spec.spec_jac & 2) != 0;
     ev.width_on = (spec.spec_jac & 4) != 0;
+    ev.narrow_walk = (spec.spec_jac & 64) != 0;
     ev.memo_valid = ev.sp_trial = ev.sp_pg = ev.hint_valid = ev.ahead_valid = ev.cand_valid = ev.probe_known = ev.sp_clip = false;
     ev.creep_fused = 0u;
     ev.sp_ls = ev.pg_last = 0;
@@ -1943,7 +1951,8 @@ int global_fit(brdfgpu_ctx* ctx, const brdfgpu_samples* s, double* p, int m, con
         // BRDFGPU_SPEC_JAC=0 switches the speculative Jacobians off (A/B tests: results must not change)
         // (a bit mask for experiments: 1 = speculate at the trial / line-search / first-candidate sites, 2 = fuse the
         // announced first candidate into the last line-search probe, 4 = start a walk at the last walk's width,
-        // 8 = self-check of the sweep kinds, 16 = scripted Jacobian + cost sweeps instead of a fit)
+        // 8 = self-check of the sweep kinds, 16 = scripted Jacobian + cost sweeps instead of a fit, 64 = walks of at most
+        // 8 candidates per sweep even when the shard is resident)
         const char* sj = getenv("BRDFGPU_SPEC_JAC");
         spec.spec_jac = sj ? atoi(sj) : 7;
         for (int i = 0; i < 3; ++i) {

@@ -416,3 +416,22 @@ def test_shard_residency_boundary(ctx, n, resident):
     np.testing.assert_allclose(a[1], b[1], rtol=PAR_RTOL)
     np.testing.assert_allclose(a[2][1], b[2][1], rtol=COST_RTOL)
     s.free()
+
+
+@pytest.mark.parametrize("n, preset", [(1_000_000, "REF_GLOBAL"), (300_001, "REF_GLOBAL"), (200_000, "REF_PERFACE")])
+def test_wide_walk_batches_change_nothing(ctx, n, preset, monkeypatch):
+    """A resident shard lets the projected-gradient walk evaluate up to 32 candidates per sweep (the futile 393-candidate
+    walk of the 10^6 case: 17 sweeps instead of 52); candidates past the deciding one are discarded uncounted, so p and
+    every entry of info[] equal the run held to 8 candidates per sweep (BRDFGPU_SPEC_JAC bit 64) bit for bit."""
+    s = ctx.synth(n, seed=synth.DEFAULT_SEED)
+    runs = {}
+    for mask in ("7", "71"):
+        monkeypatch.setenv("BRDFGPU_SPEC_JAC", mask)
+        ret, p, info = ctx.fit_global(s, getattr(A, preset))
+        st = ctx.fit_stats()
+        runs[mask] = (ret, p.tobytes(), info.tobytes(), st["jac_passes"] + st["cost_passes"], st["cost_points"])
+    assert runs["7"][:3] == runs["71"][:3]
+    assert runs["7"][3] <= runs["71"][3]          # never more sweeps ...
+    if n == 1_000_000:
+        assert runs["7"][3] < runs["71"][3]       # ... and fewer where a long walk occurs
+    s.free()
